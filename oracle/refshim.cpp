@@ -1,0 +1,296 @@
+/*
+ * refshim.cpp -- ORACLE INFRASTRUCTURE (test/baseline only, NOT product code).
+ *
+ * Drives the GENUINE reference code that is compiled into the reference's own prebuilt test binary
+ * (/root/reference/tests/trbspcs: StateValidityCheckerPCS + apc_class + collisionDetection + PQP v1.3 statically
+ * linked; non-PIE, not stripped).  The reference's collision path cannot be compiled here (PQP, OMPL and GL headers
+ * are absent), so this is how the oracle restatement is pinned against real reference outputs and how the
+ * "reference" CPU baseline is timed.
+ *
+ * Mechanism: this file is built as a shared object and LD_PRELOAD-ed into the binary.  It overrides
+ * __libc_start_main; when /proc/self/exe is the reference binary it replaces main() by a small request server:
+ * it resolves the reference functions by their mangled names from the executable's own .symtab, constructs the
+ * reference's StateValidityChecker(env) (cwd must be a directory whose ../simulator holds the .tris files) and
+ * executes one request file (env CKC_REF_REQ) into one response file (env CKC_REF_OUT).  oracle/refshim.py is the
+ * numpy front end.  Nothing of the reference is copied: the code executed is the reference's own machine code.
+ *
+ * Request : "CKCREQ1\0" | int32 op | int32 n | int32 env | int32 flags | payload
+ * Response: "CKCRSP1\0" | int32 op | int32 n | double seconds | payload
+ */
+#include <math.h>
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cstring>
+#include <dlfcn.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <elf.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include "ckc_oracle.h"
+
+typedef std::vector<double> State;
+typedef std::vector<std::vector<double> > Matrix;
+
+enum { OP_PCS_PROJECT = 1, OP_COLLIDE = 2, OP_PCS_VALIDATE = 3, OP_RBS = 4, OP_TRIDIST = 5, OP_PAIR_COUNTERS = 6,
+       OP_IDENTIFY_IK = 7, OP_MIN_DISTANCE = 8, OP_FK = 9, OP_IK = 10, OP_SPCS_SEEDED = 11 };
+
+/* ---------------- symbol resolution from the executable's .symtab ---------------- */
+static const char* g_map; static size_t g_map_len;
+static uintptr_t sym(const char* name) {
+    const Elf64_Ehdr* eh = (const Elf64_Ehdr*)g_map;
+    const Elf64_Shdr* sh = (const Elf64_Shdr*)(g_map + eh->e_shoff);
+    for (int i = 0; i < eh->e_shnum; i++) {
+        if (sh[i].sh_type != SHT_SYMTAB) continue;
+        const Elf64_Sym* st = (const Elf64_Sym*)(g_map + sh[i].sh_offset);
+        const char* str = g_map + sh[sh[i].sh_link].sh_offset;
+        const size_t n = sh[i].sh_size / sizeof(Elf64_Sym);
+        for (size_t k = 0; k < n; k++)
+            if (st[k].st_value && strcmp(str + st[k].st_name, name) == 0) return (uintptr_t)st[k].st_value;
+    }
+    fprintf(stderr, "refshim: symbol %s not found in reference binary\n", name);
+    _Exit(3);
+}
+
+/* ---------------- reference entry points (Itanium ABI: class-type by-value args are passed by address) -------- */
+typedef void (*ctor_t)(void*, int);
+typedef bool (*ikR_t)(void*, Matrix*, State*, int);
+typedef void (*getq_t)(State*, void*);
+typedef int (*coll_t)(void*, Matrix*, State*, State*);
+typedef bool (*vrbs_t)(void*, State*, State*, int, int);
+typedef bool (*rbs_t)(void*, State*, State*, State*, State*, int, int, int, int);
+typedef void (*ident_t)(State*, void*, State*, State*, State*);
+typedef double (*tridist_t)(double*, double*, const double (*)[3], const double (*)[3]);
+typedef void (*fk_t)(void*, State*, int);
+typedef void (*getT_t)(Matrix*, void*);
+typedef bool (*ik_t)(void*, Matrix*, int, int);
+typedef void (*mctor_t)(void*);
+typedef int (*mbegin_t)(void*, int);
+typedef int (*madd_t)(void*, const double*, const double*, const double*, int);
+typedef int (*mend_t)(void*);
+typedef int (*tol_t)(void*, double (*)[3], double*, void*, double (*)[3], double*, void*, double, int);
+typedef int (*dist_t)(void*, double (*)[3], double*, void*, double (*)[3], double*, void*, double, double, int);
+
+static ctor_t f_ctor; static ikR_t f_r1, f_r2; static getq_t f_getq1, f_getq2; static coll_t f_coll; static vrbs_t f_vrbs;
+static rbs_t f_rbs; static ident_t f_ident; static tridist_t f_tridist; static fk_t f_fk; static getT_t f_getT1, f_getT2; static ik_t f_ik;
+static mctor_t f_mctor; static mbegin_t f_mbegin; static madd_t f_madd; static mend_t f_mend; static tol_t f_tol; static dist_t f_dist;
+
+static void resolve_all() {
+    f_ctor = (ctor_t)sym("_ZN20StateValidityCheckerC1Ei");
+    f_r1 = (ikR_t)sym("_ZN10two_robots28calc_specific_IK_solution_R1ESt6vectorIS0_IdSaIdEESaIS2_EES2_i");
+    f_r2 = (ikR_t)sym("_ZN10two_robots28calc_specific_IK_solution_R2ESt6vectorIS0_IdSaIdEESaIS2_EES2_i");
+    f_getq1 = (getq_t)sym("_ZN10two_robots18get_IK_solution_q1Ev");
+    f_getq2 = (getq_t)sym("_ZN10two_robots18get_IK_solution_q2Ev");
+    f_coll = (coll_t)sym("_ZN18collisionDetection15collision_stateESt6vectorIS0_IdSaIdEESaIS2_EES2_S2_");
+    f_vrbs = (vrbs_t)sym("_ZN20StateValidityChecker10isValidRBSERSt6vectorIdSaIdEES3_ii");
+    f_rbs = (rbs_t)sym("_ZN20StateValidityChecker14checkMotionRBSESt6vectorIdSaIdEES2_S2_S2_iiii");
+    f_ident = (ident_t)sym("_ZN20StateValidityChecker17identify_state_ikESt6vectorIdSaIdEES2_S2_");
+    f_tridist = (tridist_t)sym("_Z7TriDistPdS_PA3_KdS2_");
+    f_fk = (fk_t)sym("_ZN10two_robots11FKsolve_robESt6vectorIdSaIdEEi");
+    f_getT1 = (getT_t)sym("_ZN10two_robots18get_FK_solution_T1Ev");
+    f_getT2 = (getT_t)sym("_ZN10two_robots18get_FK_solution_T2Ev");
+    f_ik = (ik_t)sym("_ZN10two_robots11IKsolve_robESt6vectorIS0_IdSaIdEESaIS2_EEii");
+    f_mctor = (mctor_t)sym("_ZN9PQP_ModelC1Ev");
+    f_mbegin = (mbegin_t)sym("_ZN9PQP_Model10BeginModelEi");
+    f_madd = (madd_t)sym("_ZN9PQP_Model6AddTriEPKdS1_S1_i");
+    f_mend = (mend_t)sym("_ZN9PQP_Model8EndModelEv");
+    f_tol = (tol_t)sym("_Z13PQP_ToleranceP19PQP_ToleranceResultPA3_dPdP9PQP_ModelS2_S3_S5_di");
+    f_dist = (dist_t)sym("_Z12PQP_DistanceP18PQP_DistanceResultPA3_dPdP9PQP_ModelS2_S3_S5_ddi");
+}
+
+/* PQP v1.3 result layouts (PQP.h of the external library) */
+struct PQP_ToleranceResult { int num_bv_tests; int num_tri_tests; double query_time_secs; double R[3][3]; double T[3];
+                             int closer_than_tolerance; double toler; double distance; double p1[3]; double p2[3]; int qsize; char pad[256]; };
+struct PQP_DistanceResult { int num_bv_tests; int num_tri_tests; double query_time_secs; double R[3][3]; double T[3];
+                            double rel_err; double abs_err; double distance; double p1[3]; double p2[3]; int qsize; char pad[256]; };
+
+static double now() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+static void* g_self;             /* the reference's StateValidityChecker object */
+static void* g_coll;             /* its collisionDetection sub-object (offset 0x288, from the constructor's own code) */
+static Matrix g_Q, g_P;
+static int g_env;
+
+/* own PQP models (built through the binary's PQP) for the per-pair counter / distance ops */
+static void* g_models[CKCO_NUM_MESHES];
+static ckco_world* g_world;      /* oracle world: supplies triangles (read from ../simulator) and the restated pair table */
+
+static void* new_model(const double* tris, int ntris) {
+    void* m = calloc(1, 512); f_mctor(m); f_mbegin(m, 8);
+    for (int i = 0; i < ntris; i++) f_madd(m, tris + 9 * i, tris + 9 * i + 3, tris + 9 * i + 6, i);
+    f_mend(m); return m;
+}
+static void ensure_models() {
+    if (g_world) return;
+    g_world = ckco_world_create_from_tris(g_env, "../simulator");
+    if (!g_world) { fprintf(stderr, "refshim: cannot load ../simulator/*.tris\n"); _Exit(4); }
+    for (int i = 0; i < CKCO_NUM_MESHES; i++) {
+        int nt = ckco_world_mesh_ntris(g_world, i);
+        g_models[i] = nt ? new_model(ckco_world_mesh_tris(g_world, i), nt) : NULL;
+    }
+}
+
+static bool ref_project(State& q1, State& q2, int ac, int ik) {          /* IKproject(q1,q2,ac,ik), PCS.cpp:140-162 */
+    if (!ac) { if (!f_r1(g_self, &g_Q, &q1, ik)) return false; State r; f_getq2(&r, g_self); q2 = r; return true; }
+    if (!f_r2(g_self, &g_Q, &q2, ik)) return false; State r; f_getq1(&r, g_self); q1 = r; return true;
+}
+static int ref_collide(State& q1, State& q2) { Matrix P = g_P; State a = q1, b = q2; return f_coll(g_coll, &P, &a, &b); }
+
+static long g_nodes;
+static double dd12(const State& a1, const State& a2, const State& b1, const State& b2) { double s = 0; for (int i = 0; i < 6; i++) s += pow(a1[i] - b1[i], 2) + pow(a2[i] - b2[i], 2); return sqrt(s); }
+static bool count_rbs(State qa1, State qa2, State qb1, State qb2, int ac, int ik, int depth) {     /* node counter only */
+    double d = dd12(qa1, qa2, qb1, qb2); if (d < 0.05) return true; if (depth > 150) return false;
+    State q1(6), q2(6); for (int i = 0; i < 6; i++) { q1[i] = (qa1[i] + qb1[i]) / 2; q2[i] = (qa2[i] + qb2[i]) / 2; }
+    g_nodes++; if (!f_vrbs(g_self, &q1, &q2, ac, ik)) return false;
+    return count_rbs(qa1, qa2, q1, q2, ac, ik, depth + 1) && count_rbs(q1, q2, qb1, qb2, ac, ik, depth + 1);
+}
+
+template <class T> static void put(std::vector<char>& o, const T* p, size_t n) { const char* c = (const char*)p; o.insert(o.end(), c, c + n * sizeof(T)); }
+
+static int shim_main(int, char**, char**) {
+    const char* req = getenv("CKC_REF_REQ"); const char* outp = getenv("CKC_REF_OUT");
+    if (!req || !outp) { fprintf(stderr, "refshim: CKC_REF_REQ / CKC_REF_OUT not set\n"); _Exit(2); }
+    FILE* f = fopen(req, "rb"); if (!f) { fprintf(stderr, "refshim: cannot open %s\n", req); _Exit(2); }
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<char> in(sz); if (fread(in.data(), 1, sz, f) != (size_t)sz) _Exit(2); fclose(f);
+    if (sz < 24 || memcmp(in.data(), "CKCREQ1", 8) != 0) { fprintf(stderr, "refshim: bad request\n"); _Exit(2); }
+    int32_t op, n, env, flags; memcpy(&op, &in[8], 4); memcpy(&n, &in[12], 4); memcpy(&env, &in[16], 4); memcpy(&flags, &in[20], 4);
+    const char* pay = in.data() + 24;
+    g_env = env;
+    resolve_all();
+    fflush(stdout); int so = dup(1); int dn = open("/dev/null", O_WRONLY); dup2(dn, 1);     /* silence "Robots initialized." */
+    g_self = calloc(1, 1 << 20); f_ctor(g_self, env); g_coll = (char*)g_self + 0x288;
+    fflush(stdout); dup2(so, 1);
+    const double L = env == 1 ? 300. : 500.;
+    g_Q = { {1, 0, 0, L}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1} };
+    for (int i = 0; i <= (int)(L / 20); i++) g_P.push_back({ (double)i * 20, 0, 0 });            /* setP, PCS.h:150-158 */
+
+    std::vector<char> out; double secs = 0;
+    if (op == OP_PCS_PROJECT || op == OP_PCS_VALIDATE) {
+        const double* q = (const double*)pay; const int8_t* ac = (const int8_t*)(pay + (size_t)n * 96); const int8_t* ik = ac + n;
+        std::vector<uint8_t> ok(n), valid(n); std::vector<double> qo((size_t)n * 12);
+        double t0 = now();
+        for (int i = 0; i < n; i++) {
+            State q1(q + 12 * i, q + 12 * i + 6), q2(q + 12 * i + 6, q + 12 * i + 12);
+            bool r = ref_project(q1, q2, ac[i], ik[i]); ok[i] = r; valid[i] = 0;
+            if (r && op == OP_PCS_VALIDATE) valid[i] = ref_collide(q1, q2) ? 0 : 1;
+            for (int j = 0; j < 6; j++) { qo[12 * i + j] = q1[j]; qo[12 * i + 6 + j] = q2[j]; }
+        }
+        secs = now() - t0;
+        put(out, ok.data(), n); if (op == OP_PCS_VALIDATE) put(out, valid.data(), n); put(out, qo.data(), qo.size());
+    } else if (op == OP_SPCS_SEEDED) {
+        /* timing / mask op on the counter-generated S-PCS set: payload = uint64 seed, uint64 i0 */
+        uint64_t seed, i0; memcpy(&seed, pay, 8); memcpy(&i0, pay + 8, 8);
+        std::vector<uint8_t> ok(n), valid(n);
+        double t0 = now();
+        for (int i = 0; i < n; i++) {
+            double q[12]; int ik; ckco_sample_pcs(seed, i0 + i, q, &ik);
+            State q1(q, q + 6), q2(q + 6, q + 12);
+            bool r = ref_project(q1, q2, 0, ik); ok[i] = r; valid[i] = r ? (ref_collide(q1, q2) ? 0 : 1) : 0;
+        }
+        secs = now() - t0;
+        put(out, ok.data(), n); put(out, valid.data(), n);
+    } else if (op == OP_COLLIDE) {
+        const double* q = (const double*)pay; std::vector<int32_t> r(n);
+        double t0 = now();
+        for (int i = 0; i < n; i++) { State q1(q + 12 * i, q + 12 * i + 6), q2(q + 12 * i + 6, q + 12 * i + 12); r[i] = ref_collide(q1, q2); }
+        secs = now() - t0; put(out, r.data(), n);
+    } else if (op == OP_RBS) {
+        const double* q = (const double*)pay; const int8_t* ac = (const int8_t*)(pay + (size_t)n * 192); const int8_t* ik = ac + n;
+        std::vector<uint8_t> ok(n); std::vector<int32_t> nodes(n);
+        double t0 = now();
+        for (int i = 0; i < n; i++) {
+            const double* a = q + 24 * i; const double* b = a + 12;
+            State a1(a, a + 6), a2(a + 6, a + 12), b1(b, b + 6), b2(b + 6, b + 12);
+            ok[i] = f_rbs(g_self, &a1, &a2, &b1, &b2, ac[i], ik[i], 0, 0);
+        }
+        secs = now() - t0;
+        if (flags & 1) for (int i = 0; i < n; i++) {
+            const double* a = q + 24 * i; const double* b = a + 12; g_nodes = 0;
+            count_rbs(State(a, a + 6), State(a + 6, a + 12), State(b, b + 6), State(b + 6, b + 12), ac[i], ik[i], 0); nodes[i] = (int32_t)g_nodes;
+        }
+        put(out, ok.data(), n); put(out, nodes.data(), n);
+    } else if (op == OP_TRIDIST) {
+        const double* t = (const double*)pay; std::vector<double> d(n), pq((size_t)n * 6);
+        double t0 = now();
+        for (int i = 0; i < n; i++) d[i] = f_tridist(&pq[6 * i], &pq[6 * i + 3], (const double (*)[3])(t + 18 * i), (const double (*)[3])(t + 18 * i + 9));
+        secs = now() - t0; put(out, d.data(), n); put(out, pq.data(), pq.size());
+    } else if (op == OP_PAIR_COUNTERS || op == OP_MIN_DISTANCE) {
+        /* the restated frames + pair table (oracle) issued through the binary's own PQP: per pair flag + PQP counters */
+        ensure_models();
+        const double* q = (const double*)pay; const int np = ckco_world_num_pairs(g_world); const ckco_pair* pr = ckco_world_pairs(g_world);
+        std::vector<uint8_t> flag((size_t)n * CKCO_MAX_PAIRS, 0); std::vector<int32_t> cnt((size_t)n * 2, 0); std::vector<double> dmin(n, 1e300);
+        std::vector<int32_t> ref(n);
+        double t0 = now();
+        for (int i = 0; i < n; i++) {
+            double fr[CKCO_NUM_FRAMES][12]; ckco_link_frames(g_world, q + 12 * i, fr);
+            /* the rod is rebuilt per call by the reference (collisionDetection.cpp:50-60); its triangles never change */
+            for (int p = 0; p < np; p++) {
+                double Ra[3][3], Rb[3][3], Ta[3], Tb[3];
+                memcpy(Ra, fr[pr[p].frame_a], 72); memcpy(Ta, fr[pr[p].frame_a] + 9, 24); memcpy(Rb, fr[pr[p].frame_b], 72); memcpy(Tb, fr[pr[p].frame_b] + 9, 24);
+                if (op == OP_PAIR_COUNTERS) {
+                    PQP_ToleranceResult r; memset(&r, 0, sizeof(r));
+                    f_tol(&r, Ra, Ta, g_models[pr[p].mesh_a], Rb, Tb, g_models[pr[p].mesh_b], 8.0, 2);
+                    flag[(size_t)i * CKCO_MAX_PAIRS + p] = r.closer_than_tolerance == 1; cnt[2 * i] += r.num_bv_tests; cnt[2 * i + 1] += r.num_tri_tests;
+                } else {
+                    PQP_DistanceResult r; memset(&r, 0, sizeof(r));
+                    f_dist(&r, Ra, Ta, g_models[pr[p].mesh_a], Rb, Tb, g_models[pr[p].mesh_b], 0.0, 0.0, 2);
+                    if (r.distance < dmin[i]) dmin[i] = r.distance;
+                }
+            }
+            State q1(q + 12 * i, q + 12 * i + 6), q2(q + 12 * i + 6, q + 12 * i + 12); ref[i] = ref_collide(q1, q2);
+        }
+        secs = now() - t0;
+        if (op == OP_PAIR_COUNTERS) { put(out, flag.data(), flag.size()); put(out, cnt.data(), cnt.size()); put(out, ref.data(), n); }
+        else { put(out, dmin.data(), n); put(out, ref.data(), n); }
+    } else if (op == OP_IDENTIFY_IK) {
+        const double* q = (const double*)pay; std::vector<int32_t> r((size_t)n * 2);
+        double t0 = now();
+        for (int i = 0; i < n; i++) {
+            State q1(q + 12 * i, q + 12 * i + 6), q2(q + 12 * i + 6, q + 12 * i + 12), ik0 = { -1, -1 }, res;
+            f_ident(&res, g_self, &q1, &q2, &ik0); r[2 * i] = (int32_t)res[0]; r[2 * i + 1] = (int32_t)res[1];
+        }
+        secs = now() - t0; put(out, r.data(), r.size());
+    } else if (op == OP_FK) {
+        /* payload: n*6 joints, n int8 robot (1/2) -> n*16 */
+        const double* q = (const double*)pay; const int8_t* rb = (const int8_t*)(pay + (size_t)n * 48); std::vector<double> T((size_t)n * 16);
+        double t0 = now();
+        for (int i = 0; i < n; i++) {
+            State qq(q + 6 * i, q + 6 * i + 6); f_fk(g_self, &qq, rb[i]); Matrix M; (rb[i] == 1 ? f_getT1 : f_getT2)(&M, g_self);
+            for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) T[16 * i + 4 * a + b] = M[a][b];
+        }
+        secs = now() - t0; put(out, T.data(), T.size());
+    } else if (op == OP_IK) {
+        /* payload: n*16 T, n int8 robot, n int8 sol -> n uint8 ok, n*6 q */
+        const double* T = (const double*)pay; const int8_t* rb = (const int8_t*)(pay + (size_t)n * 128); const int8_t* sol = rb + n;
+        std::vector<uint8_t> ok(n); std::vector<double> qo((size_t)n * 6, 0.0);
+        double t0 = now();
+        for (int i = 0; i < n; i++) {
+            Matrix M(4, State(4)); for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) M[a][b] = T[16 * i + 4 * a + b];
+            ok[i] = f_ik(g_self, &M, rb[i], sol[i]);
+            if (ok[i]) { State r; (rb[i] == 1 ? f_getq1 : f_getq2)(&r, g_self); for (int j = 0; j < 6; j++) qo[6 * i + j] = r[j]; }
+        }
+        secs = now() - t0; put(out, ok.data(), n); put(out, qo.data(), qo.size());
+    } else { fprintf(stderr, "refshim: unknown op %d\n", op); _Exit(2); }
+
+    FILE* o = fopen(outp, "wb"); if (!o) _Exit(2);
+    fwrite("CKCRSP1", 1, 8, o); fwrite(&op, 4, 1, o); fwrite(&n, 4, 1, o); fwrite(&secs, 8, 1, o); fwrite(out.data(), 1, out.size(), o); fclose(o);
+    _Exit(0);
+    return 0;
+}
+
+extern "C" int __libc_start_main(int (*main)(int, char**, char**), int argc, char** argv, void (*init)(void), void (*fini)(void),
+                                 void (*rtld_fini)(void), void* stack_end) {
+    typedef int (*real_t)(int (*)(int, char**, char**), int, char**, void (*)(void), void (*)(void), void (*)(void), void*);
+    real_t real = (real_t)dlsym(RTLD_NEXT, "__libc_start_main");
+    char exe[1024] = { 0 };
+    ssize_t r = readlink("/proc/self/exe", exe, sizeof(exe) - 1); (void)r;
+    const char* base = strrchr(exe, '/'); base = base ? base + 1 : exe;
+    if (strncmp(base, "trbspcs", 7) != 0 || !getenv("CKC_REF_REQ")) return real(main, argc, argv, init, fini, rtld_fini, stack_end);
+    int fd = open(exe, O_RDONLY); struct stat st; fstat(fd, &st);
+    g_map_len = st.st_size; g_map = (const char*)mmap(NULL, g_map_len, PROT_READ, MAP_PRIVATE, fd, 0);
+    return real(shim_main, argc, argv, init, fini, rtld_fini, stack_end);
+}
