@@ -1,0 +1,368 @@
+/*
+ * ckc_device.cuh -- device-side math of libckc (sm_100a): counter RNG, IRB120 kinematics in registers, link frames,
+ * the conservative FP32 box test and the FP64 triangle-pair distance.  Product code (no oracle includes).
+ *
+ * Reference behaviour each routine reproduces (paths relative to the reference root):
+ *   fk_arm            two_robots::FKsolve_rob          proj_classes/apc_class.cpp:51-76
+ *   ik_arm            two_robots::IKsolve_rob          proj_classes/apc_class.cpp:114-245
+ *   project_passive   calc_specific_IK_solution_R1/R2  proj_classes/apc_class.cpp:356-389
+ *   robot_frames      collision_state link frames      validity_checkers/collisionDetection.cpp:72-260
+ *   tri_dist          PQP v1.3 TriDist / SegPoints (external library used by collision_state)
+ */
+#ifndef CKC_DEVICE_CUH_
+#define CKC_DEVICE_CUH_
+
+#include "ckc_internal.h"
+
+#define CKC_PI_ 3.1416          /* apc_class.h:10, kdl_class.h:24 -- the reference's pi */
+
+namespace ckc {
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* counter-based generator (DESIGN.md "Synthetic inputs"): u(seed,i,k) = (mix(mix(seed) ^ (16 i + k)) >> 11) 2^-53     */
+/* ---------------------------------------------------------------------------------------------------------------- */
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ double uniform01(uint64_t key, uint64_t i, uint32_t k) {
+    return (double)(mix64(key ^ (i * 16ULL + k)) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* small rotation helpers: R is a 3x3 row-major array held in registers                                               */
+/* ---------------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void post_rot_z(double* R, double c, double s) {     /* R <- R * Rz */
+#pragma unroll
+    for (int r = 0; r < 3; r++) { const double a = R[3 * r], b = R[3 * r + 1]; R[3 * r] = a * c + b * s; R[3 * r + 1] = b * c - a * s; }
+}
+__device__ __forceinline__ void post_rot_y(double* R, double c, double s) {     /* R <- R * Ry */
+#pragma unroll
+    for (int r = 0; r < 3; r++) { const double a = R[3 * r], b = R[3 * r + 2]; R[3 * r] = a * c - b * s; R[3 * r + 2] = a * s + b * c; }
+}
+__device__ __forceinline__ void post_rot_x(double* R, double c, double s) {     /* R <- R * Rx */
+#pragma unroll
+    for (int r = 0; r < 3; r++) { const double a = R[3 * r + 1], b = R[3 * r + 2]; R[3 * r + 1] = a * c + b * s; R[3 * r + 2] = b * c - a * s; }
+}
+
+/* tool frame of one arm: T = Trans(x0,y0,0) Rz(th) Tz(b+l1) Rz(q1) Ry(q2) Tz(l2) Ry(q3) T(l3b+l4,0,l3a) Rx(q4) Ry(q5) Tx(l5+lee) Rx(q6) */
+__device__ __forceinline__ void fk_arm(const ckc_kin_dev& k, const double* q, int robot, double* R, double* p) {
+    const double bc = k.base_c[robot], bs = k.base_s[robot];
+    R[0] = bc; R[1] = -bs; R[2] = 0; R[3] = bs; R[4] = bc; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+    p[0] = k.base_x[robot]; p[1] = k.base_y[robot]; p[2] = k.b + k.l1;
+    double s, c;
+    sincos(q[0], &s, &c); post_rot_z(R, c, s);
+    sincos(q[1], &s, &c); post_rot_y(R, c, s);
+    p[0] += R[2] * k.l2; p[1] += R[5] * k.l2; p[2] += R[8] * k.l2;
+    sincos(q[2], &s, &c); post_rot_y(R, c, s);
+    const double ax = k.l3b + k.l4;
+    p[0] += R[0] * ax + R[2] * k.l3a; p[1] += R[3] * ax + R[5] * k.l3a; p[2] += R[6] * ax + R[8] * k.l3a;
+    sincos(q[3], &s, &c); post_rot_x(R, c, s);
+    sincos(q[4], &s, &c); post_rot_y(R, c, s);
+    const double le = k.l5 + k.lee;
+    p[0] += R[0] * le; p[1] += R[3] * le; p[2] += R[6] * le;
+    sincos(q[5], &s, &c); post_rot_x(R, c, s);
+}
+
+__device__ __forceinline__ double wrap_pi_(double a) {           /* apc_class.cpp:142-145 */
+    if (a > CKC_PI_) a -= 2 * CKC_PI_;
+    if (a < -CKC_PI_) a += 2 * CKC_PI_;
+    return a;
+}
+
+/* One analytic IK branch.  Rt (row-major) / pt: target pose in the world frame; returns false on the reference's
+ * early-outs (joint limit breach, unreachable). */
+__device__ __forceinline__ bool ik_arm(const ckc_kin_dev& k, const double* Rt, const double* pt, int robot, int sol, double* q) {
+    const double add1 = (sol & 4) ? CKC_PI_ : 0.0;                        /* q1_add_sol  :117 */
+    const double sg2 = (sol & 4) ? 1.0 : -1.0;                            /* q2_sign     :118 */
+    const double sg3 = (sol & 1) ? -1.0 : 1.0;                            /* q3_sign     :119 */
+    const double sg = ((0x96 >> sol) & 1) ? -1.0 : 1.0;                   /* sign456 = {1,-1,-1,1,-1,1,1,-1}  :120 */
+    const double cth = k.base_c[robot], sth = k.base_s[robot], x0 = k.base_x[robot], y0 = k.base_y[robot];
+    double R[9], p[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {                                         /* :128-130 */
+        R[j] = cth * Rt[j] + sth * Rt[3 + j];
+        R[3 + j] = cth * Rt[3 + j] - sth * Rt[j];
+        R[6 + j] = Rt[6 + j];
+    }
+    p[0] = cth * pt[0] + sth * pt[1] - cth * x0 - sth * y0;              /* :132-134 */
+    p[1] = cth * pt[1] - sth * pt[0] - cth * y0 + sth * x0;
+    p[2] = pt[2];
+    const double le = k.l5 + k.lee;
+    const double p5x = p[0] - R[0] * le, p5y = p[1] - R[3] * le, p5z = p[2] - R[6] * le;     /* :137 */
+
+    q[0] = wrap_pi_(atan2(p5y, p5x) + add1);                              /* :141-148 */
+    if (fabs(q[0]) > k.lim_hi[0]) return false;
+
+    const double k2 = p5x * p5x + p5y * p5y;
+    const double zz = p5z - (k.l1 + k.b);
+    const double D2 = k2 + zz * zz;
+    const double cosphi = (D2 - k.l2 * k.l2 - k.l34 * k.l34) / (2 * k.l2 * k.l34);   /* :160 */
+    double sinphi = 1 - cosphi * cosphi;
+    if (sinphi < 0) return false;                                         /* :164 */
+    sinphi = sg3 * sqrt(sinphi);
+    q[2] = wrap_pi_(-(atan2(sinphi, cosphi) + k.alpha));                  /* :168-172 */
+    if (q[2] < k.lim_lo[2] || q[2] > k.lim_hi[2]) return false;
+
+    const double sa1 = -k.l34 * sinphi / sqrt(D2);                        /* :180 */
+    const double alpha1 = atan2(-sg2 * sa1, sqrt(1 - sa1 * sa1));
+    const double alpha2 = atan2(p5z - k.l1 - k.b, sqrt(k2));
+    q[1] = wrap_pi_(sg2 * (alpha1 + alpha2 - CKC_PI_ / 2));               /* :182-186 */
+    if (fabs(q[1]) > k.lim_hi[1]) return false;
+
+    double s23, c23, s1, c1;
+    sincos(q[1] + q[2], &s23, &c23);
+    sincos(q[0], &s1, &c1);
+    const double S = R[0] * c23 * c1 - R[6] * s23 + R[3] * c23 * s1;      /* :206 */
+    q[4] = atan2(sg * sqrt(1 - S * S), S);
+    q[4] = fabs(q[4]) < 1e-4 ? 0 : q[4];
+    if (fabs(q[4]) > k.lim_hi[4]) return false;
+    if (q[4] != 0) {                                                      /* :215-225 */
+        const double sinq4 = R[3] * c1 - R[0] * s1;
+        const double cosq4 = R[6] * c23 + R[0] * s23 * c1 + R[3] * s23 * s1;
+        q[3] = atan2(sg * sinq4, -sg * cosq4);
+        const double sinq6 = R[1] * c23 * c1 - R[7] * s23 + R[4] * c23 * s1;
+        const double cosq6 = R[2] * c23 * c1 - R[8] * s23 + R[5] * c23 * s1;
+        q[5] = atan2(sg * sinq6, sg * cosq6);
+    } else {                                                              /* :226-231 */
+        q[3] = 0;
+        q[5] = atan2(R[7], R[8]);
+    }
+    if (fabs(q[3]) > k.lim_hi[3] || fabs(q[5]) > k.lim_hi[5]) return false;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        if (fabs(q[i]) < 1e-5) q[i] = 0;                                  /* :236-238 */
+    return true;
+}
+
+/* closure: the passive arm must hold the other end of the rod: T_passive = T_active * Trans(+-L) * diag(-1,-1,1,1)
+ * (apc_class.cpp:360-362 and :381-383; both reduce to: columns 0,1 negated, origin moved by +L along tool x) */
+__device__ __forceinline__ bool project_passive(const ckc_kin_dev& k, const double* q_active, int active_robot, int sol, double* q_passive) {
+    double R[9], p[3];
+    fk_arm(k, q_active, active_robot, R, p);
+    double Rt[9], pt[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        Rt[3 * r] = -R[3 * r]; Rt[3 * r + 1] = -R[3 * r + 1]; Rt[3 * r + 2] = R[3 * r + 2];
+        pt[r] = R[3 * r] * k.L + p[r];
+    }
+    return ik_arm(k, Rt, pt, 1 - active_robot, sol, q_passive);
+}
+
+__device__ __forceinline__ bool within_limits(const ckc_kin_dev& k, const double* q) {       /* apc_class.cpp:304-334 */
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const double* a = q + 6 * r;
+        ok = ok && !(fabs(a[0]) > k.lim_hi[0]) && !(fabs(a[1]) > k.lim_hi[1]) && !(a[2] < k.lim_lo[2] || a[2] > k.lim_hi[2]) &&
+             !(fabs(a[3]) > k.lim_hi[3]) && !(fabs(a[4]) > k.lim_hi[4]) && !(fabs(a[5]) > k.lim_hi[5]);
+    }
+    return ok;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* link frames of one robot for the collision meshes (collisionDetection.cpp:72-166 / :177-260).                      */
+/* out: 8 frames x 12 doubles: (R row-major, T) for base, link1..link6 and the EE/rod pose (R6, T7)                   */
+/* ---------------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void store_frame(double* dst, const double* R, const double* T) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) dst[i] = R[i];
+    dst[9] = T[0]; dst[10] = T[1]; dst[11] = T[2];
+}
+__device__ __forceinline__ void robot_frames(const double* R0, const double* T0, const double* q, double* out) {
+    double R[9], T[3], s, c;
+#pragma unroll
+    for (int i = 0; i < 9; i++) R[i] = R0[i];
+    T[0] = T0[0]; T[1] = T0[1]; T[2] = T0[2];
+    store_frame(out, R, T);                                               /* base */
+    T[0] += R[2] * 290.0; T[1] += R[5] * 290.0; T[2] += R[8] * 290.0;     /* T1 = T0 + R0 (0,0,145*2) */
+    sincos(q[0], &s, &c); post_rot_z(R, c, s);
+    store_frame(out + 12, R, T);                                          /* link1 (R1,T1) */
+    sincos(q[1], &s, &c); post_rot_y(R, c, s);
+    store_frame(out + 24, R, T);                                          /* link2 (R2,T2_t), T2 = T1 */
+    T[0] += R[2] * 270.0; T[1] += R[5] * 270.0; T[2] += R[8] * 270.0;     /* T3 = T2 + R2 (0,0,270) */
+    sincos(q[2], &s, &c); post_rot_y(R, c, s);
+    store_frame(out + 36, R, T);                                          /* link3 (R3,T3) */
+    T[0] += R[0] * 134.0 + R[2] * 70.0; T[1] += R[3] * 134.0 + R[5] * 70.0; T[2] += R[6] * 134.0 + R[8] * 70.0;   /* T4 */
+    sincos(q[3], &s, &c); post_rot_x(R, c, s);
+    store_frame(out + 48, R, T);                                          /* link4 (R4,T4) */
+    T[0] += R[0] * 168.0; T[1] += R[3] * 168.0; T[2] += R[6] * 168.0;     /* T5 */
+    sincos(q[4], &s, &c); post_rot_y(R, c, s);
+    store_frame(out + 60, R, T);                                          /* link5 (R5,T5) */
+    T[0] += R[0] * 66.0; T[1] += R[3] * 66.0; T[2] += R[6] * 66.0;        /* T6: 72 - 13/2 = 66 (integer division) */
+    sincos(q[5], &s, &c); post_rot_x(R, c, s);
+    store_frame(out + 72, R, T);                                          /* link6 (R6,T6) */
+    T[0] += R[0] * 66.0; T[1] += R[3] * 66.0; T[2] += R[6] * 66.0;        /* T7: 13/2 + 60 = 66 */
+    store_frame(out + 84, R, T);                                          /* EE and rod pose (R6,T7) */
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* conservative FP32 box-box test: true => the two boxes are farther apart than `tol` (tol already includes the       */
+/* guard band).  Fa/Fb = world frames (R row-major 9 + T 3) of the meshes the boxes belong to.                        */
+/* ---------------------------------------------------------------------------------------------------------------- */
+struct box32 { float c[3], h[3], a0[3], a1[3]; float size2; int child; };
+
+__device__ __forceinline__ box32 load_box(const ckc_node* n) {
+    const float4* p = reinterpret_cast<const float4*>(n);
+    const float4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
+    box32 b;
+    b.c[0] = v0.x; b.c[1] = v0.y; b.c[2] = v0.z; b.size2 = v0.w;
+    b.h[0] = v1.x; b.h[1] = v1.y; b.h[2] = v1.z; b.child = __float_as_int(v1.w);
+    b.a0[0] = v2.x; b.a0[1] = v2.y; b.a0[2] = v2.z;
+    b.a1[0] = v3.x; b.a1[1] = v3.y; b.a1[2] = v3.z;
+    return b;
+}
+
+__device__ __forceinline__ void box_to_world(const box32& b, const float* F, float* c, float (*ax)[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        c[r] = F[3 * r] * b.c[0] + F[3 * r + 1] * b.c[1] + F[3 * r + 2] * b.c[2] + F[9 + r];
+        ax[0][r] = F[3 * r] * b.a0[0] + F[3 * r + 1] * b.a0[1] + F[3 * r + 2] * b.a0[2];
+        ax[1][r] = F[3 * r] * b.a1[0] + F[3 * r + 1] * b.a1[1] + F[3 * r + 2] * b.a1[2];
+    }
+    ax[2][0] = ax[0][1] * ax[1][2] - ax[0][2] * ax[1][1];
+    ax[2][1] = ax[0][2] * ax[1][0] - ax[0][0] * ax[1][2];
+    ax[2][2] = ax[0][0] * ax[1][1] - ax[0][1] * ax[1][0];
+}
+
+__device__ __forceinline__ bool boxes_farther_than(const box32& A, const float* Fa, const box32& B, const float* Fb, float tol) {
+    float ca[3], cb[3], ua[3][3], ub[3][3];
+    box_to_world(A, Fa, ca, ua);
+    box_to_world(B, Fb, cb, ub);
+    const float d[3] = { cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2] };
+    float t[3], R[3][3], AR[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        t[i] = d[0] * ua[i][0] + d[1] * ua[i][1] + d[2] * ua[i][2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            R[i][j] = ua[i][0] * ub[j][0] + ua[i][1] * ub[j][1] + ua[i][2] * ub[j][2];
+            AR[i][j] = fabsf(R[i][j]) + 1e-5f;        /* keeps the test conservative under FP32 rounding */
+        }
+    }
+    bool far = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        far = far || (fabsf(t[i]) - (A.h[i] + B.h[0] * AR[i][0] + B.h[1] * AR[i][1] + B.h[2] * AR[i][2]) > tol);
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+        far = far || (fabsf(t[0] * R[0][j] + t[1] * R[1][j] + t[2] * R[2][j]) - (B.h[j] + A.h[0] * AR[0][j] + A.h[1] * AR[1][j] + A.h[2] * AR[2][j]) > tol);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            const float len2 = 1.0f - R[i][j] * R[i][j];             /* |a_i x b_j|^2 */
+            const float g = fabsf(t[i2] * R[i1][j] - t[i1] * R[i2][j]) - (A.h[i1] * AR[i2][j] + A.h[i2] * AR[i1][j]) -
+                            (B.h[j1] * AR[i][j2] + B.h[j2] * AR[i][j1]);
+            far = far || (len2 > 1e-3f && g > 0.0f && g * g > tol * tol * len2);
+        }
+    }
+    return far;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* FP64 triangle-pair distance with PQP v1.3 TriDist / SegPoints semantics (the value PQP_Tolerance compares to 8 mm)  */
+/* ---------------------------------------------------------------------------------------------------------------- */
+struct v3 { double x, y, z; };
+__device__ __forceinline__ v3 operator-(const v3& a, const v3& b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+__device__ __forceinline__ v3 operator+(const v3& a, const v3& b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+__device__ __forceinline__ v3 madd(const v3& a, const v3& b, double s) { return { a.x + b.x * s, a.y + b.y * s, a.z + b.z * s }; }
+__device__ __forceinline__ double dot(const v3& a, const v3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ v3 cross(const v3& a, const v3& b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+
+/* closest points X (on P + tA) and Y (on Q + uB), t,u in [0,1]; VEC: separating direction that survives X == Y */
+__device__ __noinline__ void seg_points(v3& VEC, v3& X, v3& Y, const v3& P, const v3& A, const v3& Q, const v3& B) {
+    v3 T = Q - P;
+    const double AA = dot(A, A), BB = dot(B, B), AB = dot(A, B), AT = dot(A, T), BT = dot(B, T);
+    const double denom = AA * BB - AB * AB;
+    double t = (AT * BB - BT * AB) / denom;
+    if ((t < 0) || isnan(t)) t = 0; else if (t > 1) t = 1;
+    const double u = (t * AB - BT) / BB;
+    if ((u <= 0) || isnan(u)) {
+        Y = Q;
+        t = AT / AA;
+        if ((t <= 0) || isnan(t)) { X = P; VEC = Q - P; }
+        else if (t >= 1) { X = P + A; VEC = Q - X; }
+        else { X = madd(P, A, t); VEC = cross(A, cross(T, A)); }
+    } else if (u >= 1) {
+        Y = Q + B;
+        t = (AB + AT) / AA;
+        if ((t <= 0) || isnan(t)) { X = P; VEC = Y - P; }
+        else if (t >= 1) { X = P + A; VEC = Y - X; }
+        else { X = madd(P, A, t); T = Y - P; VEC = cross(A, cross(T, A)); }
+    } else {
+        Y = madd(Q, B, u);
+        if ((t <= 0) || isnan(t)) { X = P; VEC = cross(B, cross(T, B)); }
+        else if (t >= 1) { X = P + A; T = Q - X; VEC = cross(B, cross(T, B)); }
+        else {
+            X = madd(P, A, t);
+            VEC = cross(A, B);
+            if (dot(VEC, T) < 0) { VEC.x = -VEC.x; VEC.y = -VEC.y; VEC.z = -VEC.z; }
+        }
+    }
+}
+
+/* vertex-vs-face case of TriDist: the vertices V[] of one triangle against the plane of the other (F0.., edges E[], normal N) */
+__device__ __forceinline__ bool face_case(const v3* F, const v3* E, const v3* V, bool& shown_disjoint, double& out_d) {
+    const v3 N = cross(E[0], E[1]);
+    const double Nl = dot(N, N);
+    if (!(Nl > 1e-15)) return false;
+    double pr[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pr[k] = dot(F[0] - V[k], N);
+    int point = -1;
+    if ((pr[0] > 0) && (pr[1] > 0) && (pr[2] > 0)) { point = (pr[0] < pr[1]) ? 0 : 1; if (pr[2] < pr[point]) point = 2; }
+    else if ((pr[0] < 0) && (pr[1] < 0) && (pr[2] < 0)) { point = (pr[0] > pr[1]) ? 0 : 1; if (pr[2] > pr[point]) point = 2; }
+    if (point < 0) return false;
+    shown_disjoint = true;
+    const v3 Vp = point == 0 ? V[0] : (point == 1 ? V[1] : V[2]);
+    const double prp = point == 0 ? pr[0] : (point == 1 ? pr[1] : pr[2]);
+    if (dot(Vp - F[0], cross(N, E[0])) > 0 && dot(Vp - F[1], cross(N, E[1])) > 0 && dot(Vp - F[2], cross(N, E[2])) > 0) {
+        const v3 Pf = madd(Vp, N, prp / Nl);          /* foot of the perpendicular on the face */
+        const v3 dd = Pf - Vp;
+        out_d = sqrt(dot(dd, dd));
+        return true;
+    }
+    return false;
+}
+
+__device__ __noinline__ double tri_dist(const v3* S, const v3* T) {
+    v3 Sv[3], Tv[3];
+    Sv[0] = S[1] - S[0]; Sv[1] = S[2] - S[1]; Sv[2] = S[0] - S[2];
+    Tv[0] = T[1] - T[0]; Tv[1] = T[2] - T[1]; Tv[2] = T[0] - T[2];
+    bool shown_disjoint = false;
+    double mindd;
+    { const v3 d0 = S[0] - T[0]; mindd = dot(d0, d0) + 1; }
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) {
+#pragma unroll 1
+        for (int j = 0; j < 3; j++) {
+            v3 VEC, P, Q;
+            seg_points(VEC, P, Q, S[i], Sv[i], T[j], Tv[j]);
+            const v3 V = Q - P;
+            const double dd = dot(V, V);
+            if (dd <= mindd) {
+                mindd = dd;
+                const int i2 = (i + 2) % 3, j2 = (j + 2) % 3;
+                double a = dot(S[i2] - P, VEC);
+                double b = dot(T[j2] - Q, VEC);
+                if ((a <= 0) && (b >= 0)) return sqrt(dd);
+                const double p = dot(V, VEC);
+                if (a < 0) a = 0;
+                if (b > 0) b = 0;
+                if ((p - a + b) > 0) shown_disjoint = true;
+            }
+        }
+    }
+    double d;
+    if (face_case(S, Sv, T, shown_disjoint, d)) return d;      /* a vertex of T above the interior of S */
+    if (face_case(T, Tv, S, shown_disjoint, d)) return d;      /* a vertex of S above the interior of T */
+    return shown_disjoint ? sqrt(mindd) : 0.0;
+}
+
+}  // namespace ckc
+#endif

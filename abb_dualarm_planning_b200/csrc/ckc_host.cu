@@ -1,0 +1,606 @@
+/*
+ * ckc_host.cu -- host side of libckc: context, mesh loading (.tris directory or packed .ckcmesh), OBB hierarchy
+ * construction, device upload, batching/chunking and the extern "C" entry points of include/ckc.h.
+ * Product code (no oracle includes).  There is deliberately no CPU compute path: every entry point runs the kernels
+ * of ckc_kernels.cu or fails.
+ */
+#include "../../include/ckc.h"
+#include "ckc_internal.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#define CKC_VERSION_STR "ckc-b200 0.1 (sm_100a)"
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+struct host_mesh {
+    std::vector<double> tris;        /* ntris * 9 */
+    std::vector<ckc_node> nodes;
+    int ntris() const { return (int)(tris.size() / 9); }
+};
+
+struct dev_buf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct ckc_ctx {
+    int env = 1, device = 0, num_sms = 148;
+    std::string err;
+    ckc_kin_dev kin;
+    ckc_world_dev world;
+    host_mesh meshes[CKC_NUM_MESHES];
+    cudaStream_t stream = nullptr;
+    int64_t chunk = 1 << 20;            /* samples per internal batch */
+    /* persistent device storage */
+    dev_buf d_nodes, d_tris, d_ctr, d_small;           /* d_small: list_count, work counters, overflow count */
+    /* per-chunk work buffers */
+    dev_buf d_qin, d_qout, d_ac, d_ik, d_ok, d_valid, d_list, d_frames, d_ovf, d_bigstack, d_flags, d_aux, d_aux2;
+    dev_buf d_qb, d_edge;               /* RBS */
+    int64_t launches = 0;
+    ckc_stats host_stats;
+};
+
+static int fail(ckc_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, CKC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* mesh input                                                                                                         */
+/* ---------------------------------------------------------------------------------------------------------------- */
+static const char* const k_mesh_file[CKC_NUM_MESHES] = {   /* the files collisionDetection::load_models opens (:502-923) */
+    "Base_r.tris", "Link1_r.tris", "Link2_r.tris", "Link3_r.tris", "Link4_r2.tris", "Link5_r.tris", "Link6.tris",
+    "EE_r.tris", "table.tris", "obs.tris", "cone.tris", nullptr };
+
+static bool read_tris_file(const std::string& path, std::vector<double>& out) {
+    FILE* fp = fopen(path.c_str(), "r");
+    if (!fp) return false;
+    int n = 0;
+    bool ok = fscanf(fp, "%d", &n) == 1 && n >= 0;
+    if (ok) {
+        out.resize((size_t)n * 9);
+        for (size_t i = 0; ok && i < out.size(); i++) ok = fscanf(fp, "%lf", &out[i]) == 1;
+    }
+    fclose(fp);
+    return ok;
+}
+
+static bool read_pack(const std::string& path, host_mesh* meshes) {
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    char magic[8]; int32_t nm = 0;
+    bool ok = fread(magic, 1, 8, fp) == 8 && memcmp(magic, "CKCMESH1", 8) == 0 && fread(&nm, 4, 1, fp) == 1;
+    for (int m = 0; ok && m < nm; m++) {
+        int32_t id = -1, nt = 0;
+        ok = fread(&id, 4, 1, fp) == 1 && fread(&nt, 4, 1, fp) == 1 && id >= 0 && id < CKC_NUM_MESHES && nt >= 0;
+        if (!ok) break;
+        meshes[id].tris.resize((size_t)nt * 9);
+        ok = fread(meshes[id].tris.data(), 8, (size_t)nt * 9, fp) == (size_t)nt * 9;
+    }
+    fclose(fp);
+    return ok;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* OBB hierarchy: top-down, PCA-oriented boxes, median split along the longest box axis, one triangle per leaf.        */
+/* Any conservative hierarchy yields the reference's boolean (PQP's own RSS tree only prunes).                        */
+/* ---------------------------------------------------------------------------------------------------------------- */
+static void sym_eig3(double A[3][3], double V[3][3]) {
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[i][j] = i == j;
+    for (int sweep = 0; sweep < 64; sweep++) {
+        const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+        if (off < 1e-28) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (fabs(A[p][q]) < 1e-300) continue;
+                const double th = (A[q][q] - A[p][p]) / (2 * A[p][q]);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1));
+                const double c = 1 / sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < 3; k++) { const double x = A[k][p], y = A[k][q]; A[k][p] = c * x - s * y; A[k][q] = s * x + c * y; }
+                for (int k = 0; k < 3; k++) { const double x = A[p][k], y = A[q][k]; A[p][k] = c * x - s * y; A[q][k] = s * x + c * y; }
+                for (int k = 0; k < 3; k++) { const double x = V[k][p], y = V[k][q]; V[k][p] = c * x - s * y; V[k][q] = s * x + c * y; }
+            }
+    }
+}
+
+struct builder {
+    host_mesh& m;
+    explicit builder(host_mesh& mm) : m(mm) {}
+    const double* vert(int t, int v) const { return &m.tris[9 * (size_t)t + 3 * v]; }
+
+    void fit(const std::vector<int>& idx, ckc_node& n, double axes[3][3]) {
+        double mean[3] = { 0, 0, 0 };
+        for (int t : idx) for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) mean[k] += vert(t, v)[k];
+        for (int k = 0; k < 3; k++) mean[k] /= 3.0 * idx.size();
+        double C[3][3] = { { 0 } };
+        for (int t : idx) for (int v = 0; v < 3; v++) {
+            double d[3]; for (int k = 0; k < 3; k++) d[k] = vert(t, v)[k] - mean[k];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C[i][j] += d[i] * d[j];
+        }
+        double V[3][3]; sym_eig3(C, V);
+        /* order the eigenvectors by decreasing eigenvalue, Gram-Schmidt, right-handed */
+        int ord[3] = { 0, 1, 2 };
+        std::sort(ord, ord + 3, [&](int a, int b) { return C[a][a] > C[b][b]; });
+        double a0[3] = { V[0][ord[0]], V[1][ord[0]], V[2][ord[0]] }, a1[3] = { V[0][ord[1]], V[1][ord[1]], V[2][ord[1]] }, a2[3];
+        auto nrm = [](double* a) { double l = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); if (l > 0) { a[0] /= l; a[1] /= l; a[2] /= l; } return l; };
+        if (nrm(a0) < 1e-12) { a0[0] = 1; a0[1] = 0; a0[2] = 0; }
+        double d = a0[0] * a1[0] + a0[1] * a1[1] + a0[2] * a1[2];
+        for (int k = 0; k < 3; k++) a1[k] -= d * a0[k];
+        if (nrm(a1) < 1e-9) {
+            double e[3] = { fabs(a0[0]) < 0.9 ? 1.0 : 0.0, fabs(a0[0]) < 0.9 ? 0.0 : 1.0, 0 };
+            a1[0] = a0[1] * e[2] - a0[2] * e[1]; a1[1] = a0[2] * e[0] - a0[0] * e[2]; a1[2] = a0[0] * e[1] - a0[1] * e[0];
+            nrm(a1);
+        }
+        /* the kernel rebuilds a2 = a0 x a1 from the FP32 copies: round first so that host extents match what it sees */
+        float f0[3], f1[3];
+        for (int k = 0; k < 3; k++) { f0[k] = (float)a0[k]; f1[k] = (float)a1[k]; a0[k] = f0[k]; a1[k] = f1[k]; }
+        a2[0] = a0[1] * a1[2] - a0[2] * a1[1]; a2[1] = a0[2] * a1[0] - a0[0] * a1[2]; a2[2] = a0[0] * a1[1] - a0[1] * a1[0];
+        const double* ax[3] = { a0, a1, a2 };
+        double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+        for (int t : idx) for (int v = 0; v < 3; v++)
+            for (int i = 0; i < 3; i++) {
+                const double* p = vert(t, v);
+                const double pr = p[0] * ax[i][0] + p[1] * ax[i][1] + p[2] * ax[i][2];
+                lo[i] = std::min(lo[i], pr); hi[i] = std::max(hi[i], pr);
+            }
+        /* the FP32 axes are not exactly orthonormal (1e-7): pad the extents by a relative + absolute slack so that the
+         * box still contains every vertex when evaluated in FP32 */
+        double cworld[3] = { 0, 0, 0 };
+        for (int i = 0; i < 3; i++) {
+            const double mid = 0.5 * (lo[i] + hi[i]);
+            for (int k = 0; k < 3; k++) cworld[k] += mid * ax[i][k];
+        }
+        double ext = 0;
+        for (int i = 0; i < 3; i++) ext = std::max(ext, 0.5 * (hi[i] - lo[i]));
+        double cmag = std::max(std::max(fabs(cworld[0]), fabs(cworld[1])), fabs(cworld[2]));
+        const double slack = 1e-3 + 4e-6 * (ext + cmag);
+        for (int i = 0; i < 3; i++) { n.h[i] = (float)(0.5 * (hi[i] - lo[i]) + slack); n.c[i] = (float)cworld[i]; }
+        for (int k = 0; k < 3; k++) { n.a0[k] = f0[k]; n.a1[k] = f1[k]; }
+        n.size2 = n.h[0] * n.h[0] + n.h[1] * n.h[1] + n.h[2] * n.h[2];
+        n.pad0 = n.pad1 = 0;
+        for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) axes[i][k] = ax[i][k];
+    }
+
+    void build(std::vector<int>& idx, int self) {
+        double axes[3][3];
+        ckc_node n; memset(&n, 0, sizeof(n));
+        fit(idx, n, axes);
+        if (idx.size() == 1) { n.child = ~idx[0]; m.nodes[self] = n; return; }
+        int axis = 0; if (n.h[1] > n.h[axis]) axis = 1; if (n.h[2] > n.h[axis]) axis = 2;
+        const double* a = axes[axis];
+        std::vector<std::pair<double, int>> key(idx.size());
+        for (size_t i = 0; i < idx.size(); i++) {
+            double c = 0;
+            for (int v = 0; v < 3; v++) { const double* p = vert(idx[i], v); c += p[0] * a[0] + p[1] * a[1] + p[2] * a[2]; }
+            key[i] = { c, idx[i] };
+        }
+        std::sort(key.begin(), key.end());
+        const size_t half = idx.size() / 2;
+        std::vector<int> L, R;
+        for (size_t i = 0; i < key.size(); i++) (i < half ? L : R).push_back(key[i].second);
+        const int child = (int)m.nodes.size();
+        m.nodes.resize(m.nodes.size() + 2);          /* siblings are adjacent: right = left + 1 */
+        n.child = child;
+        m.nodes[self] = n;
+        build(L, child);
+        build(R, child + 1);
+    }
+};
+
+static void build_hierarchy(host_mesh& m) {
+    m.nodes.clear();
+    if (m.ntris() == 0) return;
+    std::vector<int> idx(m.ntris());
+    for (int i = 0; i < m.ntris(); i++) idx[i] = i;
+    m.nodes.resize(1);
+    builder b(m);
+    b.build(idx, 0);
+}
+
+/* the rod: setP() (StateValidityCheckerPCS.h:150-158) + collision_state :50-60 -- points (20 i, 0, 0), i = 0..L/20, taken
+ * three at a time as (degenerate) triangles */
+static void make_rod(host_mesh& m, double L) {
+    const int dl = 20, n = (int)(L / dl);
+    const int ntri = (n + 1) / 3;
+    m.tris.clear();
+    for (int t = 0; t < ntri; t++)
+        for (int v = 0; v < 3; v++) { m.tris.push_back((double)((3 * t + v) * dl)); m.tris.push_back(0); m.tris.push_back(0); }
+}
+
+/* pair table of collision_state (collisionDetection.cpp:267-355, env 1 :372-420, env 2 :443-472) */
+static void build_pair_table(ckc_world_dev& w, int env) {
+    const uint8_t lm[8] = { CKC_M_BASE, CKC_M_LINK1, CKC_M_LINK2, CKC_M_LINK3, CKC_M_LINK4, CKC_M_LINK5, CKC_M_LINK6, CKC_M_EE };
+    int n = 0;
+    auto add = [&](int ma, int fa, int mb, int fb) { w.pairs[n].mesh_a = (uint8_t)ma; w.pairs[n].frame_a = (uint8_t)fa; w.pairs[n].mesh_b = (uint8_t)mb; w.pairs[n].frame_b = (uint8_t)fb; n++; };
+    for (int r = 0; r < 2; r++) {                       /* self collision of each arm */
+        const int o = 8 * r;
+        for (int b = 4; b <= 6; b++) for (int a = 0; a <= 2; a++) add(lm[a], o + a, lm[b], o + b);
+        add(CKC_M_BASE, o, CKC_M_LINK3, o + 3);
+        for (int a = 0; a <= 2; a++) add(lm[a], o + a, CKC_M_EE, o + 7);
+    }
+    for (int a = 3; a <= 6; a++) for (int b = 3; b <= 6; b++) add(lm[a], a, lm[b], 8 + b);     /* arm-arm */
+    for (int a = 3; a <= 6; a++) add(lm[a], a, CKC_M_EE, 15);
+    for (int b = 3; b <= 6; b++) add(CKC_M_EE, 7, lm[b], 8 + b);
+    for (int r = 0; r < 2; r++) for (int b = 0; b <= 6; b++) add(CKC_M_ROD, 7, lm[b], 8 * r + b);   /* rod-arm */
+    for (int r = 0; r < 2; r++) for (int b = 2; b <= 7; b++) add(CKC_M_TABLE, 0, lm[b], 8 * r + b); /* table-arm */
+    add(CKC_M_TABLE, 0, CKC_M_ROD, 7);
+    const int nobs = env == 1 ? 3 : 2, om = env == 1 ? CKC_M_OBS : CKC_M_CONE;
+    for (int k = 0; k < nobs; k++) {
+        const int fo = 18 + k;
+        add(om, fo, CKC_M_ROD, 7);
+        add(om, fo, CKC_M_LINK2, k == 0 ? 16 : 2);       /* res[78] poses link2 with (R22, T2_t) */
+        for (int b = 3; b <= 7; b++) add(om, fo, lm[b], b);
+        add(om, fo, CKC_M_LINK2, k == 0 ? 10 : 17);      /* res[97], res[110] pose link22 with (R2, T2_t2) */
+        for (int b = 3; b <= 7; b++) add(om, fo, lm[b], 8 + b);
+    }
+    w.npairs = n;
+}
+
+static void rotz(double M[9], double t) { const double c = cos(t), s = sin(t); M[0] = c; M[1] = -s; M[2] = 0; M[3] = s; M[4] = c; M[5] = 0; M[6] = 0; M[7] = 0; M[8] = 1; }
+static void mul33(double C[9], const double A[9], const double B[9]) {
+    double R[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j]);
+    memcpy(C, R, sizeof(R));
+}
+
+static void init_constants(ckc_ctx* c) {
+    ckc_kin_dev& k = c->kin;
+    const int env = c->env;
+    k.b = 166; k.l1 = 124; k.l2 = 270; k.l3a = 70; k.l3b = 149.6; k.l4 = 152.4;
+    k.l5 = 72 - 13. / 2; k.lee = 60 + 13. / 2;                                    /* apc_class.cpp:11-12 */
+    k.D = env == 1 ? 900. : 1200.; k.L = env == 1 ? 300. : 500.;                 /* StateValidityCheckerPCS.h:23-26 */
+    const double deg[6][2] = { { -165, 165 }, { -110, 110 }, { -110, 70 }, { -160, 160 }, { -120, 120 }, { -400, 400 } };
+    for (int j = 0; j < 6; j++) { k.lim_lo[j] = deg[j][0] * 3.1416 / 180.0; k.lim_hi[j] = deg[j][1] * 3.1416 / 180.0; }   /* deg2rad uses PI_ */
+    k.base_x[0] = -k.D / 2; k.base_y[0] = 0; k.base_c[0] = cos(0.0); k.base_s[0] = sin(0.0);
+    k.base_x[1] = k.D / 2; k.base_y[1] = 0; k.base_c[1] = cos(3.1416); k.base_s[1] = sin(3.1416);                       /* PCS.h:37 */
+    k.l34 = sqrt((k.l3a * k.l3a + (k.l3b + k.l4) * (k.l3b + k.l4)));
+    k.alpha = atan2(k.l3b + k.l4, k.l3a);
+    /* KDL chain (kdl_class.cpp:11-12,32-45): integer-division link lengths */
+    const double kl5 = 72 - 13 / 2, klee = 60 + 13 / 2;
+    const double tips[13][3] = { { 0, 0, k.b }, { 0, 0, k.l1 }, { 0, 0, k.l2 }, { k.l3b, 0, k.l3a }, { k.l4, 0, 0 }, { kl5, 0, 0 }, { 2 * klee + k.L, 0, 0 },
+                                 { kl5, 0, 0 }, { k.l4, 0, 0 }, { k.l3b, 0, -k.l3a }, { 0, 0, -k.l2 }, { 0, 0, -k.l1 }, { 0, 0, -k.b } };
+    const int axes[13] = { -1, 2, 1, 1, 0, 1, 0, 0, 1, 0, 1, 1, 2 };
+    memcpy(k.kdl_tip, tips, sizeof(tips)); memcpy(k.kdl_axis, axes, sizeof(axes));
+
+    ckc_world_dev& w = c->world;
+    w.env = env; w.D = k.D; w.tol = 8.0; w.cull_tol = 8.0f + 0.05f;
+    /* robot 2 base: M02 = Rz(3.14159265/2 + offsetRot), R02 = M02 * M02 (collisionDetection.cpp:177-178) */
+    double M[9]; rotz(M, 3.14159265 / 2 + 0.0); mul33(w.base2_rot, M, M);
+    /* T0 = (-offsetX/2, offsetY/2, offsetZ/2) then MxV(T0, R0, T0) IN PLACE (:99-103, :203-207): components computed
+     * later read the already overwritten earlier ones */
+    double I[9]; rotz(M, 0.0); mul33(I, M, M);
+    const double* Rb[2] = { I, w.base2_rot };
+    for (int r = 0; r < 2; r++) {
+        double T[3] = { -k.D / 2, 0.0 / 2, 0.0 / 2 };
+        const double* R = Rb[r];
+        T[0] = (R[0] * T[0] + R[1] * T[1] + R[2] * T[2]);
+        T[1] = (R[3] * T[0] + R[4] * T[1] + R[5] * T[2]);
+        T[2] = (R[6] * T[0] + R[7] * T[1] + R[8] * T[2]);
+        memcpy(w.base_t[r], T, sizeof(T));
+    }
+    /* static obstacle poses (:363-406 env 1; :431-456 env 2) */
+    for (int o = 0; o < 3; o++) { memset(w.static_frames[o], 0, sizeof(w.static_frames[o])); w.static_frames[o][0] = w.static_frames[o][4] = w.static_frames[o][8] = 1; }
+    if (env == 1) {
+        w.static_frames[1][9] = 250; w.static_frames[1][10] = 250;
+        w.static_frames[2][9] = -250; w.static_frames[2][10] = -250;
+    } else {
+        const double cx = cos(3.14), sx = sin(3.14);                              /* MRotX(Mobs, 3.14) */
+        double* F = w.static_frames[1];
+        F[0] = 1; F[1] = 0; F[2] = 0; F[3] = 0; F[4] = cx; F[5] = -sx; F[6] = 0; F[7] = sx; F[8] = cx; F[11] = 790;
+    }
+    build_pair_table(w, env);
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* lifetime                                                                                                           */
+/* ---------------------------------------------------------------------------------------------------------------- */
+extern "C" const char* ckc_version(void) { return CKC_VERSION_STR; }
+extern "C" const char* ckc_last_error(const ckc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int ckc_num_pairs(const ckc_ctx* ctx) { return ctx ? ctx->world.npairs : CKC_ERR_ARG; }
+
+static thread_local std::string g_create_error;
+extern "C" const char* ckc_create_error(void) { return g_create_error.c_str(); }
+
+extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int device) {
+    if (!out || (env != 1 && env != 2) || !mesh_path) { g_create_error = "bad argument"; return CKC_ERR_ARG; }
+    *out = nullptr;
+    ckc_ctx* ctx = new ckc_ctx();
+    ctx->env = env; ctx->device = device;
+    memset(&ctx->host_stats, 0, sizeof(ctx->host_stats));
+    auto bail = [&](int code, const std::string& msg) { g_create_error = msg; delete ctx; return code; };
+
+    struct stat st;
+    if (stat(mesh_path, &st) != 0) return bail(CKC_ERR_IO, std::string("cannot stat ") + mesh_path);
+    if (S_ISDIR(st.st_mode)) {
+        for (int m = 0; m < CKC_NUM_MESHES; m++) {
+            if (!k_mesh_file[m]) continue;
+            if (m == CKC_M_OBS && env != 1) continue;
+            if (m == CKC_M_CONE && env != 2) continue;
+            if (!read_tris_file(std::string(mesh_path) + "/" + k_mesh_file[m], ctx->meshes[m].tris))
+                return bail(CKC_ERR_IO, std::string("Couldn't open ") + k_mesh_file[m]);
+        }
+    } else if (!read_pack(mesh_path, ctx->meshes)) return bail(CKC_ERR_IO, std::string("bad mesh pack ") + mesh_path);
+    init_constants(ctx);
+    make_rod(ctx->meshes[CKC_M_ROD], ctx->kin.L);
+    for (int m = 0; m < CKC_NUM_MESHES; m++) build_hierarchy(ctx->meshes[m]);
+    for (int p = 0; p < ctx->world.npairs; p++)
+        if (ctx->meshes[ctx->world.pairs[p].mesh_a].ntris() == 0 || ctx->meshes[ctx->world.pairs[p].mesh_b].ntris() == 0)
+            return bail(CKC_ERR_IO, "a mesh used by the pair table is empty");
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return bail(CKC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return bail(CKC_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    ctx->num_sms = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return bail(CKC_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+
+    /* concatenate and upload */
+    std::vector<ckc_node> nodes; std::vector<double> tris;
+    for (int m = 0; m < CKC_NUM_MESHES; m++) {
+        ctx->world.node_off[m] = (int)nodes.size(); ctx->world.tri_off[m] = (int)(tris.size() / 9);
+        nodes.insert(nodes.end(), ctx->meshes[m].nodes.begin(), ctx->meshes[m].nodes.end());
+        tris.insert(tris.end(), ctx->meshes[m].tris.begin(), ctx->meshes[m].tris.end());
+    }
+    bool okc = ctx->d_nodes.reserve(nodes.size() * sizeof(ckc_node)) == cudaSuccess && ctx->d_tris.reserve(tris.size() * 8) == cudaSuccess &&
+               ctx->d_ctr.reserve(sizeof(ckc_counters_dev)) == cudaSuccess && ctx->d_small.reserve(64) == cudaSuccess;
+    if (okc) okc = cudaMemcpy(ctx->d_nodes.p, nodes.data(), nodes.size() * sizeof(ckc_node), cudaMemcpyHostToDevice) == cudaSuccess &&
+                   cudaMemcpy(ctx->d_tris.p, tris.data(), tris.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+                   cudaMemset(ctx->d_ctr.p, 0, sizeof(ckc_counters_dev)) == cudaSuccess && cudaMemset(ctx->d_small.p, 0, 64) == cudaSuccess;
+    if (!okc) { std::string msg = std::string("device upload: ") + cudaGetErrorString(cudaGetLastError()); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA; }
+    ctx->world.nodes = ctx->d_nodes.as<ckc_node>();
+    ctx->world.tris = ctx->d_tris.as<double>();
+    const char* ch = getenv("CKC_CHUNK");
+    if (ch && atoll(ch) >= 1024) ctx->chunk = atoll(ch);
+    *out = ctx;
+    return CKC_OK;
+}
+
+extern "C" void ckc_destroy(ckc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    dev_buf* bufs[] = { &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_small, &ctx->d_qin, &ctx->d_qout, &ctx->d_ac, &ctx->d_ik, &ctx->d_ok,
+                        &ctx->d_valid, &ctx->d_list, &ctx->d_frames, &ctx->d_ovf, &ctx->d_bigstack, &ctx->d_flags, &ctx->d_aux, &ctx->d_aux2, &ctx->d_qb, &ctx->d_edge };
+    for (dev_buf* b : bufs) b->release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int ckc_synchronize(ckc_ctx* ctx) {
+    if (!ctx) return CKC_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return CKC_OK;
+}
+
+extern "C" int ckc_host_alloc(void** p, uint64_t bytes) { return cudaMallocHost(p, bytes) == cudaSuccess ? CKC_OK : CKC_ERR_CUDA; }
+extern "C" int ckc_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? CKC_OK : CKC_ERR_CUDA; }
+
+extern "C" int ckc_get_stats(ckc_ctx* ctx, ckc_stats* out) {
+    if (!ctx || !out) return CKC_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ckc_counters_dev c;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(&c, ctx->d_ctr.p, sizeof(c), cudaMemcpyDeviceToHost));
+    *out = ctx->host_stats;
+    out->ik_feasible = (int64_t)c.ik_feasible; out->collision_calls = (int64_t)c.collision_calls; out->collisions = (int64_t)c.collisions;
+    out->bv_tests = (int64_t)c.bv_tests; out->tri_tests = (int64_t)c.tri_tests; out->queue_overflows = (int64_t)(c.queue_overflows & 0xffffffffull);
+    out->gd_iterations = (int64_t)c.gd_iterations; out->is_valid_calls = ctx->host_stats.is_valid_calls + (int64_t)c.is_valid_calls;
+    out->kernel_launches = ctx->launches;
+    return CKC_OK;
+}
+
+extern "C" int ckc_reset_stats(ckc_ctx* ctx) {
+    if (!ctx) return CKC_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemset(ctx->d_ctr.p, 0, sizeof(ckc_counters_dev)));
+    memset(&ctx->host_stats, 0, sizeof(ctx->host_stats));
+    ctx->launches = 0;
+    return CKC_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* shared pipeline pieces                                                                                             */
+/* ---------------------------------------------------------------------------------------------------------------- */
+static const ckc_layout AOS = { 12, 1 };
+static ckc_layout soa(int64_t n) { ckc_layout l = { 1, n }; return l; }
+
+static int32_t* p_list_count(ckc_ctx* c) { return c->d_small.as<int32_t>(); }
+static int32_t* p_work_counter(ckc_ctx* c) { return c->d_small.as<int32_t>() + 2; }       /* 2 ints */
+static int32_t* p_ovf_count(ckc_ctx* c) { return c->d_small.as<int32_t>() + 4; }
+
+/* K2 + K3 on the configurations listed in d_list (count on the device) */
+static int run_collision_stage(ckc_ctx* ctx, int64_t m_max, const double* d_q, ckc_layout l, const int32_t* d_list, const int32_t* d_m,
+                               uint8_t* d_hit, uint8_t* d_valid, uint8_t* d_pair_flags, cudaStream_t st) {
+    if (m_max <= 0) return CKC_OK;
+    CU(ctx->d_frames.reserve((size_t)m_max * CKC_FRAME_DOUBLES * 8));
+    CU(ctx->d_ovf.reserve((size_t)m_max * 4));
+    CU(ctx->d_bigstack.reserve((size_t)16 * 8 * 65536 * 4));
+    ckc_launch_link_frames(ctx->world, d_q, l, d_list, d_m, m_max, ctx->d_frames.as<double>(), st);
+    ckc_launch_cfg cfg = { ctx->num_sms };
+    ckc_launch_collide(ctx->world, cfg, ctx->d_frames.as<double>(), d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, p_work_counter(ctx),
+                       ctx->d_ovf.as<int32_t>(), p_ovf_count(ctx), ctx->d_bigstack.as<uint32_t>(), ctx->d_ctr.as<ckc_counters_dev>(), st);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return CKC_OK;
+}
+
+/* project (+ collide) one device-resident chunk */
+static int run_pcs_chunk(ckc_ctx* ctx, int64_t n, const double* d_q, ckc_layout li, const int8_t* d_ac, const int8_t* d_ik, uint64_t seed,
+                         uint64_t i0, int seeded, double* d_qout, ckc_layout lo, uint8_t* d_ok, uint8_t* d_valid, bool collide, cudaStream_t st) {
+    CU(ctx->d_list.reserve((size_t)n * 4));
+    CU(cudaMemsetAsync(p_list_count(ctx), 0, 4, st));
+    ckc_launch_pcs_project(ctx->kin, n, d_q, li, d_ac, d_ik, seed, i0, seeded, d_qout, lo, d_ok, d_valid, collide ? ctx->d_list.as<int32_t>() : nullptr,
+                           p_list_count(ctx), ctx->d_ctr.as<ckc_counters_dev>(), st);
+    ctx->launches += 1;
+    ctx->host_stats.ik_calls += n;
+    CU(cudaGetLastError());
+    if (collide) return run_collision_stage(ctx, n, d_qout, lo, ctx->d_list.as<int32_t>(), p_list_count(ctx), nullptr, d_valid, nullptr, st);
+    return CKC_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* PCS entry points                                                                                                   */
+/* ---------------------------------------------------------------------------------------------------------------- */
+static int pcs_host(ckc_ctx* ctx, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out, uint8_t* ok, uint8_t* valid, bool collide) {
+    if (!ctx || n < 0 || (n > 0 && (!q || !ik))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_qout.reserve((size_t)c * 96)); CU(ctx->d_ac.reserve((size_t)c)); CU(ctx->d_ik.reserve((size_t)c));
+        CU(ctx->d_ok.reserve((size_t)c)); CU(ctx->d_valid.reserve((size_t)c));
+        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        if (ac) CU(cudaMemcpyAsync(ctx->d_ac.p, ac + off, (size_t)c, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_ik.p, ik + off, (size_t)c, cudaMemcpyHostToDevice, st));
+        int rc = run_pcs_chunk(ctx, c, ctx->d_qin.as<double>(), AOS, ac ? ctx->d_ac.as<int8_t>() : nullptr, ctx->d_ik.as<int8_t>(), 0, 0, 0,
+                               ctx->d_qout.as<double>(), AOS, ctx->d_ok.as<uint8_t>(), ctx->d_valid.as<uint8_t>(), collide, st);
+        if (rc) return rc;
+        if (q_out) CU(cudaMemcpyAsync(q_out + off * 12, ctx->d_qout.p, (size_t)c * 96, cudaMemcpyDeviceToHost, st));
+        if (ok) CU(cudaMemcpyAsync(ok + off, ctx->d_ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (valid) CU(cudaMemcpyAsync(valid + off, ctx->d_valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return CKC_OK;
+}
+
+extern "C" int ckc_pcs_project(ckc_ctx* ctx, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out, uint8_t* ok) {
+    return pcs_host(ctx, n, q, ac, ik, q_out, ok, nullptr, false);
+}
+extern "C" int ckc_pcs_validate(ckc_ctx* ctx, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out, uint8_t* ok, uint8_t* valid) {
+    if (!valid) return fail(ctx, CKC_ERR_ARG, "valid must not be NULL");
+    if (ctx) ctx->host_stats.is_valid_calls += n;
+    return pcs_host(ctx, n, q, ac, ik, q_out, ok, valid, true);
+}
+
+extern "C" int ckc_pcs_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, const int8_t* d_ac, const int8_t* d_ik, double* d_q_out,
+                                    uint8_t* d_ok, uint8_t* d_valid, void* stream) {
+    if (!ctx || n < 0 || !d_q || !d_ik || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    /* the projected configurations are needed by the collision stage: use the caller's buffer or an internal one */
+    double* qo = d_q_out;
+    if (!qo) { CU(ctx->d_qout.reserve((size_t)n * 96)); qo = ctx->d_qout.as<double>(); }
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        ckc_layout l = { 1, n };                       /* SoA over the whole batch; chunk = index window */
+        int rc = run_pcs_chunk(ctx, c, d_q + off, l, d_ac ? d_ac + off : nullptr, d_ik + off, 0, 0, 0, qo + off, l, d_ok ? d_ok + off : nullptr,
+                               d_valid + off, true, st);
+        if (rc) return rc;
+    }
+    return CKC_OK;
+}
+
+extern "C" int ckc_spcs_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out, uint8_t* d_ok, uint8_t* d_valid, void* stream) {
+    if (!ctx || n < 0 || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        double* qo; ckc_layout l;
+        if (d_q_out) { qo = d_q_out + off; l = soa(n); }
+        else { CU(ctx->d_qout.reserve((size_t)c * 96)); qo = ctx->d_qout.as<double>(); l = soa(c); }
+        int rc = run_pcs_chunk(ctx, c, nullptr, l, nullptr, nullptr, seed, i0 + (uint64_t)off, 1, qo, l, d_ok ? d_ok + off : nullptr, d_valid + off, true, st);
+        if (rc) return rc;
+    }
+    return CKC_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* collision entry points                                                                                             */
+/* ---------------------------------------------------------------------------------------------------------------- */
+static int collide_host(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* hit, uint8_t* flags) {
+    if (!ctx || n < 0 || (n > 0 && (!q || (!hit && !flags)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t chunk = std::min<int64_t>(ctx->chunk, 1 << 18);
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t c = std::min(chunk, n - off);
+        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_ok.reserve((size_t)c));
+        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        if (flags) { CU(ctx->d_flags.reserve((size_t)c * CKC_MAX_PAIRS)); CU(cudaMemsetAsync(ctx->d_flags.p, 0, (size_t)c * CKC_MAX_PAIRS, st)); }
+        int rc = run_collision_stage(ctx, c, ctx->d_qin.as<double>(), AOS, nullptr, nullptr, ctx->d_ok.as<uint8_t>(), nullptr,
+                                     flags ? ctx->d_flags.as<uint8_t>() : nullptr, st);
+        if (rc) return rc;
+        if (hit) CU(cudaMemcpyAsync(hit + off, ctx->d_ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (flags) CU(cudaMemcpyAsync(flags + off * CKC_MAX_PAIRS, ctx->d_flags.p, (size_t)c * CKC_MAX_PAIRS, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return CKC_OK;
+}
+extern "C" int ckc_collide(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* hit) { return collide_host(ctx, n, q, hit, nullptr); }
+extern "C" int ckc_collide_pairs(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* flags) { return collide_host(ctx, n, q, nullptr, flags); }
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+extern "C" int ckc_check_angle_limits(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* ok) {
+    if (!ctx || n < 0 || (n > 0 && (!q || !ok))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_ok.reserve((size_t)c));
+        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        ckc_launch_limits(ctx->kin, c, ctx->d_qin.as<double>(), AOS, ctx->d_ok.as<uint8_t>(), st);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(ok + off, ctx->d_ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return CKC_OK;
+}
+
+extern "C" int ckc_identify_ik(ckc_ctx* ctx, int64_t n, const double* q, int8_t* ik01) {
+    if (!ctx || n < 0 || (n > 0 && (!q || !ik01))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_aux.reserve((size_t)c * 2));
+        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        ckc_launch_identify_ik(ctx->kin, c, ctx->d_qin.as<double>(), AOS, ctx->d_aux.as<int8_t>(), st);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(ik01 + off * 2, ctx->d_aux.p, (size_t)c * 2, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return CKC_OK;
+}
+
+extern "C" int ckc_measure_fma_peak(ckc_ctx* ctx, int precision, double* tflops) {
+    if (!ctx || !tflops || (precision != 32 && precision != 64)) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_aux.reserve(64));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int iters = precision == 64 ? 1 << 15 : 1 << 16;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, ctx->stream));
+        ckc_launch_fma_peak(precision, ctx->num_sms, iters, ctx->d_aux.as<float>(), ctx->stream);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 8.0 * iters * 1024.0 * 2.0 * ctx->num_sms;
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
+    return CKC_OK;
+}

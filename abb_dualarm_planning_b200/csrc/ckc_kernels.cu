@@ -1,0 +1,423 @@
+/*
+ * ckc_kernels.cu -- the sm_100a kernels of libckc and their launchers.  Product code (no oracle includes).
+ *
+ *   k_pcs_project   K1  one thread per sample: FK(active arm) -> closure target -> one analytic IK branch -> joint
+ *                       limits; FP64 in registers; warp-aggregated append of the IK-feasible samples to a work list.
+ *   k_link_frames   K2  one thread per feasible configuration: the 18 configuration-dependent link frames (FP64).
+ *   k_collide       K3  one WARP per feasible configuration: warp-cooperative traversal of the OBB hierarchies of
+ *                       the pair table with a shared-memory task stack; FP32 conservative box culling (guard band),
+ *                       FP64 PQP-exact triangle distance at the leaves, __ballot_sync early-out on the first hit.
+ *   k_limits, k_identify_ik, k_fma_peak, k_transpose: small helpers.
+ */
+#include "ckc_device.cuh"
+
+using namespace ckc;
+
+#define CKC_STACK_CAP 640           /* per-warp shared-memory task stack (entries) */
+#define CKC_BIG_STACK_CAP 65536     /* per-warp global-memory stack of the overflow path */
+#define CKC_TRIQ_CAP 64
+#define CKC_COLLIDE_WARPS 8
+
+/* ================================================================================================================ */
+/* K1                                                                                                                 */
+/* ================================================================================================================ */
+__device__ __forceinline__ void append_to_list(bool flag, int32_t value, int32_t* list, int32_t* list_count) {
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (m == 0 || list == nullptr) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == (__ffs(m) - 1)) base = atomicAdd(list_count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (flag) list[base + __popc(m & ((1u << lane) - 1))] = value;
+}
+
+__global__ void __launch_bounds__(256)
+k_pcs_project(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, ckc_layout li, const int8_t* __restrict__ ac_in,
+              const int8_t* __restrict__ ik_in, uint64_t key, uint64_t i0, int seeded, double* __restrict__ q_out, ckc_layout lo,
+              uint8_t* __restrict__ ok_out, uint8_t* __restrict__ valid_out, int32_t* __restrict__ list, int32_t* list_count,
+              ckc_counters_dev* ctr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (i < n) {
+        double q[12];
+        int ac = 0, sol;
+        if (seeded) {
+            /* S-PCS: uniform in the rand_q_ambient box (apc_class.cpp:643-661), ik = floor(8 u) */
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                const int jj = j % 6;
+                const double lo_j = (jj == 5) ? -CKC_PI_ : kin.lim_lo[jj], hi_j = (jj == 5) ? CKC_PI_ : kin.lim_hi[jj];
+                q[j] = lo_j + uniform01(key, i0 + (uint64_t)i, j) * (hi_j - lo_j);
+            }
+            sol = (int)(uniform01(key, i0 + (uint64_t)i, 12) * 8.0);
+            sol = sol > 7 ? 7 : sol;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; j++) q[j] = q_in[i * li.stride_i + j * li.stride_j];
+            ac = ac_in ? ac_in[i] : 0;
+            sol = ik_in[i] & 7;
+        }
+        double qp[6];
+        if (ac == 0) {
+            ok = project_passive(kin, q, 0, sol, qp);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 6; j++) q[6 + j] = qp[j];
+            }
+        } else {
+            ok = project_passive(kin, q + 6, 1, sol, qp);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 6; j++) q[j] = qp[j];
+            }
+        }
+        if (q_out) {
+#pragma unroll
+            for (int j = 0; j < 12; j++) q_out[i * lo.stride_i + j * lo.stride_j] = q[j];
+        }
+        if (ok_out) ok_out[i] = ok ? 1 : 0;
+        if (valid_out) valid_out[i] = 0;
+    }
+    append_to_list(ok, (int32_t)i, list, list_count);
+    if (ctr) {
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&ctr->ik_feasible, (unsigned long long)__popc(m));
+    }
+}
+
+void ckc_launch_pcs_project(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout li, const int8_t* ac, const int8_t* ik,
+                            uint64_t seed, uint64_t i0, int seeded, double* q_out, ckc_layout lo, uint8_t* ok, uint8_t* valid,
+                            int32_t* list, int32_t* list_count, ckc_counters_dev* ctr, cudaStream_t st) {
+    if (n <= 0) return;
+    const int threads = 256;
+    const int64_t blocks = (n + threads - 1) / threads;
+    k_pcs_project<<<(unsigned)blocks, threads, 0, st>>>(kin, n, q, li, ac, ik, mix64(seed), i0, seeded, q_out, lo, ok, valid, list, list_count, ctr);
+}
+
+/* ================================================================================================================ */
+/* K2                                                                                                                 */
+/* ================================================================================================================ */
+__global__ void __launch_bounds__(128)
+k_link_frames(const ckc_world_dev w, const double* __restrict__ q, ckc_layout l, const int32_t* __restrict__ list,
+              const int32_t* __restrict__ d_m, int64_t m_max, double* __restrict__ frames) {
+    int64_t m = d_m ? (int64_t)*d_m : m_max;
+    if (m > m_max) m = m_max;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
+        const int64_t i = list ? (int64_t)list[k] : k;
+        double qq[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) qq[j] = q[i * l.stride_i + j * l.stride_j];
+        double* out = frames + k * CKC_FRAME_DOUBLES;
+        const double I3[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+        robot_frames(I3, w.base_t[0], qq, out);                   /* robot 1: R0 = Rz(0)^2 = I */
+        robot_frames(w.base2_rot, w.base_t[1], qq + 6, out + 96); /* robot 2: R02 = Rz(3.14159265/2)^2 */
+        /* the two frames the reference's pair table mixes up (collisionDetection.cpp:373, :397, :415) */
+#pragma unroll
+        for (int e = 0; e < 9; e++) { out[16 * 12 + e] = out[10 * 12 + e]; out[17 * 12 + e] = out[2 * 12 + e]; }
+#pragma unroll
+        for (int e = 9; e < 12; e++) { out[16 * 12 + e] = out[2 * 12 + e]; out[17 * 12 + e] = out[10 * 12 + e]; }
+    }
+}
+
+void ckc_launch_link_frames(const ckc_world_dev& w, const double* q, ckc_layout l, const int32_t* list, const int32_t* d_m, int64_t m_max,
+                            double* frames, cudaStream_t st) {
+    if (m_max <= 0) return;
+    int64_t blocks = (m_max + 127) / 128;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_link_frames<<<(unsigned)blocks, 128, 0, st>>>(w, q, l, list, d_m, m_max, frames);
+}
+
+/* ================================================================================================================ */
+/* K3: warp-cooperative collision                                                                                     */
+/* ================================================================================================================ */
+struct collide_args {
+    const double* frames;        /* [m][18][12] */
+    const int32_t* list;         /* sample index of configuration k (NULL: k) */
+    const int32_t* d_m;          /* number of configurations (device), or NULL */
+    int64_t m_max;
+    uint8_t* hit_out;            /* hit_out[sample] = 1/0   (may be NULL) */
+    uint8_t* valid_out;          /* valid_out[sample] = !hit (may be NULL) */
+    uint8_t* pair_flags;         /* [sample][116] per-pair flags, disables early exit (may be NULL) */
+    int32_t* work_counter;
+    int32_t* ovf_list;           /* configurations whose task stack overflowed (k indices) */
+    int32_t* ovf_count;
+    uint32_t* big_stack;         /* overflow path: per-warp global stacks */
+    ckc_counters_dev* ctr;
+};
+
+__device__ __forceinline__ const double* frame64(const ckc_world_dev& w, const double* cfg_frames, int f) {
+    return f < CKC_NUM_DYN_FRAMES ? cfg_frames + 12 * f : w.static_frames[f - CKC_NUM_DYN_FRAMES];
+}
+
+/* exact leaf test: triangle ta of mesh A vs tb of mesh B under the pair's poses, PQP_Tolerance conventions:
+ * R = Ra^T Rb, T = Ra^T (Tb - Ta), triangle B transformed into A's frame, then TriDist */
+__device__ __forceinline__ double leaf_distance(const ckc_world_dev& w, const double* cfg_frames, const ckc_pair pr, int ta, int tb) {
+    const double* Fa = frame64(w, cfg_frames, pr.frame_a);
+    const double* Fb = frame64(w, cfg_frames, pr.frame_b);
+    double R[9], T[3];
+    const double tx = Fb[9] - Fa[9], ty = Fb[10] - Fa[10], tz = Fb[11] - Fa[11];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) R[3 * i + j] = Fa[i] * Fb[j] + Fa[3 + i] * Fb[3 + j] + Fa[6 + i] * Fb[6 + j];
+        T[i] = Fa[i] * tx + Fa[3 + i] * ty + Fa[6 + i] * tz;
+    }
+    const double* pa = w.tris + 9 * (int64_t)(w.tri_off[pr.mesh_a] + ta);
+    const double* pb = w.tris + 9 * (int64_t)(w.tri_off[pr.mesh_b] + tb);
+    v3 S[3], Tt[3];
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+        S[v] = { pa[3 * v], pa[3 * v + 1], pa[3 * v + 2] };
+        const double x = pb[3 * v], y = pb[3 * v + 1], z = pb[3 * v + 2];
+        Tt[v] = { R[0] * x + R[1] * y + R[2] * z + T[0], R[3] * x + R[4] * y + R[5] * z + T[1], R[6] * x + R[7] * y + R[8] * z + T[2] };
+    }
+    return tri_dist(S, Tt);
+}
+
+template <bool kBigStack>
+__global__ void __launch_bounds__(CKC_COLLIDE_WARPS * 32)
+k_collide(const ckc_world_dev w, const collide_args a) {
+    __shared__ float s_frames[CKC_COLLIDE_WARPS][CKC_NUM_FRAMES * 12];
+    __shared__ uint32_t s_stack[kBigStack ? 1 : CKC_COLLIDE_WARPS][kBigStack ? 1 : CKC_STACK_CAP];
+    __shared__ uint32_t s_triq[CKC_COLLIDE_WARPS][CKC_TRIQ_CAP];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1;
+    float* F = s_frames[wib];
+    uint32_t* triq = s_triq[wib];
+    uint32_t* stack = kBigStack ? a.big_stack + (size_t)(blockIdx.x * CKC_COLLIDE_WARPS + wib) * CKC_BIG_STACK_CAP : s_stack[kBigStack ? 0 : wib];
+    const int cap = kBigStack ? CKC_BIG_STACK_CAP : CKC_STACK_CAP;
+
+    int64_t m = kBigStack ? (int64_t)*a.ovf_count : (a.d_m ? (int64_t)*a.d_m : a.m_max);
+    if (m > a.m_max) m = a.m_max;
+    const bool per_pair = a.pair_flags != nullptr;
+
+    unsigned long long n_bv = 0, n_tri = 0, n_cfg = 0, n_hit = 0;
+
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(a.work_counter, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= m) break;
+        const int cfg = kBigStack ? a.ovf_list[k] : k;                 /* index into frames[] / list[] */
+        const int64_t sample = a.list ? (int64_t)a.list[cfg] : (int64_t)cfg;
+        const double* cfg_frames = a.frames + (int64_t)cfg * CKC_FRAME_DOUBLES;
+
+        /* stage this configuration's frames as FP32 in shared memory (static obstacle poses from the parameter bank) */
+        for (int e = lane; e < CKC_NUM_FRAMES * 12; e += 32)
+            F[e] = e < CKC_FRAME_DOUBLES ? (float)cfg_frames[e] : (float)w.static_frames[(e - CKC_FRAME_DOUBLES) / 12][(e - CKC_FRAME_DOUBLES) % 12];
+        /* seed the stack with the root task of every table entry, first entry on top */
+        int top = w.npairs;
+        for (int p = lane; p < w.npairs; p += 32) stack[w.npairs - 1 - p] = (uint32_t)p << 22;
+        int ntri = 0;
+        bool hit = false, overflow = false;
+        /* env 2: "path not from above" rule, collisionDetection.cpp:427-428 */
+        if (w.env == 2 && (cfg_frames[7 * 12 + 11] > 800.0 || cfg_frames[15 * 12 + 11] > 800.0)) { hit = true; top = 0; }
+        __syncwarp();
+
+        while (!hit) {
+            if (ntri >= 32 || (top == 0 && ntri > 0)) {
+                /* ---- exact triangle tests, up to 32 at a time ---- */
+                const int cnt = ntri < 32 ? ntri : 32;
+                bool h = false;
+                uint32_t t = 0;
+                if (lane < cnt) {
+                    t = triq[ntri - 1 - lane];
+                    const int p = t >> 20;
+                    const double d = leaf_distance(w, cfg_frames, w.pairs[p], (t >> 10) & 1023, t & 1023);
+                    h = d <= w.tol;                                   /* PQP: closer_than_tolerance iff d <= tolerance */
+                }
+                n_tri += cnt;
+                ntri -= cnt;
+                if (per_pair) {
+                    if (h) a.pair_flags[sample * CKC_MAX_PAIRS + (t >> 20)] = 1;
+                } else if (__any_sync(0xffffffffu, h)) hit = true;
+                __syncwarp();
+                continue;
+            }
+            if (top == 0) break;
+            /* ---- box tests, one task per lane ---- */
+            const int cnt = top < 32 ? top : 32;
+            const bool active = lane < cnt;
+            bool expand = false, leafpair = false;
+            uint32_t c0 = 0, c1 = 0, tt = 0;
+            if (active) {
+                const uint32_t t = stack[top - 1 - lane];
+                const int p = t >> 22, na = (t >> 11) & 2047, nb = t & 2047;
+                const ckc_pair pr = w.pairs[p];
+                bool skip = false;
+                if (per_pair) skip = a.pair_flags[sample * CKC_MAX_PAIRS + p] != 0;      /* pair already decided */
+                if (!skip) {
+                    const box32 A = load_box(w.nodes + w.node_off[pr.mesh_a] + na);
+                    const box32 B = load_box(w.nodes + w.node_off[pr.mesh_b] + nb);
+                    const bool far = boxes_farther_than(A, F + 12 * pr.frame_a, B, F + 12 * pr.frame_b, w.cull_tol);
+                    if (!far) {
+                        if (A.child < 0 && B.child < 0) { leafpair = true; tt = ((uint32_t)p << 20) | ((uint32_t)(~A.child) << 10) | (uint32_t)(~B.child); }
+                        else {
+                            expand = true;
+                            if (B.child < 0 || (A.child >= 0 && A.size2 > B.size2)) {       /* descend the larger box */
+                                c0 = ((uint32_t)p << 22) | ((uint32_t)A.child << 11) | (uint32_t)nb;
+                                c1 = c0 + (1u << 11);
+                            } else {
+                                c0 = ((uint32_t)p << 22) | ((uint32_t)na << 11) | (uint32_t)B.child;
+                                c1 = c0 + 1u;
+                            }
+                        }
+                    }
+                }
+            }
+            n_bv += cnt;
+            top -= cnt;
+            __syncwarp();
+            const unsigned mt = __ballot_sync(0xffffffffu, leafpair);
+            const unsigned me = __ballot_sync(0xffffffffu, expand);
+            if (leafpair) triq[ntri + __popc(mt & lt_mask)] = tt;
+            ntri += __popc(mt);
+            const int npush = 2 * __popc(me);
+            if (top + npush > cap) { overflow = true; break; }
+            if (expand) { const int pos = top + 2 * __popc(me & lt_mask); stack[pos] = c1; stack[pos + 1] = c0; }
+            top += npush;
+            __syncwarp();
+        }
+
+        if (overflow) {
+            if (!kBigStack) {
+                if (lane == 0) { const int o = atomicAdd(a.ovf_count, 1); a.ovf_list[o] = cfg; }
+                if (per_pair) for (int p = lane; p < CKC_MAX_PAIRS; p += 32) a.pair_flags[sample * CKC_MAX_PAIRS + p] = 0;
+                __syncwarp();
+                continue;                                             /* redone by the big-stack launch */
+            }
+            hit = true;                                               /* capacity exhausted even there: report conservatively */
+            if (lane == 0 && a.ctr) atomicAdd(&a.ctr->queue_overflows, 1ull << 32);
+        }
+        if (per_pair) {
+            __syncwarp();
+            unsigned any = 0;
+            for (int p = lane; p < CKC_MAX_PAIRS; p += 32) any |= a.pair_flags[sample * CKC_MAX_PAIRS + p];
+            hit = __any_sync(0xffffffffu, any != 0) || hit;
+        }
+        if (lane == 0) {
+            if (a.hit_out) a.hit_out[sample] = hit ? 1 : 0;
+            if (a.valid_out) a.valid_out[sample] = hit ? 0 : 1;
+        }
+        n_cfg++; n_hit += hit ? 1 : 0;
+        __syncwarp();
+    }
+    if (lane == 0 && a.ctr) {
+        atomicAdd(&a.ctr->bv_tests, n_bv);
+        atomicAdd(&a.ctr->tri_tests, n_tri);
+        atomicAdd(&a.ctr->collision_calls, n_cfg);
+        atomicAdd(&a.ctr->collisions, n_hit);
+        if (kBigStack) atomicAdd(&a.ctr->queue_overflows, n_cfg);
+    }
+}
+
+void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const double* frames, const int32_t* list, const int32_t* d_m,
+                        int64_t m_max, uint8_t* hit_out, uint8_t* valid_out, uint8_t* pair_flags, int32_t* work_counter,
+                        int32_t* ovf_list, int32_t* ovf_count, uint32_t* big_stack, ckc_counters_dev* ctr, cudaStream_t st) {
+    if (m_max <= 0) return;
+    collide_args a;
+    a.frames = frames; a.list = list; a.d_m = d_m; a.m_max = m_max; a.hit_out = hit_out; a.valid_out = valid_out; a.pair_flags = pair_flags;
+    a.work_counter = work_counter; a.ovf_list = ovf_list; a.ovf_count = ovf_count; a.big_stack = big_stack; a.ctr = ctr;
+    cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st);           /* work_counter[0] main pass, [1] overflow pass */
+    cudaMemsetAsync(ovf_count, 0, sizeof(int32_t), st);
+    int64_t blocks = (m_max + CKC_COLLIDE_WARPS - 1) / CKC_COLLIDE_WARPS;
+    const int64_t resident = (int64_t)cfg.num_sms * 6;
+    if (blocks > resident) blocks = resident;
+    k_collide<false><<<(unsigned)blocks, CKC_COLLIDE_WARPS * 32, 0, st>>>(w, a);
+    /* overflow pass: tiny grid, global-memory stacks; exits immediately when nothing overflowed */
+    collide_args b = a;
+    b.work_counter = work_counter + 1;
+    k_collide<true><<<16, CKC_COLLIDE_WARPS * 32, 0, st>>>(w, b);
+}
+
+/* ================================================================================================================ */
+/* helpers                                                                                                            */
+/* ================================================================================================================ */
+__global__ void k_limits(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q, ckc_layout l, uint8_t* __restrict__ ok) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double qq[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) qq[j] = q[i * l.stride_i + j * l.stride_j];
+    ok[i] = within_limits(kin, qq) ? 1 : 0;
+}
+void ckc_launch_limits(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, uint8_t* ok, cudaStream_t st) {
+    if (n <= 0) return;
+    k_limits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kin, n, q, l, ok);
+}
+
+/* identify_state_ik (StateValidityCheckerPCS.cpp:275-316): 2 FK + up to 16 IK branches per configuration, one thread each */
+__global__ void __launch_bounds__(128)
+k_identify_ik(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q, ckc_layout l, int8_t* __restrict__ ik01) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double qq[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) qq[j] = q[i * l.stride_i + j * l.stride_j];
+    int ik0 = -1, ik1 = -1;
+    double R[9], p[3], Rt[9], pt[3], cand[6];
+    fk_arm(kin, qq, 0, R, p);
+#pragma unroll
+    for (int r = 0; r < 3; r++) { Rt[3 * r] = -R[3 * r]; Rt[3 * r + 1] = -R[3 * r + 1]; Rt[3 * r + 2] = R[3 * r + 2]; pt[r] = R[3 * r] * kin.L + p[r]; }
+    int nsol = 0;
+#pragma unroll 1
+    for (int s = 0; s < 8; s++) {
+        if (!ik_arm(kin, Rt, pt, 1, s, cand)) continue;
+        nsol++;
+        double d2 = 0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) { const double d = cand[j] - qq[6 + j]; d2 += d * d; }
+        if (sqrt(d2) < 1e-1) { ik0 = s; break; }
+    }
+    if (nsol > 0) {          /* :283-284: with no IK solution at all for the first chain the function returns early */
+        fk_arm(kin, qq + 6, 1, R, p);
+#pragma unroll
+        for (int r = 0; r < 3; r++) { Rt[3 * r] = -R[3 * r]; Rt[3 * r + 1] = -R[3 * r + 1]; Rt[3 * r + 2] = R[3 * r + 2]; pt[r] = R[3 * r] * kin.L + p[r]; }
+#pragma unroll 1
+        for (int s = 0; s < 8; s++) {
+            if (!ik_arm(kin, Rt, pt, 0, s, cand)) continue;
+            double d2 = 0;
+#pragma unroll
+            for (int j = 0; j < 6; j++) { const double d = cand[j] - qq[j]; d2 += d * d; }
+            if (sqrt(d2) < 1e-1) { ik1 = s; break; }
+        }
+    }
+    ik01[2 * i] = (int8_t)ik0;
+    ik01[2 * i + 1] = (int8_t)ik1;
+}
+void ckc_launch_identify_ik(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, int8_t* ik01, cudaStream_t st) {
+    if (n <= 0) return;
+    k_identify_ik<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kin, n, q, l, ik01);
+}
+
+/* FMA-chain peak probe: 8 independent dependent-chains per thread, 2 flop per FMA */
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_fma_peak(int iters, float* sink) {
+    T a0 = (T)threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const T m = (T)0.9999, c = (T)1e-3;
+    for (int i = 0; i < iters; i++) {
+        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+    const T s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == (T)-1) sink[0] = (float)s;
+}
+void ckc_launch_fma_peak(int precision, int num_sms, int iters, float* sink, cudaStream_t st) {
+    if (precision == 64) k_fma_peak<double><<<num_sms * 2, 1024, 0, st>>>(iters, sink);
+    else k_fma_peak<float><<<num_sms * 2, 1024, 0, st>>>(iters, sink);
+}
+
+__global__ void k_transpose(const double* __restrict__ src, ckc_layout ls, double* __restrict__ dst, ckc_layout ld, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int j = 0; j < 12; j++) dst[i * ld.stride_i + j * ld.stride_j] = src[i * ls.stride_i + j * ls.stride_j];
+}
+void ckc_launch_transpose(const double* src, ckc_layout ls, double* dst, ckc_layout ld, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_transpose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, ls, dst, ld, n);
+}
