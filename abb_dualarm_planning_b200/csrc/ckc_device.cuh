@@ -365,4 +365,234 @@ __device__ __noinline__ double tri_dist(const v3* S, const v3* T) {
 }
 
 }  // namespace ckc
+
+/* ================================================================================================================ */
+/* GD flavour: the 12-joint serial chain of kdl_class.cpp:32-45 and the Newton-Raphson closure projection of          */
+/* kdl::GD (kdl_class.cpp:68-140) = KDL ChainIkSolverPos_NR(fk_recursive, vel_pinv(eps 1e-5), 10000, 1e-5).           */
+/* ================================================================================================================ */
+namespace ckc {
+
+/* chain FK in chain joint order.  Optionally the columns of the 6x12 geometric Jacobian referred to the BASE ORIGIN:
+ * col0_j = [ a_j x (-o_j) ; a_j ].  The tip-referred Jacobian of KDL's ChainJntToJacSolver is J = X col0 with
+ * X = [[I, -[p]x],[0, I]] (velocity of the tip point = v_origin + w x p). */
+template <bool kJac>
+__device__ __forceinline__ void chain_fk(const ckc_kin_dev& k, const double* qc, double* R, double* p, double (*J0)[12]) {
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+    p[0] = 0; p[1] = 0; p[2] = 0;
+    /* joint axes of the 13 segments (kdl_class.cpp:32-45): None, Z, Y, Y, X, Y, X | X, Y, X, Y, Y, Z -- compile-time so
+     * that the unrolled walk indexes registers statically */
+    constexpr int kAxis[13] = { -1, 2, 1, 1, 0, 1, 0, 0, 1, 0, 1, 1, 2 };
+    int j = 0;
+#pragma unroll
+    for (int i = 0; i < 13; i++) {
+        const int ax = kAxis[i];
+        if (i > 0) {            /* segment 0 has no joint (Joint::None) */
+            if (kJac) {
+                const double a0 = R[ax], a1 = R[3 + ax], a2 = R[6 + ax];
+                J0[0][j] = p[1] * a2 - p[2] * a1;       /* a x (-o) = o x a */
+                J0[1][j] = p[2] * a0 - p[0] * a2;
+                J0[2][j] = p[0] * a1 - p[1] * a0;
+                J0[3][j] = a0; J0[4][j] = a1; J0[5][j] = a2;
+            }
+            double s, c;
+            sincos(qc[j], &s, &c);
+            if (ax == 0) post_rot_x(R, c, s); else if (ax == 1) post_rot_y(R, c, s); else post_rot_z(R, c, s);
+            j++;
+        }
+        const double tx = k.kdl_tip[i][0], ty = k.kdl_tip[i][1], tz = k.kdl_tip[i][2];
+        p[0] += R[0] * tx + R[1] * ty + R[2] * tz;
+        p[1] += R[3] * tx + R[4] * ty + R[5] * tz;
+        p[2] += R[6] * tx + R[7] * ty + R[8] * tz;
+    }
+}
+
+/* KDL Rotation::GetRot() = axis * angle via GetRotAngle(axis, eps = 1e-6): rotation vector of M (row-major) */
+__device__ __forceinline__ void kdl_rotvec(const double* M, double* rv) {
+    const double eps = 1e-6, eps2 = 1e-5;
+    if (fabs(M[1] - M[3]) < eps && fabs(M[2] - M[6]) < eps && fabs(M[5] - M[7]) < eps) {
+        if (fabs(M[1] + M[3]) < eps2 && fabs(M[2] + M[6]) < eps2 && fabs(M[5] + M[7]) < eps2 && fabs(M[0] + M[4] + M[8] - 3) < eps2) {
+            rv[0] = rv[1] = rv[2] = 0; return;
+        }
+        const double angle = 3.14159265358979323846;
+        const double xx = (M[0] + 1) / 2, yy = (M[4] + 1) / 2, zz = (M[8] + 1) / 2;
+        const double xy = (M[1] + M[3]) / 4, xz = (M[2] + M[6]) / 4, yz = (M[5] + M[7]) / 4;
+        double x, y, z;
+        if (xx > yy && xx > zz) { x = sqrt(xx); y = xy / x; z = xz / x; }
+        else if (yy > zz) { y = sqrt(yy); x = xy / y; z = yz / y; }
+        else { z = sqrt(zz); x = xz / z; y = yz / z; }
+        rv[0] = x * angle; rv[1] = y * angle; rv[2] = z * angle; return;
+    }
+    const double f = (M[0] + M[4] + M[8] - 1) / 2;
+    double x = M[7] - M[5], y = M[2] - M[6], z = M[3] - M[1];
+    const double n = sqrt(x * x + y * y + z * z);
+    const double angle = atan2(n / 2, f);
+    if (n > 0) { x /= n; y /= n; z /= n; }
+    rv[0] = x * angle; rv[1] = y * angle; rv[2] = z * angle;
+}
+
+/* exact truncated pseudo-inverse step dq = V S^+ U^T tw (singular values < eps dropped) by one-sided Jacobi on J^T.
+ * Only reached near singular configurations (the Cholesky path below covers the regular case). */
+__device__ __noinline__ void pinv_step_svd(const double (*J)[12], const double* tw, double eps, double* dq) {
+    double B[12][6], W[6][6];
+    for (int r = 0; r < 12; r++) for (int c = 0; c < 6; c++) B[r][c] = J[c][r];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) W[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 150; sweep++) {
+        double off = 0;
+        for (int a = 0; a < 6; a++)
+            for (int b = a + 1; b < 6; b++) {
+                double aa = 0, bb = 0, ab = 0;
+                for (int r = 0; r < 12; r++) { aa += B[r][a] * B[r][a]; bb += B[r][b] * B[r][b]; ab += B[r][a] * B[r][b]; }
+                if (fabs(ab) <= 1e-300 || fabs(ab) <= 1e-17 * sqrt(aa * bb)) continue;
+                off = fmax(off, fabs(ab) / sqrt(aa * bb));
+                const double zeta = (bb - aa) / (2 * ab);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+                const double c = 1 / sqrt(1 + t * t), s = c * t;
+                for (int r = 0; r < 12; r++) { const double x = B[r][a], y = B[r][b]; B[r][a] = c * x - s * y; B[r][b] = s * x + c * y; }
+                for (int r = 0; r < 6; r++) { const double x = W[r][a], y = W[r][b]; W[r][a] = c * x - s * y; W[r][b] = s * x + c * y; }
+            }
+        if (off < 1e-15) break;
+    }
+    for (int r = 0; r < 12; r++) dq[r] = 0;
+    for (int c = 0; c < 6; c++) {
+        double s2 = 0;
+        for (int r = 0; r < 12; r++) s2 += B[r][c] * B[r][c];
+        if (sqrt(s2) < eps) continue;
+        double ut = 0;
+        for (int r = 0; r < 6; r++) ut += W[r][c] * tw[r];
+        const double coef = ut / s2;
+        for (int r = 0; r < 12; r++) dq[r] += B[r][c] * coef;
+    }
+}
+
+/* One Newton step: dq = pinv(J) tw.  Regular case: dq = J^T (J J^T)^-1 tw by Cholesky (identical to the SVD pseudo
+ * inverse when no singular value is truncated); a lower bound on the smallest singular value proves regularity,
+ * otherwise the exact truncated SVD path runs. */
+__device__ __forceinline__ void newton_step(const double (*J0)[12], const double* p, const double* tw, double* dq) {
+    /* tip-referred Jacobian rows: v_tip = v_0 + w x p  =>  Jv = J0v - [p]x Jw */
+    double J[6][12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+        const double w0 = J0[3][c], w1 = J0[4][c], w2 = J0[5][c];
+        J[0][c] = J0[0][c] + (w1 * p[2] - w2 * p[1]);
+        J[1][c] = J0[1][c] + (w2 * p[0] - w0 * p[2]);
+        J[2][c] = J0[2][c] + (w0 * p[1] - w1 * p[0]);
+        J[3][c] = w0; J[4][c] = w1; J[5][c] = w2;
+    }
+    double A[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double s = 0;
+#pragma unroll
+            for (int c = 0; c < 12; c++) s += J[i][c] * J[j][c];
+            A[i][j] = s;
+        }
+    /* Cholesky A = L L^T (in place, lower) */
+    bool regular = true;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double s = A[i][j];
+#pragma unroll
+            for (int kk = 0; kk < j; kk++) s -= A[i][kk] * A[j][kk];
+            if (i == j) { if (!(s > 1e-300)) { regular = false; s = 1; } A[i][i] = sqrt(s); }
+            else A[i][j] = s / A[j][j];
+        }
+    }
+    if (regular) {
+        /* ||L^-1||_F^2 = trace(A^-1) >= 1 / lambda_min(A)  =>  sigma_min(J)^2 >= 1 / ||L^-1||_F^2 */
+        double Li[6][6], fro = 0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+#pragma unroll
+            for (int r = c; r < 6; r++) {
+                double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int kk = c; kk < r; kk++) s -= A[r][kk] * Li[kk][c];
+                Li[r][c] = s / A[r][r];
+                fro += Li[r][c] * Li[r][c];
+            }
+        }
+        regular = fro < 1e8;              /* sigma_min > 1e-4 > eps = 1e-5: nothing would be truncated */
+    }
+    if (!regular) { pinv_step_svd(J, tw, 1e-5, dq); return; }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { double s = tw[i]; 
+#pragma unroll
+        for (int kk = 0; kk < i; kk++) s -= A[i][kk] * y[kk]; y[i] = s / A[i][i]; }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) { double s = y[i];
+#pragma unroll
+        for (int kk = i + 1; kk < 6; kk++) s -= A[kk][i] * y[kk]; y[i] = s / A[i][i]; }
+#pragma unroll
+    for (int c = 0; c < 12; c++) dq[c] = J[0][c] * y[0] + J[1][c] * y[1] + J[2][c] * y[2] + J[3][c] * y[3] + J[4][c] * y[4] + J[5][c] * y[5];
+}
+
+/* kdl::GD.  q: user order in/out.  returns converged; *iters = Newton iterations */
+__device__ __forceinline__ bool gd_project(const ckc_kin_dev& k, double* q, int max_iter, int* iters) {
+    double qc[12];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { qc[i] = q[i]; qc[6 + i] = q[11 - i]; }       /* kdl_class.cpp:73-78 */
+    qc[11] = -qc[11];
+    bool conv = false;
+    int it = 0;
+#pragma unroll 1
+    for (; it < max_iter; it++) {
+        double R[9], p[3], J0[6][12], tw[6], dq[12];
+        chain_fk<true>(k, qc, R, p, J0);
+        /* delta_twist = diff(f, target): vel = (D,0,0) - p ; rot = R * rotvec(R^T * I) */
+        tw[0] = k.D - p[0]; tw[1] = -p[1]; tw[2] = -p[2];
+        double Rt[9], rv[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) Rt[3 * a + b] = R[3 * b + a];
+        kdl_rotvec(Rt, rv);
+#pragma unroll
+        for (int a = 0; a < 3; a++) tw[3 + a] = R[3 * a] * rv[0] + R[3 * a + 1] * rv[1] + R[3 * a + 2] * rv[2];
+        newton_step(J0, p, tw, dq);
+#pragma unroll
+        for (int i = 0; i < 12; i++) qc[i] += dq[i];
+        bool eq = true;
+#pragma unroll
+        for (int i = 0; i < 6; i++) eq = eq && (fabs(tw[i]) < 1e-5);          /* Equal(delta_twist, Twist::Zero(), eps) */
+        if (eq) { conv = true; it++; break; }
+    }
+    *iters = it;
+    if (!conv) return false;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {                                           /* kdl_class.cpp:110-122 */
+        double v = (fabs(qc[i]) < 1e-4) ? 0.0 : qc[i];
+        v = fmod(v, 2 * CKC_PI_);
+        if (v > CKC_PI_) v -= 2 * CKC_PI_;
+        if (v < -CKC_PI_) v += 2 * CKC_PI_;
+        qc[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { q[i] = qc[i]; q[6 + i] = qc[11 - i]; }       /* :124-128 */
+    q[6] = -q[6];
+    return true;
+}
+
+/* check_relax_constraint StateValidityCheckerRX.cpp:105-135 */
+__device__ __forceinline__ double rx_residual(const ckc_kin_dev& k, const double* q) {
+    double qc[12], R[9], p[3];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { qc[i] = q[i]; qc[6 + i] = q[11 - i]; }
+    qc[11] = -qc[11];
+    chain_fk<false>(k, qc, R, p, nullptr);
+    const double dx = p[0] - k.D, dy = p[1], dz = p[2];
+    const double d = dx * dx + dy * dy + dz * dz;
+    const double roll = atan2(R[3], R[0]);
+    const double pitch = atan2(-R[6], sqrt(R[7] * R[7] + R[8] * R[8]));
+    const double yaw = atan2(R[7], R[8]);
+    const double a = (yaw * yaw + pitch * pitch + roll * roll);
+    const double Ka = (0.3 * 0.3) / (100.0 * 100.0);                           /* RX.h:230-233 */
+    return sqrt(Ka * d + a);
+}
+
+}  // namespace ckc
 #endif

@@ -604,3 +604,202 @@ extern "C" int ckc_measure_fma_peak(ckc_ctx* ctx, int precision, double* tflops)
     *tflops = best;
     return CKC_OK;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* GD / RX entry points                                                                                               */
+/* ---------------------------------------------------------------------------------------------------------------- */
+static int run_gd_chunk(ckc_ctx* ctx, int64_t n, const double* d_q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded, double* d_qout,
+                        ckc_layout lo, uint8_t* d_ok, uint8_t* d_conv, int32_t* d_iters, uint8_t* d_valid, bool collide, cudaStream_t st) {
+    CU(ctx->d_list.reserve((size_t)n * 4));
+    CU(cudaMemsetAsync(p_list_count(ctx), 0, 4, st));
+    ckc_launch_gd_project(ctx->kin, n, d_q, li, seed, i0, seeded, d_qout, lo, d_ok, d_conv, d_iters, d_valid, collide ? ctx->d_list.as<int32_t>() : nullptr,
+                          p_list_count(ctx), ctx->d_ctr.as<ckc_counters_dev>(), st);
+    ctx->launches += 1;
+    ctx->host_stats.ik_calls += n;
+    CU(cudaGetLastError());
+    if (collide) return run_collision_stage(ctx, n, d_qout, lo, ctx->d_list.as<int32_t>(), p_list_count(ctx), nullptr, d_valid, nullptr, st);
+    return CKC_OK;
+}
+
+static int gd_host(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* ok, uint8_t* conv, int32_t* iters, uint8_t* valid, bool collide) {
+    if (!ctx || n < 0 || (n > 0 && !q)) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_qout.reserve((size_t)c * 96)); CU(ctx->d_ok.reserve((size_t)c)); CU(ctx->d_valid.reserve((size_t)c));
+        CU(ctx->d_aux.reserve((size_t)c)); CU(ctx->d_aux2.reserve((size_t)c * 4));
+        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        int rc = run_gd_chunk(ctx, c, ctx->d_qin.as<double>(), AOS, 0, 0, 0, ctx->d_qout.as<double>(), AOS, ctx->d_ok.as<uint8_t>(), ctx->d_aux.as<uint8_t>(),
+                              ctx->d_aux2.as<int32_t>(), ctx->d_valid.as<uint8_t>(), collide, st);
+        if (rc) return rc;
+        if (q_out) CU(cudaMemcpyAsync(q_out + off * 12, ctx->d_qout.p, (size_t)c * 96, cudaMemcpyDeviceToHost, st));
+        if (ok) CU(cudaMemcpyAsync(ok + off, ctx->d_ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (conv) CU(cudaMemcpyAsync(conv + off, ctx->d_aux.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (iters) CU(cudaMemcpyAsync(iters + off, ctx->d_aux2.p, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+        if (valid) CU(cudaMemcpyAsync(valid + off, ctx->d_valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return CKC_OK;
+}
+
+extern "C" int ckc_gd_project(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* ok, uint8_t* converged, int32_t* iters) {
+    return gd_host(ctx, n, q, q_out, ok, converged, iters, nullptr, false);
+}
+extern "C" int ckc_gd_validate(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* valid) {
+    if (!valid) return fail(ctx, CKC_ERR_ARG, "valid must not be NULL");
+    if (ctx) ctx->host_stats.is_valid_calls += n;
+    return gd_host(ctx, n, q, q_out, nullptr, nullptr, nullptr, valid, true);
+}
+
+extern "C" int ckc_gd_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, double* d_q_out, uint8_t* d_valid, void* stream) {
+    if (!ctx || n < 0 || !d_q || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* qo = d_q_out;
+    if (!qo) { CU(ctx->d_qout.reserve((size_t)n * 96)); qo = ctx->d_qout.as<double>(); }
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        ckc_layout l = { 1, n };
+        int rc = run_gd_chunk(ctx, c, d_q + off, l, 0, 0, 0, qo + off, l, nullptr, nullptr, nullptr, d_valid + off, true, st);
+        if (rc) return rc;
+    }
+    return CKC_OK;
+}
+
+extern "C" int ckc_sgd_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out, uint8_t* d_ok, uint8_t* d_valid, void* stream) {
+    if (!ctx || n < 0 || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        double* qo; ckc_layout l;
+        if (d_q_out) { qo = d_q_out + off; l = soa(n); }
+        else { CU(ctx->d_qout.reserve((size_t)c * 96)); qo = ctx->d_qout.as<double>(); l = soa(c); }
+        int rc = run_gd_chunk(ctx, c, nullptr, l, seed, i0 + (uint64_t)off, 1, qo, l, d_ok ? d_ok + off : nullptr, nullptr, nullptr, d_valid + off, true, st);
+        if (rc) return rc;
+    }
+    return CKC_OK;
+}
+
+extern "C" int ckc_rx_validate(ckc_ctx* ctx, int64_t n, const double* q, double epsilon, uint8_t* valid, double* resid) {
+    if (!ctx || n < 0 || (n > 0 && (!q || !valid))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->host_stats.is_valid_calls += n;
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_valid.reserve((size_t)c)); CU(ctx->d_aux2.reserve((size_t)c * 8)); CU(ctx->d_list.reserve((size_t)c * 4));
+        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(p_list_count(ctx), 0, 4, st));
+        ckc_launch_rx_check(ctx->kin, c, ctx->d_qin.as<double>(), AOS, epsilon, nullptr, ctx->d_aux2.as<double>(), ctx->d_valid.as<uint8_t>(),
+                            ctx->d_list.as<int32_t>(), p_list_count(ctx), st);
+        ctx->launches++; ctx->host_stats.ik_calls += c;
+        CU(cudaGetLastError());
+        int rc = run_collision_stage(ctx, c, ctx->d_qin.as<double>(), AOS, ctx->d_list.as<int32_t>(), p_list_count(ctx), nullptr, ctx->d_valid.as<uint8_t>(), nullptr, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(valid + off, ctx->d_valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (resid) CU(cudaMemcpyAsync(resid + off, ctx->d_aux2.p, (size_t)c * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return CKC_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* RBS entry points                                                                                                   */
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* grow a device buffer keeping its contents */
+static cudaError_t reserve_keep(dev_buf& b, size_t bytes, size_t used, cudaStream_t st) {
+    if (bytes <= b.cap) return cudaSuccess;
+    size_t ncap = std::max(bytes, b.cap + b.cap / 2);
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess) return e;
+    if (b.p && used) { e = cudaMemcpyAsync(np, b.p, used, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; e = cudaStreamSynchronize(st); if (e != cudaSuccess) return e; }
+    if (b.p) cudaFree(b.p);
+    b.p = np; b.cap = ncap;
+    return cudaSuccess;
+}
+
+static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa, const double* qb, const int8_t* ac, const int8_t* ik,
+                    uint8_t* ok, int32_t* nchecks) {
+    if (!ctx || n_edges < 0 || n_edges > (1 << 28) || (n_edges > 0 && (!qa || !qb || !ok || (flavour == 0 && !ik)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    if (n_edges == 0) return CKC_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int ne = (int)n_edges;
+    dev_buf seg[2], cand, pool, eok, nck, hit, eac, eik;
+    struct cleanup { dev_buf* b[9]; ~cleanup() { for (dev_buf* x : b) x->release(); } } guard = { { &seg[0], &seg[1], &cand, &pool, &eok, &nck, &hit, &eac, &eik } };
+    int64_t seg_cap = std::max<int64_t>(2 * (int64_t)ne, 1024);
+    CU(seg[0].reserve((size_t)seg_cap * 16)); CU(seg[1].reserve((size_t)seg_cap * 16)); CU(cand.reserve((size_t)seg_cap * 8));
+    CU(pool.reserve((size_t)(2 * (int64_t)ne + seg_cap) * 96));
+    CU(eok.reserve(ne)); CU(nck.reserve((size_t)ne * 4)); CU(eac.reserve(ne)); CU(eik.reserve(ne));
+    /* endpoints interleaved: node 2e = a, node 2e+1 = b */
+    CU(cudaMemcpy2DAsync(pool.p, 192, qa, 96, 96, ne, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpy2DAsync((char*)pool.p + 96, 192, qb, 96, 96, ne, cudaMemcpyHostToDevice, st));
+    if (ac) CU(cudaMemcpyAsync(eac.p, ac, ne, cudaMemcpyHostToDevice, st));
+    if (ik) CU(cudaMemcpyAsync(eik.p, ik, ne, cudaMemcpyHostToDevice, st));
+    int32_t* d_cnt = ctx->d_small.as<int32_t>() + 8;       /* [0] candidates, [1] next segments */
+    int cur = 0;
+    int64_t nseg = ne, nnodes = 2 * (int64_t)ne;
+    auto make = [&](int c) {
+        ckc_rbs_dev r;
+        r.nodes = pool.as<double>();
+        int32_t* s0 = seg[c].as<int32_t>(); int32_t* s1 = seg[1 - c].as<int32_t>();
+        const int64_t cap0 = (int64_t)(seg[c].cap / 16), cap1 = (int64_t)(seg[1 - c].cap / 16);
+        r.seg_a = s0; r.seg_b = s0 + cap0; r.seg_edge = s0 + 2 * cap0; r.seg_depth = s0 + 3 * cap0;
+        r.next_a = s1; r.next_b = s1 + cap1; r.next_edge = s1 + 2 * cap1; r.next_depth = s1 + 3 * cap1;
+        r.cand_node = cand.as<int32_t>(); r.cand_seg = cand.as<int32_t>() + (int64_t)(cand.cap / 8);
+        r.cand_count = d_cnt; r.next_count = d_cnt + 1;
+        r.edge_ok = eok.as<uint8_t>(); r.nchecks = nck.as<int32_t>();
+        r.edge_ac = ac ? eac.as<int8_t>() : nullptr; r.edge_ik = eik.as<int8_t>();
+        r.tol = 0.05; r.max_depth = 150;                    /* StateValidityCheckerPCS.h:218-220 */
+        return r;
+    };
+    ckc_launch_rbs_init(make(cur), ne, st);
+    ctx->launches++;
+    int rounds = 0;
+    while (nseg > 0) {
+        /* capacity for this level: <= nseg new nodes / candidates, <= 2 nseg next segments */
+        if ((int64_t)(seg[1 - cur].cap / 16) < 2 * nseg) { seg[1 - cur].release(); CU(seg[1 - cur].reserve((size_t)(2 * nseg + 1024) * 16)); }
+        if ((int64_t)(cand.cap / 8) < nseg) { cand.release(); CU(cand.reserve((size_t)(nseg + 1024) * 8)); }
+        CU(reserve_keep(pool, (size_t)(nnodes + nseg) * 96, (size_t)nnodes * 96, st));
+        CU(hit.reserve((size_t)(nnodes + nseg)));
+        ckc_rbs_dev r = make(cur);
+        CU(cudaMemsetAsync(d_cnt, 0, 8, st));
+        ckc_launch_rbs_expand(ctx->kin, r, flavour, (int)nseg, (int)nnodes, st);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        /* collision on the surviving midpoints (work list = candidate node ids), in bounded sub-batches */
+        int32_t h[2];
+        CU(cudaMemcpyAsync(h, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const int64_t sub = 1 << 21;
+        for (int64_t off = 0; off < h[0]; off += sub) {
+            int rc = run_collision_stage(ctx, std::min<int64_t>(sub, h[0] - off), pool.as<double>(), AOS, r.cand_node + off, nullptr, hit.as<uint8_t>(), nullptr, nullptr, st);
+            if (rc) return rc;
+        }
+        ckc_launch_rbs_push(r, h[0], d_cnt, hit.as<uint8_t>(), st);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(h, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ctx->host_stats.is_valid_calls += h[0];
+        nnodes += h[0];
+        nseg = h[1];
+        cur = 1 - cur;
+        if (++rounds > 200) return fail(ctx, CKC_ERR_CAPACITY, "RBS did not terminate");
+    }
+    CU(cudaMemcpyAsync(ok, eok.p, ne, cudaMemcpyDeviceToHost, st));
+    if (nchecks) CU(cudaMemcpyAsync(nchecks, nck.p, (size_t)ne * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return CKC_OK;
+}
+
+extern "C" int ckc_pcs_check_motion_rbs(ckc_ctx* ctx, int64_t n_edges, const double* qa, const double* qb, const int8_t* ac, const int8_t* ik,
+                                        uint8_t* ok, int32_t* nchecks) {
+    return rbs_host(ctx, 0, n_edges, qa, qb, ac, ik, ok, nchecks);
+}
+extern "C" int ckc_gd_check_motion_rbs(ckc_ctx* ctx, int64_t n_edges, const double* qa, const double* qb, uint8_t* ok, int32_t* nchecks) {
+    return rbs_host(ctx, 1, n_edges, qa, qb, nullptr, nullptr, ok, nchecks);
+}

@@ -66,7 +66,24 @@ struct ckc_counters_dev {       /* device-side accumulators, one struct per cont
         gd_iterations, is_valid_calls;
 };
 
+/* RBS frontier state (device pointers). Nodes = configurations (AoS, 12 doubles); a segment joins two nodes. */
+struct ckc_rbs_dev {
+    double* nodes;                       /* node pool: [2*n_edges endpoints | midpoints ...] */
+    int32_t *seg_a, *seg_b, *seg_edge, *seg_depth;          /* current level */
+    int32_t *next_a, *next_b, *next_edge, *next_depth;      /* next level */
+    int32_t *cand_node, *cand_seg;       /* midpoints that passed projection and await the collision check */
+    int32_t *cand_count, *next_count;
+    uint8_t* edge_ok;                    /* per edge: 1 until any node of its bisection tree is invalid */
+    int32_t* nchecks;                    /* per edge: isValidRBS evaluations (may be NULL) */
+    const int8_t *edge_ac, *edge_ik;     /* PCS flavour: active chain / IK branch per edge */
+    double tol;                          /* RBS_tol = 0.05 */
+    int max_depth;                       /* RBS_max_depth = 150 */
+};
+
 /* ---- launchers implemented in ckc_kernels.cu (all asynchronous on `st`) ---- */
+void ckc_launch_rbs_init(const ckc_rbs_dev& r, int n_edges, cudaStream_t st);
+void ckc_launch_rbs_expand(const ckc_kin_dev& kin, const ckc_rbs_dev& r, int flavour, int nseg, int node_base, cudaStream_t st);
+void ckc_launch_rbs_push(const ckc_rbs_dev& r, int max_cand, const int32_t* d_ncand, const uint8_t* hit, cudaStream_t st);
 struct ckc_launch_cfg { int num_sms; };
 
 /* K1: projection. src == NULL => generate S-PCS samples (seed, i0).  Writes q_out (layout lo), ok, zeroes valid,

@@ -421,3 +421,188 @@ void ckc_launch_transpose(const double* src, ckc_layout ls, double* dst, ckc_lay
     if (n <= 0) return;
     k_transpose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, ls, dst, ld, n);
 }
+
+/* ================================================================================================================ */
+/* GD / RX flavours                                                                                                   */
+/* ================================================================================================================ */
+/* K5: one thread per sample -- Newton-Raphson closure projection on the 12-joint chain (kdl::GD), joint limits,
+ * append of the surviving samples to the collision work list */
+__global__ void __launch_bounds__(128)
+k_gd_project(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, ckc_layout li, uint64_t key, uint64_t i0, int seeded,
+             double* __restrict__ q_out, ckc_layout lo, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ conv_out,
+             int32_t* __restrict__ iters_out, uint8_t* __restrict__ valid_out, int32_t* __restrict__ list, int32_t* list_count,
+             ckc_counters_dev* ctr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    int it = 0;
+    if (i < n) {
+        double q[12];
+        if (seeded) {
+#pragma unroll
+            for (int j = 0; j < 12; j++) q[j] = -CKC_PI_ + uniform01(key, i0 + (uint64_t)i, j) * (2 * CKC_PI_);   /* GD.cpp:60-61 */
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; j++) q[j] = q_in[i * li.stride_i + j * li.stride_j];
+        }
+        const bool conv = gd_project(kin, q, 10000, &it);
+        ok = conv && within_limits(kin, q);                        /* kdl_class.cpp:130 */
+        if (q_out) {
+#pragma unroll
+            for (int j = 0; j < 12; j++) q_out[i * lo.stride_i + j * lo.stride_j] = q[j];
+        }
+        if (ok_out) ok_out[i] = ok ? 1 : 0;
+        if (conv_out) conv_out[i] = conv ? 1 : 0;
+        if (iters_out) iters_out[i] = it;
+        if (valid_out) valid_out[i] = 0;
+    }
+    append_to_list(ok, (int32_t)i, list, list_count);
+    if (ctr) {
+        unsigned long long s = (unsigned long long)it;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&ctr->gd_iterations, s); if (m) atomicAdd(&ctr->ik_feasible, (unsigned long long)__popc(m)); }
+    }
+}
+
+void ckc_launch_gd_project(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded,
+                           double* q_out, ckc_layout lo, uint8_t* ok, uint8_t* converged, int32_t* iters, uint8_t* valid,
+                           int32_t* list, int32_t* list_count, ckc_counters_dev* ctr, cudaStream_t st) {
+    if (n <= 0) return;
+    k_gd_project<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kin, n, q, li, mix64(seed), i0, seeded, q_out, lo, ok, converged, iters, valid,
+                                                              list, list_count, ctr);
+}
+
+/* RX: relaxed-constraint residual + joint limits; survivors go to the collision work list */
+__global__ void __launch_bounds__(256)
+k_rx_check(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, ckc_layout l, double eps, uint8_t* __restrict__ ok_out,
+           double* __restrict__ resid, uint8_t* __restrict__ valid_out, int32_t* __restrict__ list, int32_t* list_count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (i < n) {
+        double q[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) q[j] = q_in[i * l.stride_i + j * l.stride_j];
+        const double r = rx_residual(kin, q);
+        ok = (r < eps) && within_limits(kin, q);                   /* RX.cpp:209: !check_relax_constraint || !check_angle_limits || collision */
+        if (resid) resid[i] = r;
+        if (ok_out) ok_out[i] = ok ? 1 : 0;
+        if (valid_out) valid_out[i] = 0;
+    }
+    append_to_list(ok, (int32_t)i, list, list_count);
+}
+
+void ckc_launch_rx_check(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, double eps, uint8_t* ok, double* resid,
+                         uint8_t* valid, int32_t* list, int32_t* list_count, cudaStream_t st) {
+    if (n <= 0) return;
+    k_rx_check<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kin, n, q, l, eps, ok, resid, valid, list, list_count);
+}
+
+/* ================================================================================================================ */
+/* K4: recursive bi-section (checkMotionRBS) as a level-synchronous frontier                                          */
+/*   StateValidityCheckerPCS.cpp:486-511, StateValidityCheckerGD.cpp:214-241.  The reference recurses depth first and   */
+/*   stops at the first invalid midpoint; the boolean it returns is "every node of the bisection tree is valid and no  */
+/*   branch passes depth 150", which is order independent, so all segments of one level are evaluated together.        */
+/* ================================================================================================================ */
+/* flavour 0 = PCS (analytic projection of the passive arm), 1 = GD (Newton projection of all 12 joints) */
+template <int kFlavour>
+__global__ void __launch_bounds__(128)
+k_rbs_expand(const ckc_kin_dev kin, const ckc_rbs_dev r, int nseg, int node_base) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool cand = false;
+    int my_node = -1;
+    double m[12];
+    if (s < nseg) {
+        const int e = r.seg_edge[s];
+        if (r.edge_ok[e]) {
+            const double* a = r.nodes + 12 * (int64_t)r.seg_a[s];
+            const double* b = r.nodes + 12 * (int64_t)r.seg_b[s];
+            double sum = 0;
+#pragma unroll
+            for (int j = 0; j < 12; j++) { const double d = a[j] - b[j]; sum += d * d; m[j] = (a[j] + b[j]) / 2; }
+            if (!(sqrt(sum) < r.tol)) {                               /* d < RBS_tol: this branch is done */
+                if (r.seg_depth[s] > r.max_depth) r.edge_ok[e] = 0;   /* recursion_depth > RBS_max_depth */
+                else {
+                    if (r.nchecks) atomicAdd(&r.nchecks[e], 1);       /* one isValidRBS evaluation */
+                    bool ok;
+                    if (kFlavour == 0) {
+                        double qp[6];
+                        const int ac = r.edge_ac ? r.edge_ac[e] : 0, sol = r.edge_ik[e] & 7;
+                        if (ac == 0) { ok = project_passive(kin, m, 0, sol, qp); if (ok) { for (int j = 0; j < 6; j++) m[6 + j] = qp[j]; } }
+                        else { ok = project_passive(kin, m + 6, 1, sol, qp); if (ok) { for (int j = 0; j < 6; j++) m[j] = qp[j]; } }
+                    } else {
+                        int it;
+                        ok = gd_project(kin, m, 10000, &it) && within_limits(kin, m);
+                    }
+                    if (ok) cand = true; else r.edge_ok[e] = 0;
+                }
+            }
+        }
+    }
+    /* warp-aggregated allocation of one new node + one candidate slot per surviving midpoint */
+    const unsigned mk = __ballot_sync(0xffffffffu, cand);
+    if (mk) {
+        const int lane = threadIdx.x & 31, leader = __ffs(mk) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(r.cand_count, __popc(mk));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (cand) {
+            const int c = base + __popc(mk & ((1u << lane) - 1));
+            my_node = node_base + c;
+            double* dst = r.nodes + 12 * (int64_t)my_node;
+#pragma unroll
+            for (int j = 0; j < 12; j++) dst[j] = m[j];
+            r.cand_node[c] = my_node;
+            r.cand_seg[c] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rbs_push(const ckc_rbs_dev r, const int32_t* __restrict__ d_ncand, const uint8_t* __restrict__ hit) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ncand = *d_ncand;
+    bool push = false;
+    int s = 0, node = 0;
+    if (c < ncand) {
+        s = r.cand_seg[c]; node = r.cand_node[c];
+        const int e = r.seg_edge[s];
+        if (hit[node]) r.edge_ok[e] = 0;
+        else push = true;      /* edge_ok may still be cleared by a sibling; stale segments are dropped at the next expand */
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, push);
+    if (mk) {
+        const int lane = threadIdx.x & 31, leader = __ffs(mk) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(r.next_count, 2 * __popc(mk));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (push) {
+            const int o = base + 2 * __popc(mk & ((1u << lane) - 1));
+            const int e = r.seg_edge[s], d = r.seg_depth[s] + 1;
+            r.next_a[o] = r.seg_a[s]; r.next_b[o] = node; r.next_edge[o] = e; r.next_depth[o] = d;
+            r.next_a[o + 1] = node; r.next_b[o + 1] = r.seg_b[s]; r.next_edge[o + 1] = e; r.next_depth[o + 1] = d;
+        }
+    }
+}
+
+__global__ void k_rbs_init(const ckc_rbs_dev r, int n_edges) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    r.seg_a[e] = 2 * e; r.seg_b[e] = 2 * e + 1; r.seg_edge[e] = e; r.seg_depth[e] = 0;
+    r.edge_ok[e] = 1;
+    if (r.nchecks) r.nchecks[e] = 0;
+}
+
+void ckc_launch_rbs_init(const ckc_rbs_dev& r, int n_edges, cudaStream_t st) {
+    if (n_edges <= 0) return;
+    k_rbs_init<<<(n_edges + 255) / 256, 256, 0, st>>>(r, n_edges);
+}
+void ckc_launch_rbs_expand(const ckc_kin_dev& kin, const ckc_rbs_dev& r, int flavour, int nseg, int node_base, cudaStream_t st) {
+    if (nseg <= 0) return;
+    if (flavour == 0) k_rbs_expand<0><<<(nseg + 127) / 128, 128, 0, st>>>(kin, r, nseg, node_base);
+    else k_rbs_expand<1><<<(nseg + 127) / 128, 128, 0, st>>>(kin, r, nseg, node_base);
+}
+void ckc_launch_rbs_push(const ckc_rbs_dev& r, int max_cand, const int32_t* d_ncand, const uint8_t* hit, cudaStream_t st) {
+    if (max_cand <= 0) return;
+    k_rbs_push<<<(max_cand + 255) / 256, 256, 0, st>>>(r, d_ncand, hit);
+}
