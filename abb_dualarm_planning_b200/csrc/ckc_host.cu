@@ -54,6 +54,27 @@ struct ckc_ctx {
     dev_buf d_qb, d_edge;               /* RBS */
     int64_t launches = 0;
     ckc_stats host_stats;
+    /* optional per-stage CUDA-event timing */
+    bool stage_timing = false;
+    struct stage_ev { int stage; cudaEvent_t e0, e1; };
+    std::vector<stage_ev> pending;
+    double stage_ms[4] = { 0, 0, 0, 0 };
+    int64_t stage_n[4] = { 0, 0, 0, 0 };
+};
+
+/* RAII helper: records an event pair around a stage when timing is enabled */
+struct stage_scope {
+    ckc_ctx* c; cudaStream_t st; int stage; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    stage_scope(ckc_ctx* c_, cudaStream_t st_, int stage_) : c(c_), st(st_), stage(stage_) {
+        if (!c->stage_timing) return;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+        cudaEventRecord(e0, st);
+    }
+    ~stage_scope() {
+        if (!e0) return;
+        cudaEventRecord(e1, st);
+        c->pending.push_back({ stage, e0, e1 });
+    }
 };
 
 static int fail(ckc_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
@@ -432,10 +453,12 @@ static int run_collision_stage(ckc_ctx* ctx, int64_t m_max, const double* d_q, c
     CU(ctx->d_frames.reserve((size_t)m_max * CKC_FRAME_DOUBLES * 8));
     CU(ctx->d_ovf.reserve((size_t)m_max * 4));
     CU(ctx->d_bigstack.reserve((size_t)16 * 8 * 65536 * 4));
-    ckc_launch_link_frames(ctx->world, d_q, l, d_list, d_m, m_max, ctx->d_frames.as<double>(), st);
+    { stage_scope ts(ctx, st, 1);
+      ckc_launch_link_frames(ctx->world, d_q, l, d_list, d_m, m_max, ctx->d_frames.as<double>(), st); }
     ckc_launch_cfg cfg = { ctx->num_sms };
-    ckc_launch_collide(ctx->world, cfg, ctx->d_frames.as<double>(), d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, p_work_counter(ctx),
-                       ctx->d_ovf.as<int32_t>(), p_ovf_count(ctx), ctx->d_bigstack.as<uint32_t>(), ctx->d_ctr.as<ckc_counters_dev>(), st);
+    { stage_scope ts(ctx, st, 2);
+      ckc_launch_collide(ctx->world, cfg, ctx->d_frames.as<double>(), d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, p_work_counter(ctx),
+                         ctx->d_ovf.as<int32_t>(), p_ovf_count(ctx), ctx->d_bigstack.as<uint32_t>(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
     ctx->launches += 3;
     CU(cudaGetLastError());
     return CKC_OK;
@@ -446,8 +469,9 @@ static int run_pcs_chunk(ckc_ctx* ctx, int64_t n, const double* d_q, ckc_layout 
                          uint64_t i0, int seeded, double* d_qout, ckc_layout lo, uint8_t* d_ok, uint8_t* d_valid, bool collide, cudaStream_t st) {
     CU(ctx->d_list.reserve((size_t)n * 4));
     CU(cudaMemsetAsync(p_list_count(ctx), 0, 4, st));
-    ckc_launch_pcs_project(ctx->kin, n, d_q, li, d_ac, d_ik, seed, i0, seeded, d_qout, lo, d_ok, d_valid, collide ? ctx->d_list.as<int32_t>() : nullptr,
-                           p_list_count(ctx), ctx->d_ctr.as<ckc_counters_dev>(), st);
+    { stage_scope ts(ctx, st, 0);
+      ckc_launch_pcs_project(ctx->kin, n, d_q, li, d_ac, d_ik, seed, i0, seeded, d_qout, lo, d_ok, d_valid, collide ? ctx->d_list.as<int32_t>() : nullptr,
+                             p_list_count(ctx), ctx->d_ctr.as<ckc_counters_dev>(), st); }
     ctx->launches += 1;
     ctx->host_stats.ik_calls += n;
     CU(cudaGetLastError());
@@ -612,8 +636,9 @@ static int run_gd_chunk(ckc_ctx* ctx, int64_t n, const double* d_q, ckc_layout l
                         ckc_layout lo, uint8_t* d_ok, uint8_t* d_conv, int32_t* d_iters, uint8_t* d_valid, bool collide, cudaStream_t st) {
     CU(ctx->d_list.reserve((size_t)n * 4));
     CU(cudaMemsetAsync(p_list_count(ctx), 0, 4, st));
-    ckc_launch_gd_project(ctx->kin, n, d_q, li, seed, i0, seeded, d_qout, lo, d_ok, d_conv, d_iters, d_valid, collide ? ctx->d_list.as<int32_t>() : nullptr,
-                          p_list_count(ctx), ctx->d_ctr.as<ckc_counters_dev>(), st);
+    { stage_scope ts(ctx, st, 0);
+      ckc_launch_gd_project(ctx->kin, n, d_q, li, seed, i0, seeded, d_qout, lo, d_ok, d_conv, d_iters, d_valid, collide ? ctx->d_list.as<int32_t>() : nullptr,
+                            p_list_count(ctx), ctx->d_ctr.as<ckc_counters_dev>(), st); }
     ctx->launches += 1;
     ctx->host_stats.ik_calls += n;
     CU(cudaGetLastError());
@@ -767,7 +792,8 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
         CU(hit.reserve((size_t)(nnodes + nseg)));
         ckc_rbs_dev r = make(cur);
         CU(cudaMemsetAsync(d_cnt, 0, 8, st));
-        ckc_launch_rbs_expand(ctx->kin, r, flavour, (int)nseg, (int)nnodes, st);
+        { stage_scope ts(ctx, st, 3);
+          ckc_launch_rbs_expand(ctx->kin, r, flavour, (int)nseg, (int)nnodes, st); }
         ctx->launches++;
         CU(cudaGetLastError());
         /* collision on the surviving midpoints (work list = candidate node ids), in bounded sub-batches */
@@ -779,7 +805,8 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
             int rc = run_collision_stage(ctx, std::min<int64_t>(sub, h[0] - off), pool.as<double>(), AOS, r.cand_node + off, nullptr, hit.as<uint8_t>(), nullptr, nullptr, st);
             if (rc) return rc;
         }
-        ckc_launch_rbs_push(r, h[0], d_cnt, hit.as<uint8_t>(), st);
+        { stage_scope ts(ctx, st, 3);
+          ckc_launch_rbs_push(r, h[0], d_cnt, hit.as<uint8_t>(), st); }
         ctx->launches++;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(h, d_cnt, 8, cudaMemcpyDeviceToHost, st));
@@ -802,4 +829,32 @@ extern "C" int ckc_pcs_check_motion_rbs(ckc_ctx* ctx, int64_t n_edges, const dou
 }
 extern "C" int ckc_gd_check_motion_rbs(ckc_ctx* ctx, int64_t n_edges, const double* qa, const double* qb, uint8_t* ok, int32_t* nchecks) {
     return rbs_host(ctx, 1, n_edges, qa, qb, nullptr, nullptr, ok, nchecks);
+}
+
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* per-stage timing                                                                                                   */
+/* ---------------------------------------------------------------------------------------------------------------- */
+extern "C" int ckc_set_stage_timing(ckc_ctx* ctx, int enable) {
+    if (!ctx) return CKC_ERR_ARG;
+    ctx->stage_timing = enable != 0;
+    for (auto& p : ctx->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    ctx->pending.clear();
+    for (int i = 0; i < 4; i++) { ctx->stage_ms[i] = 0; ctx->stage_n[i] = 0; }
+    return CKC_OK;
+}
+
+extern "C" int ckc_get_stage_times(ckc_ctx* ctx, double ms[4], int64_t launches[4]) {
+    if (!ctx || !ms || !launches) return CKC_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    for (auto& p : ctx->pending) {
+        CU(cudaEventSynchronize(p.e1));
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, p.e0, p.e1));
+        ctx->stage_ms[p.stage] += t; ctx->stage_n[p.stage]++;
+        cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+    }
+    ctx->pending.clear();
+    for (int i = 0; i < 4; i++) { ms[i] = ctx->stage_ms[i]; launches[i] = ctx->stage_n[i]; }
+    return CKC_OK;
 }

@@ -127,6 +127,11 @@ int ckc_spcs_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64
 int ckc_gd_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, double* d_q_out, uint8_t* d_valid, void* stream);
 int ckc_sgd_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out,
                                 uint8_t* d_ok, uint8_t* d_valid, void* stream);
+/* Per-stage device timing (CUDA events recorded on the launching stream around each kernel stage; resolved lazily).
+ * stage 0 = projection kernel (PCS / GD / RX), 1 = link frames, 2 = collision (both passes), 3 = RBS expand/push.
+ * ms[s] = accumulated device milliseconds, launches[s] = number of timed stage executions since the last reset. */
+int ckc_set_stage_timing(ckc_ctx* ctx, int enable);
+int ckc_get_stage_times(ckc_ctx* ctx, double ms[4], int64_t launches[4]);
 /* FMA-chain peak probes for the roofline denominator (DESIGN.md "Measurement"): runs `iters` dependent-chain
  * FMAs per thread on every SM and returns the achieved TFLOP/s (2 flop per FMA). precision: 32 or 64 */
 int ckc_measure_fma_peak(ckc_ctx* ctx, int precision, double* tflops);
