@@ -1,6 +1,6 @@
 /*
  * ckc_internal.h -- data layout shared by the host side (ckc_host.cu) and the kernels (ckc_kernels.cu) of libckc.
- * Product code: must not include anything from oracle/.
+ * Product code: must not include anything of the CPU checker (the oracle directory).
  */
 #ifndef CKC_INTERNAL_H_
 #define CKC_INTERNAL_H_

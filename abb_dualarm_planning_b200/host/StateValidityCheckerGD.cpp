@@ -1,0 +1,158 @@
+/* StateValidityCheckerGD.cpp -- see the header.  Replaces validity_checkers/StateValidityChecker{GD,RX}.cpp. */
+#include "StateValidityCheckerGD.h"
+#include <cmath>
+
+void StateValidityChecker::init(int env) {
+    L = env == 1 ? ROD_LENGTH_ENV_I : ROD_LENGTH_ENV_II;
+    const int dl = 20, np = (int)(L / dl);
+    for (int i = 0; i <= np; i++) P.push_back({ (double)i * dl, 0, 0 });
+    q_solution.assign(12, 0); q_prev.assign(12, 0);
+    initiate_log_parameters();
+}
+void StateValidityChecker::initiate_log_parameters() {
+    IK_counter = 0; IK_time = 0; collisionCheck_counter = 0; collisionCheck_time = 0; isValid_counter = 0; sampling_time = 0; sampling_counter.assign(2, 0);
+}
+
+bool StateValidityChecker::GD(State q) {
+    IK_counter++;
+    clock_t b = clock();
+    double qo[12]; uint8_t ok = 0, conv = 0; int32_t it = 0;
+    ckc_gd_project(ckc_.ctx(), 1, q.data(), qo, &ok, &conv, &it);
+    if (conv) q_solution.assign(qo, qo + 12);          /* q_solution is only written when the solver converged (kdl_class.cpp:108-128) */
+    IK_time += double(clock() - b) / CLOCKS_PER_SEC;
+    return ok != 0;
+}
+bool StateValidityChecker::check_angle_limits(State q) { uint8_t ok = 0; ckc_check_angle_limits(ckc_.ctx(), 1, q.data(), &ok); return ok != 0; }
+int StateValidityChecker::collision_state(Matrix, State q1, State q2) {
+    collisionCheck_counter++;
+    clock_t b = clock();
+    double q[12]; ckc_pack(q1, q2, q); uint8_t hit = 1;
+    ckc_collide(ckc_.ctx(), 1, q, &hit);
+    collisionCheck_time += double(clock() - b) / CLOCKS_PER_SEC;
+    return hit;
+}
+
+#ifdef CKC_FLAVOUR_RX
+bool StateValidityChecker::check_relax_constraint(State q) {
+    IK_counter++;
+    uint8_t v = 0; double r = 0;
+    ckc_rx_validate(ckc_.ctx(), 1, q.data(), epsilon, &v, &r);
+    return r < epsilon;
+}
+bool StateValidityChecker::isValidRBS(State q) {
+    isValid_counter++; IK_counter++;
+    uint8_t v = 0;
+    ckc_rx_validate(ckc_.ctx(), 1, q.data(), epsilon, &v, nullptr);
+    return v != 0;
+}
+bool StateValidityChecker::check_project(const ob::State* state) { State q(12); retrieveStateVector(state, q); return isValidRBS(q); }
+bool StateValidityChecker::isValid(const ob::State* state) {
+    State q(12); retrieveStateVector(state, q);
+    if (!isValidRBS(q)) return false;
+    q_prev = q; return true;
+}
+void StateValidityChecker::isValidBatch(std::vector<State>& q, std::vector<unsigned char>& valid) {
+    const size_t m = q.size(); std::vector<double> in(12 * m); valid.assign(m, 0);
+    for (size_t i = 0; i < m; i++) for (int j = 0; j < 12; j++) in[12 * i + j] = q[i][j];
+    ckc_rx_validate(ckc_.ctx(), (int64_t)m, in.data(), epsilon, valid.data(), nullptr);
+    isValid_counter += (int)m;
+}
+State StateValidityChecker::sample_q() {
+    const int B = 4096; std::vector<double> q(12 * B); std::vector<uint8_t> v(B);
+    for (;;) {
+        for (int i = 0; i < 12 * B; i++) q[i] = -PI + (double)rand() / RAND_MAX * 2 * PI;
+        ckc_rx_validate(ckc_.ctx(), B, q.data(), epsilon, v.data(), nullptr);
+        for (int i = 0; i < B; i++) { if (v[i]) { sampling_counter[0]++; return State(q.begin() + 12 * i, q.begin() + 12 * i + 12); } sampling_counter[1]++; }
+    }
+}
+bool StateValidityChecker::checkMotionRBS(State s1, State s2, int recursion_depth, int ndc) {
+    /* RX keeps the midpoint as is (no projection): host recursion over single-sample device checks, reference order */
+    double d = normDistance(s1, s2);
+    if (d < RBS_tol) return true;
+    if (recursion_depth > RBS_max_depth) return false;
+    State mid(12); for (int i = 0; i < 12; i++) mid[i] = (s1[i] + s2[i]) / 2;
+    if (!isValidRBS(mid)) return false;
+    return checkMotionRBS(s1, mid, recursion_depth + 1, ndc) && checkMotionRBS(mid, s2, recursion_depth + 1, ndc);
+}
+void StateValidityChecker::checkMotionRBSBatch(const std::vector<State>& a, const std::vector<State>& b, std::vector<unsigned char>& ok) {
+    ok.assign(a.size(), 0);
+    for (size_t i = 0; i < a.size(); i++) ok[i] = checkMotionRBS(a[i], b[i], 0, 0);
+}
+#else
+bool StateValidityChecker::IKproject(State& q, bool includeObs) {
+    if (!GD(q)) return false;
+    q = get_GD_result();
+    State q1(6), q2(6); seperate_Vector(q, q1, q2);
+    if (includeObs && withObs && collision_state(P, q1, q2)) return false;
+    return true;
+}
+bool StateValidityChecker::IKproject(const ob::State* state, bool includeObs) {
+    State q(12); retrieveStateVector(state, q);
+    if (!IKproject(q, includeObs)) return false;
+    updateStateVector(state, q); return true;
+}
+bool StateValidityChecker::isValidRBS(State& q) {
+    isValid_counter++; IK_counter++;
+    double qo[12]; uint8_t v = 0;
+    ckc_gd_validate(ckc_.ctx(), 1, q.data(), qo, &v);
+    if (v) q.assign(qo, qo + 12);
+    return v != 0;
+}
+bool StateValidityChecker::isValid(const ob::State* state) {
+    State q(12); retrieveStateVector(state, q);
+    if (!isValidRBS(q)) return false;
+    updateStateVector(state, q); q_prev = q; return true;
+}
+void StateValidityChecker::isValidBatch(std::vector<State>& q, std::vector<unsigned char>& valid) {
+    const size_t m = q.size(); std::vector<double> in(12 * m), out(12 * m); valid.assign(m, 0);
+    for (size_t i = 0; i < m; i++) for (int j = 0; j < 12; j++) in[12 * i + j] = q[i][j];
+    ckc_gd_validate(ckc_.ctx(), (int64_t)m, in.data(), out.data(), valid.data());
+    for (size_t i = 0; i < m; i++) if (valid[i]) q[i].assign(out.begin() + 12 * i, out.begin() + 12 * i + 12);
+    isValid_counter += (int)m; IK_counter += (int)m;
+}
+State StateValidityChecker::sample_q() {                     /* GD.cpp:53-80, candidates validated a batch at a time */
+    const int B = 1024; std::vector<double> q(12 * B), qo(12 * B); std::vector<uint8_t> v(B);
+    clock_t sT = clock();
+    for (;;) {
+        for (int i = 0; i < 12 * B; i++) q[i] = -PI + (double)rand() / RAND_MAX * 2 * PI;
+        ckc_gd_validate(ckc_.ctx(), B, q.data(), qo.data(), v.data());
+        IK_counter += B;
+        for (int i = 0; i < B; i++) {
+            if (v[i]) { sampling_time += double(clock() - sT) / CLOCKS_PER_SEC; sampling_counter[0]++; return State(qo.begin() + 12 * i, qo.begin() + 12 * i + 12); }
+            sampling_counter[1]++;
+        }
+    }
+}
+bool StateValidityChecker::checkMotionRBS(State s1, State s2, int, int) {
+    uint8_t ok = 0; int32_t nc = 0;
+    ckc_gd_check_motion_rbs(ckc_.ctx(), 1, s1.data(), s2.data(), &ok, &nc);
+    isValid_counter += nc;
+    return ok != 0;
+}
+void StateValidityChecker::checkMotionRBSBatch(const std::vector<State>& a, const std::vector<State>& b, std::vector<unsigned char>& ok) {
+    const size_t m = a.size(); std::vector<double> qa(12 * m), qb(12 * m); std::vector<int32_t> nc(m); ok.assign(m, 0);
+    for (size_t i = 0; i < m; i++) for (int j = 0; j < 12; j++) { qa[12 * i + j] = a[i][j]; qb[12 * i + j] = b[i][j]; }
+    ckc_gd_check_motion_rbs(ckc_.ctx(), (int64_t)m, qa.data(), qb.data(), ok.data(), nc.data());
+    for (size_t i = 0; i < m; i++) isValid_counter += nc[i];
+}
+#endif
+
+bool StateValidityChecker::checkMotionRBS(const ob::State* s1, const ob::State* s2) {
+    State q1(12), q2(12); retrieveStateVector(s1, q1); retrieveStateVector(s2, q2);
+    return checkMotionRBS(q1, q2, 0, 0);
+}
+void StateValidityChecker::retrieveStateVector(const ob::State* state, State& q) {
+    const ob::RealVectorStateSpace::StateType* S = state->as<ob::RealVectorStateSpace::StateType>();
+    for (unsigned i = 0; i < 12; i++) q[i] = S->values[i];
+}
+void StateValidityChecker::retrieveStateVector(const ob::State* state, State& q1, State& q2) {
+    const ob::RealVectorStateSpace::StateType* S = state->as<ob::RealVectorStateSpace::StateType>();
+    for (unsigned i = 0; i < 6; i++) { q1[i] = S->values[i]; q2[i] = S->values[i + 6]; }
+}
+void StateValidityChecker::updateStateVector(const ob::State* state, State q) {
+    const ob::RealVectorStateSpace::StateType* S = state->as<ob::RealVectorStateSpace::StateType>();
+    for (unsigned i = 0; i < 12; i++) S->values[i] = q[i];
+}
+void StateValidityChecker::seperate_Vector(State q, State& q1, State& q2) { for (size_t i = 0; i < q.size() / 2; i++) { q1[i] = q[i]; q2[i] = q[i + q.size() / 2]; } }
+State StateValidityChecker::join_Vectors(State q1, State q2) { State q(q1); q.insert(q.end(), q2.begin(), q2.end()); return q; }
+double StateValidityChecker::normDistance(State a1, State a2) { double s = 0; for (size_t i = 0; i < a1.size(); i++) s += pow(a1[i] - a2[i], 2); return sqrt(s); }

@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--workload", default="gd", choices=["gd", "pcs", "rbs"])
     ap.add_argument("--samples", type=int, default=0, help="units per GPU per step (default: 1e6 samples; 2e4 edges for rbs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary PCS / RBS measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     return ap.parse_args()
 
 
@@ -304,7 +305,7 @@ def run_native(args):
         out["path_stats"] = {"edges_ok_fraction": okc / n, "checks_per_edge": stats["collision_calls"] / (K * n)}
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(wl, cores=1, budget_s=12.0)
 
     # ---- secondary measurements on the other workloads (not the headline, same run, same box) ----

@@ -1,0 +1,85 @@
+"""GPU: the C++ drop-in StateValidityChecker classes (abb_dualarm_planning_b200/host) driven the way the reference's own
+tests/test_rbs_pcs.cpp / test_rbs_gd.cpp drive the original classes, every answer compared with the CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(REPO, "abb_dualarm_planning_b200", "host")
+PACK = os.path.join(REPO, "abb_dualarm_planning_b200", "data", "meshes.ckcmesh")
+
+
+def _run(binary, inp, out):
+    env = dict(os.environ, CKC_MESH_PATH=PACK)
+    r = subprocess.run([os.path.join(HOST, binary), inp, out], env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(out))
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_pcs_dropin_class(tmp_path, oracle, gold):
+    from abb_dualarm_planning_b200 import sampling
+    g = gold("rbs.npz")
+    n = 60
+    q, ik = sampling.sample_pcs(31, 0, 400)
+    rows = []
+    for i in range(n):                      # valid RBS endpoints from the golden set + random (mostly infeasible) samples
+        rows.append(np.concatenate([g["qa"][i], [g["ik"][i]], g["qb"][i]]))
+    for i in range(n):
+        rows.append(np.concatenate([q[i], [ik[i]], q[i + 100]]))
+    rows = np.array(rows)
+    inp, out = str(tmp_path / "in.txt"), str(tmp_path / "out.txt")
+    os.makedirs(tmp_path / "paths", exist_ok=True)
+    with open(inp, "w") as f:
+        f.write("%d\n" % len(rows))
+        for r in rows:
+            f.write(" ".join(repr(float(x)) for x in r[:12]) + " %d " % int(r[12]) + " ".join(repr(float(x)) for x in r[13:]) + "\n")
+    _run("test_dropin_pcs", inp, out)
+    lines = open(out).read().strip().split("\n")
+    res = np.array([[float(x) for x in ln.split()] for ln in lines[:len(rows)]])
+    qq, kk, qb = rows[:, :12], rows[:, 12].astype(np.int8), rows[:, 13:]
+    ok_o, q_o = oracle.pcs_project(qq, 0, kk)
+    assert (res[:, 0] == ok_o).all()
+    m = ok_o == 1
+    assert np.abs(res[m][:, 6:12] - q_o[m][:, 6:]).max() < 1e-6
+    coll_o = oracle.collision_state(q_o[m])
+    assert (res[m][:, 1] == coll_o).all()
+    id_o = oracle.identify_state_ik(q_o[m])
+    assert (res[m][:, 2:4] == id_o).all()
+    _, valid_o, _ = oracle.pcs_validate(qq, 0, kk)
+    assert (res[:, 4] == valid_o).all()
+    # RBS on rows whose two endpoints are valid
+    _, vb, qbo = oracle.pcs_validate(qb, 0, kk)
+    both = (valid_o == 1) & (vb == 1)
+    rbs_o, _ = oracle.pcs_check_motion_rbs(q_o[both], qbo[both], 0, kk[both])
+    assert (res[both][:, 5] == rbs_o).all() and both.sum() >= n // 2
+    assert (res[~both][:, 5] == 0).all()
+    # sampler: returns a closed configuration accepted by the reference's (quirky) acceptance rule
+    s = [float(x) for x in lines[len(rows)].split()[1:]]
+    hit, lim, qs = int(s[0]), int(s[1]), np.array(s[2:])
+    assert not (hit and not lim)
+    assert (oracle.identify_state_ik(qs[None])[0] >= 0).any()
+    # LogPerf2file wrote the 16-line record of StateValidityCheckerPCS.cpp:628-651
+    assert len(open(tmp_path / "paths" / "perf_log.txt").read().split()) == 16
+
+
+def test_gd_dropin_class(tmp_path, oracle):
+    from abb_dualarm_planning_b200 import sampling
+    q = sampling.sample_gd(41, 0, 300)
+    inp, out = str(tmp_path / "in.txt"), str(tmp_path / "out.txt")
+    with open(inp, "w") as f:
+        f.write("%d\n" % len(q))
+        for r in q:
+            f.write(" ".join(repr(float(x)) for x in r) + "\n")
+    _run("test_dropin_gd", inp, out)
+    lines = open(out).read().strip().split("\n")
+    res = np.array([[float(x) for x in ln.split()] for ln in lines[:len(q)]])
+    ok_o, conv_o, it_o, q_o = oracle.gd_project(q)
+    valid_o, _ = oracle.gd_validate(q)
+    assert (res[:, 0] == ok_o).all() and (res[:, 1] == valid_o).all()
+    d = np.abs(res[:, 2:] - q_o); d = np.minimum(d, np.abs(d - 2 * 3.1416))
+    assert d.max() < 2e-5
+    batch = np.array([int(x) for x in lines[len(q)].split()[1:]])
+    assert (batch == valid_o).all()
