@@ -464,13 +464,46 @@ __device__ __noinline__ void pinv_step_svd(const double (*J)[12], const double* 
     }
 }
 
-/* One Newton step: dq = pinv(J) tw.  Regular case: dq = J^T (J J^T)^-1 tw by Cholesky (identical to the SVD pseudo
- * inverse when no singular value is truncated); a lower bound on the smallest singular value proves regularity,
- * otherwise the exact truncated SVD path runs. */
-__device__ __forceinline__ void newton_step(const double (*J0)[12], const double* p, const double* tw, double* dq) {
-    /* tip-referred Jacobian rows: v_tip = v_0 + w x p  =>  Jv = J0v - [p]x Jw */
-    double J[6][12];
+/* ---- Newton iteration without a stored Jacobian -------------------------------------------------------------------
+ * State per sample: the 12 chain-order joints and their cached sin / cos, held in SHARED memory (column per thread,
+ * conflict free) so that the joint loops can stay rolled: one copy of the per-joint code instead of twelve keeps the
+ * kernel inside the instruction cache and frees ~70 registers.  One iteration = two walks along the chain:
+ *   walk 1: sin / cos of every joint (the only transcendental site), FK, and A0 = J0 J0^T accumulated column by column
+ *           (J0 = Jacobian referred to the base origin; a column is known as soon as its joint frame is reached:
+ *           col0_j = [o_j x a_j ; a_j]);
+ *   solve : KDL's tip-referred J = X J0, X = [[I, -[p]x],[0, I]], so  pinv(J) tw = J0^T A0^-1 (X^-1 tw)  whenever no
+ *           singular value is truncated (ChainIkSolverVel_pinv drops sigma < 1e-5).  A0 z = X^-1 tw by Cholesky;
+ *           regularity is PROVEN by  sigma_min(J) >= sigma_min(J0) / ||X^-1|| >= 1 / (sqrt(trace(A0^-1)) (1 + |p|)) > 1.5e-5,
+ *           otherwise the exact truncated SVD step runs (needs sigma_min < ~1e-4: essentially never for random seeds);
+ *   walk 2: the columns again from the cached sin / cos, dq_j = col0_j . z, q_j += dq_j. */
+#define CKC_GD_BLOCK 128
+/* per-joint constants of the chain in __constant__ memory: the rolled joint loops index them with a warp-uniform
+ * runtime index (an indexed kernel-parameter struct would be copied to local memory).  [env-1][segment][xyz];
+ * kdl_class.cpp:11-12 (integer-division l5 = lee = 66) and :32-45; segment 6 carries the rod: 2*lee + L. */
+__constant__ int c_kdl_axis[13] = { -1, 2, 1, 1, 0, 1, 0, 0, 1, 0, 1, 1, 2 };
+__constant__ double c_kdl_tip[2][13][3] = {
+    { { 0, 0, 166 }, { 0, 0, 124 }, { 0, 0, 270 }, { 149.6, 0, 70 }, { 152.4, 0, 0 }, { 66, 0, 0 }, { 2 * 66 + 300.0, 0, 0 },
+      { 66, 0, 0 }, { 152.4, 0, 0 }, { 149.6, 0, -70 }, { 0, 0, -270 }, { 0, 0, -124 }, { 0, 0, -166 } },
+    { { 0, 0, 166 }, { 0, 0, 124 }, { 0, 0, 270 }, { 149.6, 0, 70 }, { 152.4, 0, 0 }, { 66, 0, 0 }, { 2 * 66 + 500.0, 0, 0 },
+      { 66, 0, 0 }, { 152.4, 0, 0 }, { 149.6, 0, -70 }, { 0, 0, -270 }, { 0, 0, -124 }, { 0, 0, -166 } } };
+struct gd_ref {                     /* view of one thread's column of the block's shared state array [36][CKC_GD_BLOCK] */
+    double* b;
+    __device__ __forceinline__ double& qc(int j) const { return b[j * CKC_GD_BLOCK]; }
+    __device__ __forceinline__ double& cs(int j) const { return b[(12 + j) * CKC_GD_BLOCK]; }
+    __device__ __forceinline__ double& sn(int j) const { return b[(24 + j) * CKC_GD_BLOCK]; }
+};
+
+__device__ __forceinline__ void gd_init(const gd_ref& s, const double* q) {
 #pragma unroll
+    for (int i = 0; i < 6; i++) { s.qc(i) = q[i]; s.qc(6 + i) = q[11 - i]; }     /* kdl_class.cpp:73-78 */
+    s.qc(11) = -q[6];
+}
+
+/* rare path: tip-referred Jacobian in local memory + exact truncated pseudo inverse */
+__device__ __noinline__ void gd_singular_step(const ckc_kin_dev& k, const gd_ref& s, const double* tw) {
+    double qc[12], R[9], p[3], J0[6][12], J[6][12], dq[12];
+    for (int c = 0; c < 12; c++) qc[c] = s.qc(c);
+    chain_fk<true>(k, qc, R, p, J0);
     for (int c = 0; c < 12; c++) {
         const double w0 = J0[3][c], w1 = J0[4][c], w2 = J0[5][c];
         J[0][c] = J0[0][c] + (w1 * p[2] - w2 * p[1]);
@@ -478,73 +511,52 @@ __device__ __forceinline__ void newton_step(const double (*J0)[12], const double
         J[2][c] = J0[2][c] + (w0 * p[1] - w1 * p[0]);
         J[3][c] = w0; J[4][c] = w1; J[5][c] = w2;
     }
+    pinv_step_svd(J, tw, 1e-5, dq);
+    for (int c = 0; c < 12; c++) s.qc(c) = qc[c] + dq[c];
+}
+
+__device__ __forceinline__ void rot_by_axis(int ax, double* R, double c, double s) {     /* ax is warp-uniform */
+    if (ax == 0) post_rot_x(R, c, s); else if (ax == 1) post_rot_y(R, c, s); else post_rot_z(R, c, s);
+}
+
+/* one ChainIkSolverPos_NR iteration; returns Equal(delta_twist, 0, 1e-5) evaluated on the twist BEFORE the update */
+__device__ __forceinline__ bool gd_iterate(const ckc_kin_dev& k, const gd_ref& s) {
+    const int e = k.env_index;
+    double R[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    double p[3] = { c_kdl_tip[e][0][0], c_kdl_tip[e][0][1], c_kdl_tip[e][0][2] };  /* segment 0: Joint::None */
     double A[6][6];
 #pragma unroll
     for (int i = 0; i < 6; i++)
 #pragma unroll
-        for (int j = 0; j <= i; j++) {
-            double s = 0;
-#pragma unroll
-            for (int c = 0; c < 12; c++) s += J[i][c] * J[j][c];
-            A[i][j] = s;
-        }
-    /* Cholesky A = L L^T (in place, lower) */
-    bool regular = true;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-            double s = A[i][j];
-#pragma unroll
-            for (int kk = 0; kk < j; kk++) s -= A[i][kk] * A[j][kk];
-            if (i == j) { if (!(s > 1e-300)) { regular = false; s = 1; } A[i][i] = sqrt(s); }
-            else A[i][j] = s / A[j][j];
-        }
-    }
-    if (regular) {
-        /* ||L^-1||_F^2 = trace(A^-1) >= 1 / lambda_min(A)  =>  sigma_min(J)^2 >= 1 / ||L^-1||_F^2 */
-        double Li[6][6], fro = 0;
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-#pragma unroll
-            for (int r = c; r < 6; r++) {
-                double s = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-                for (int kk = c; kk < r; kk++) s -= A[r][kk] * Li[kk][c];
-                Li[r][c] = s / A[r][r];
-                fro += Li[r][c] * Li[r][c];
-            }
-        }
-        regular = fro < 1e8;              /* sigma_min > 1e-4 > eps = 1e-5: nothing would be truncated */
-    }
-    if (!regular) { pinv_step_svd(J, tw, 1e-5, dq); return; }
-    double y[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) { double s = tw[i]; 
-#pragma unroll
-        for (int kk = 0; kk < i; kk++) s -= A[i][kk] * y[kk]; y[i] = s / A[i][i]; }
-#pragma unroll
-    for (int i = 5; i >= 0; i--) { double s = y[i];
-#pragma unroll
-        for (int kk = i + 1; kk < 6; kk++) s -= A[kk][i] * y[kk]; y[i] = s / A[i][i]; }
-#pragma unroll
-    for (int c = 0; c < 12; c++) dq[c] = J[0][c] * y[0] + J[1][c] * y[1] + J[2][c] * y[2] + J[3][c] * y[3] + J[4][c] * y[4] + J[5][c] * y[5];
-}
-
-/* kdl::GD.  q: user order in/out.  returns converged; *iters = Newton iterations */
-__device__ __forceinline__ bool gd_project(const ckc_kin_dev& k, double* q, int max_iter, int* iters) {
-    double qc[12];
-#pragma unroll
-    for (int i = 0; i < 6; i++) { qc[i] = q[i]; qc[6 + i] = q[11 - i]; }       /* kdl_class.cpp:73-78 */
-    qc[11] = -qc[11];
-    bool conv = false;
-    int it = 0;
+        for (int j = 0; j <= i; j++) A[i][j] = 0;
+    /* ---- walk 1 ---- */
 #pragma unroll 1
-    for (; it < max_iter; it++) {
-        double R[9], p[3], J0[6][12], tw[6], dq[12];
-        chain_fk<true>(k, qc, R, p, J0);
-        /* delta_twist = diff(f, target): vel = (D,0,0) - p ; rot = R * rotvec(R^T * I) */
-        tw[0] = k.D - p[0]; tw[1] = -p[1]; tw[2] = -p[2];
+    for (int j = 0; j < 12; j++) {
+        const int ax = c_kdl_axis[j + 1];
+        double col[6];
+        if (ax == 0) { col[3] = R[0]; col[4] = R[3]; col[5] = R[6]; }
+        else if (ax == 1) { col[3] = R[1]; col[4] = R[4]; col[5] = R[7]; }
+        else { col[3] = R[2]; col[4] = R[5]; col[5] = R[8]; }
+        col[0] = p[1] * col[5] - p[2] * col[4];
+        col[1] = p[2] * col[3] - p[0] * col[5];
+        col[2] = p[0] * col[4] - p[1] * col[3];
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++) A[a][b] += col[a] * col[b];
+        double sj, cj;
+        sincos(s.qc(j), &sj, &cj);
+        s.cs(j) = cj; s.sn(j) = sj;
+        rot_by_axis(ax, R, cj, sj);
+        const double tx = c_kdl_tip[e][j + 1][0], ty = c_kdl_tip[e][j + 1][1], tz = c_kdl_tip[e][j + 1][2];
+        p[0] += R[0] * tx + R[1] * ty + R[2] * tz;
+        p[1] += R[3] * tx + R[4] * ty + R[5] * tz;
+        p[2] += R[6] * tx + R[7] * ty + R[8] * tz;
+    }
+    /* ---- delta_twist = diff(f, target): vel = (D,0,0) - p ; rot = R * GetRot(R^T) ---- */
+    double tw[6];
+    tw[0] = k.D - p[0]; tw[1] = -p[1]; tw[2] = -p[2];
+    {
         double Rt[9], rv[3];
 #pragma unroll
         for (int a = 0; a < 3; a++)
@@ -553,27 +565,128 @@ __device__ __forceinline__ bool gd_project(const ckc_kin_dev& k, double* q, int 
         kdl_rotvec(Rt, rv);
 #pragma unroll
         for (int a = 0; a < 3; a++) tw[3 + a] = R[3 * a] * rv[0] + R[3 * a + 1] * rv[1] + R[3 * a + 2] * rv[2];
-        newton_step(J0, p, tw, dq);
-#pragma unroll
-        for (int i = 0; i < 12; i++) qc[i] += dq[i];
-        bool eq = true;
-#pragma unroll
-        for (int i = 0; i < 6; i++) eq = eq && (fabs(tw[i]) < 1e-5);          /* Equal(delta_twist, Twist::Zero(), eps) */
-        if (eq) { conv = true; it++; break; }
     }
-    *iters = it;
-    if (!conv) return false;
+    bool eq = true;
 #pragma unroll
-    for (int i = 0; i < 12; i++) {                                           /* kdl_class.cpp:110-122 */
-        double v = (fabs(qc[i]) < 1e-4) ? 0.0 : qc[i];
-        v = fmod(v, 2 * CKC_PI_);
+    for (int i = 0; i < 6; i++) eq = eq && (fabs(tw[i]) < 1e-5);
+    /* ---- Cholesky of A0 (lower, in place; reciprocal pivots kept) ---- */
+    bool regular = true;
+    double inv[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double v = A[i][j];
+#pragma unroll
+            for (int kk = 0; kk < j; kk++) v -= A[i][kk] * A[j][kk];
+            if (i == j) { if (!(v > 1e-300)) { regular = false; v = 1; } const double r = rsqrt(v); inv[i] = r; A[i][i] = v * r; }
+            else A[i][j] = v * inv[j];
+        }
+    }
+    if (regular) {
+        /* trace(A0^-1) = ||L^-1||_F^2, one column of L^-1 at a time */
+        double fro = 0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            double Lc[6];
+#pragma unroll
+            for (int r = c; r < 6; r++) {
+                double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int kk = c; kk < r; kk++) v -= A[r][kk] * Lc[kk];
+                Lc[r] = v * inv[r];
+                fro += Lc[r] * Lc[r];
+            }
+        }
+        const double reach = 1.0 + sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+        regular = fro * (1.5e-5 * 1.5e-5) * reach * reach < 1.0;
+    }
+    if (!regular) { gd_singular_step(k, s, tw); return eq; }
+    /* ---- z = A0^-1 X^-1 tw,  X^-1 tw = [tw_v + p x tw_w ; tw_w] ---- */
+    double z[6];
+    z[0] = tw[0] + (p[1] * tw[5] - p[2] * tw[4]);
+    z[1] = tw[1] + (p[2] * tw[3] - p[0] * tw[5]);
+    z[2] = tw[2] + (p[0] * tw[4] - p[1] * tw[3]);
+    z[3] = tw[3]; z[4] = tw[4]; z[5] = tw[5];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double v = z[i];
+#pragma unroll
+        for (int kk = 0; kk < i; kk++) v -= A[i][kk] * z[kk];
+        z[i] = v * inv[i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        double v = z[i];
+#pragma unroll
+        for (int kk = i + 1; kk < 6; kk++) v -= A[kk][i] * z[kk];
+        z[i] = v * inv[i];
+    }
+    /* ---- walk 2: dq_j = col0_j . z with the frames of the configuration the twist was measured at ---- */
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+    p[0] = c_kdl_tip[e][0][0]; p[1] = c_kdl_tip[e][0][1]; p[2] = c_kdl_tip[e][0][2];
+#pragma unroll 1
+    for (int j = 0; j < 12; j++) {
+        const int ax = c_kdl_axis[j + 1];
+        double a0, a1, a2;
+        if (ax == 0) { a0 = R[0]; a1 = R[3]; a2 = R[6]; }
+        else if (ax == 1) { a0 = R[1]; a1 = R[4]; a2 = R[7]; }
+        else { a0 = R[2]; a1 = R[5]; a2 = R[8]; }
+        const double dq = (p[1] * a2 - p[2] * a1) * z[0] + (p[2] * a0 - p[0] * a2) * z[1] + (p[0] * a1 - p[1] * a0) * z[2] +
+                          a0 * z[3] + a1 * z[4] + a2 * z[5];
+        s.qc(j) += dq;
+        if (j < 11) {
+            rot_by_axis(ax, R, s.cs(j), s.sn(j));
+            const double tx = c_kdl_tip[e][j + 1][0], ty = c_kdl_tip[e][j + 1][1], tz = c_kdl_tip[e][j + 1][2];
+            p[0] += R[0] * tx + R[1] * ty + R[2] * tz;
+            p[1] += R[3] * tx + R[4] * ty + R[5] * tz;
+            p[2] += R[6] * tx + R[7] * ty + R[8] * tz;
+        }
+    }
+    return eq;
+}
+
+/* exact fmod(v, P) for the magnitudes a Newton iterate reaches: fma(-k, P, v) is the exactly representable remainder when
+ * k = trunc(v / P) is right; the rounded quotient can be off by one next to a multiple of P, which the fix-ups repair
+ * (each fix-up result is again the exactly representable true remainder).  Falls back to fmod() for huge arguments. */
+__device__ __forceinline__ double fmod_exact(double v, double P) {
+    if (!(fabs(v) < 1e6)) return fmod(v, P);
+    const double kq = trunc(v / P);
+    double r = fma(-kq, P, v);
+    if (v >= 0) { if (r < 0) r += P; else if (r >= P) r -= P; }
+    else { if (r > 0) r -= P; else if (r <= -P) r += P; }
+    return r;
+}
+
+/* post-processing of kdl::GD (kdl_class.cpp:110-128): zero snap, fmod / wrap with PI = 3.1416, back to user order */
+__device__ __forceinline__ void gd_finish(const gd_ref& s, double* q) {
+    double qc[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        double v = s.qc(i);
+        v = (fabs(v) < 1e-4) ? 0.0 : v;
+        v = fmod_exact(v, 2 * CKC_PI_);
         if (v > CKC_PI_) v -= 2 * CKC_PI_;
         if (v < -CKC_PI_) v += 2 * CKC_PI_;
         qc[i] = v;
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++) { q[i] = qc[i]; q[6 + i] = qc[11 - i]; }       /* :124-128 */
+    for (int i = 0; i < 6; i++) { q[i] = qc[i]; q[6 + i] = qc[11 - i]; }
     q[6] = -q[6];
+}
+
+/* kdl::GD as a plain per-thread loop (used by the RBS frontier).  q: user order in/out.  returns converged */
+__device__ __forceinline__ bool gd_project(const ckc_kin_dev& k, const gd_ref& s, double* q, int max_iter, int* iters) {
+    gd_init(s, q);
+    bool conv = false;
+    int it = 0;
+#pragma unroll 1
+    for (; it < max_iter; it++) {
+        if (gd_iterate(k, s)) { conv = true; it++; break; }
+    }
+    *iters = it;
+    if (!conv) return false;
+    gd_finish(s, q);
     return true;
 }
 

@@ -48,7 +48,7 @@ struct ckc_ctx {
     cudaStream_t stream = nullptr;
     int64_t chunk = 1 << 20;            /* samples per internal batch */
     /* persistent device storage */
-    dev_buf d_nodes, d_tris, d_ctr, d_small;           /* d_small: list_count, work counters, overflow count */
+    dev_buf d_nodes, d_tris, d_ctr, d_small, d_pairtab, d_static;           /* d_small: list_count, work counters, overflow count */
     /* per-chunk work buffers */
     dev_buf d_qin, d_qout, d_ac, d_ik, d_ok, d_valid, d_list, d_frames, d_ovf, d_bigstack, d_flags, d_aux, d_aux2;
     dev_buf d_qb, d_edge;               /* RBS */
@@ -296,6 +296,7 @@ static void init_constants(ckc_ctx* c) {
                                  { kl5, 0, 0 }, { k.l4, 0, 0 }, { k.l3b, 0, -k.l3a }, { 0, 0, -k.l2 }, { 0, 0, -k.l1 }, { 0, 0, -k.b } };
     const int axes[13] = { -1, 2, 1, 1, 0, 1, 0, 0, 1, 0, 1, 1, 2 };
     memcpy(k.kdl_tip, tips, sizeof(tips)); memcpy(k.kdl_axis, axes, sizeof(axes));
+    k.env_index = env - 1;
 
     ckc_world_dev& w = c->world;
     w.env = env; w.D = k.D; w.tol = 8.0; w.cull_tol = 8.0f + 0.05f;
@@ -386,6 +387,21 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
     if (!okc) { std::string msg = std::string("device upload: ") + cudaGetErrorString(cudaGetLastError()); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA; }
     ctx->world.nodes = ctx->d_nodes.as<ckc_node>();
     ctx->world.tris = ctx->d_tris.as<double>();
+    {   /* pair table and static poses as global-memory tables */
+        std::vector<ckc_pair_dev> pt(ctx->world.npairs);
+        for (int p = 0; p < ctx->world.npairs; p++) {
+            const ckc_pair& pr = ctx->world.pairs[p];
+            pt[p].node_a = ctx->world.node_off[pr.mesh_a]; pt[p].node_b = ctx->world.node_off[pr.mesh_b];
+            pt[p].tri_a = ctx->world.tri_off[pr.mesh_a]; pt[p].tri_b = ctx->world.tri_off[pr.mesh_b];
+            pt[p].frame_a = pr.frame_a; pt[p].frame_b = pr.frame_b; pt[p].pad0 = pt[p].pad1 = 0;
+        }
+        bool okt = ctx->d_pairtab.reserve(pt.size() * sizeof(ckc_pair_dev)) == cudaSuccess && ctx->d_static.reserve(sizeof(ctx->world.static_frames)) == cudaSuccess &&
+                   cudaMemcpy(ctx->d_pairtab.p, pt.data(), pt.size() * sizeof(ckc_pair_dev), cudaMemcpyHostToDevice) == cudaSuccess &&
+                   cudaMemcpy(ctx->d_static.p, ctx->world.static_frames, sizeof(ctx->world.static_frames), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!okt) { std::string msg = std::string("device upload: ") + cudaGetErrorString(cudaGetLastError()); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA; }
+        ctx->world.pair_tab = ctx->d_pairtab.as<ckc_pair_dev>();
+        ctx->world.static_frames_dev = ctx->d_static.as<double>();
+    }
     const char* ch = getenv("CKC_CHUNK");
     if (ch && atoll(ch) >= 1024) ctx->chunk = atoll(ch);
     *out = ctx;
@@ -395,7 +411,7 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
 extern "C" void ckc_destroy(ckc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    dev_buf* bufs[] = { &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_small, &ctx->d_qin, &ctx->d_qout, &ctx->d_ac, &ctx->d_ik, &ctx->d_ok,
+    dev_buf* bufs[] = { &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_small, &ctx->d_qin, &ctx->d_qout, &ctx->d_ac, &ctx->d_ik, &ctx->d_ok,
                         &ctx->d_valid, &ctx->d_list, &ctx->d_frames, &ctx->d_ovf, &ctx->d_bigstack, &ctx->d_flags, &ctx->d_aux, &ctx->d_aux2, &ctx->d_qb, &ctx->d_edge };
     for (dev_buf* b : bufs) b->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -637,8 +653,9 @@ static int run_gd_chunk(ckc_ctx* ctx, int64_t n, const double* d_q, ckc_layout l
     CU(ctx->d_list.reserve((size_t)n * 4));
     CU(cudaMemsetAsync(p_list_count(ctx), 0, 4, st));
     { stage_scope ts(ctx, st, 0);
-      ckc_launch_gd_project(ctx->kin, n, d_q, li, seed, i0, seeded, d_qout, lo, d_ok, d_conv, d_iters, d_valid, collide ? ctx->d_list.as<int32_t>() : nullptr,
-                            p_list_count(ctx), ctx->d_ctr.as<ckc_counters_dev>(), st); }
+      ckc_launch_gd_project(ctx->kin, ctx->num_sms, n, d_q, li, seed, i0, seeded, d_qout, lo, d_ok, d_conv, d_iters, d_valid,
+                            collide ? ctx->d_list.as<int32_t>() : nullptr, p_list_count(ctx), (unsigned long long*)(ctx->d_small.as<int32_t>() + 12),
+                            ctx->d_ctr.as<ckc_counters_dev>(), st); }
     ctx->launches += 1;
     ctx->host_stats.ik_calls += n;
     CU(cudaGetLastError());

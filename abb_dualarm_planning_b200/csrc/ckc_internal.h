@@ -29,10 +29,14 @@ struct __align__(16) ckc_node {
 };
 
 struct ckc_pair { uint8_t mesh_a, frame_a, mesh_b, frame_b; };
+/* device copy of one pair-table entry, 32 bytes, read with two 16-byte loads by the lane that owns the task */
+struct __align__(16) ckc_pair_dev { int node_a, node_b, tri_a, tri_b, frame_a, frame_b, pad0, pad1; };
 
 /* Everything the collision kernels need; passed BY VALUE as a kernel parameter (constant bank, broadcast reads). */
 struct ckc_world_dev {
     const ckc_node* nodes;              /* all meshes, concatenated */
+    const ckc_pair_dev* pair_tab;       /* [npairs] in global memory: indexed per lane (a kernel-parameter array would be copied to local memory) */
+    const double* static_frames_dev;    /* [3][12] obstacle poses in global memory (same values as static_frames) */
     const double*   tris;               /* all meshes, concatenated, 9 doubles per triangle (FP64, as parsed) */
     int node_off[CKC_NUM_MESHES];       /* first node of each mesh */
     int tri_off[CKC_NUM_MESHES];        /* first triangle of each mesh */
@@ -56,6 +60,7 @@ struct ckc_kin_dev {
     double l34, alpha;                           /* sqrt(l3a^2+(l3b+l4)^2), atan2(l3b+l4, l3a) */
     double kdl_tip[13][3];                       /* KDL chain segment tips (integer-division l5/lee = 66) */
     int    kdl_axis[13];                         /* -1 none, 0 X, 1 Y, 2 Z */
+    int    env_index;                            /* env - 1: selects the __constant__ chain table */
 };
 
 /* how a batch of configurations is addressed: element (i, j) = base[i * stride_i + j * stride_j] */
@@ -100,9 +105,9 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
                         int32_t* ovf_list, int32_t* ovf_count, uint32_t* big_stack, ckc_counters_dev* ctr, cudaStream_t st);
 void ckc_launch_limits(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, uint8_t* ok, cudaStream_t st);
 void ckc_launch_identify_ik(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, int8_t* ik01, cudaStream_t st);
-void ckc_launch_gd_project(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded,
+void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const double* q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded,
                            double* q_out, ckc_layout lo, uint8_t* ok, uint8_t* converged, int32_t* iters, uint8_t* valid,
-                           int32_t* list, int32_t* list_count, ckc_counters_dev* ctr, cudaStream_t st);
+                           int32_t* list, int32_t* list_count, unsigned long long* work_counter, ckc_counters_dev* ctr, cudaStream_t st);
 void ckc_launch_rx_check(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, double eps, uint8_t* ok, double* resid,
                          uint8_t* valid, int32_t* list, int32_t* list_count, cudaStream_t st);
 void ckc_launch_fma_peak(int precision, int num_sms, int iters, float* sink, cudaStream_t st);

@@ -147,12 +147,18 @@ struct collide_args {
 };
 
 __device__ __forceinline__ const double* frame64(const ckc_world_dev& w, const double* cfg_frames, int f) {
-    return f < CKC_NUM_DYN_FRAMES ? cfg_frames + 12 * f : w.static_frames[f - CKC_NUM_DYN_FRAMES];
+    return f < CKC_NUM_DYN_FRAMES ? cfg_frames + 12 * f : w.static_frames_dev + 12 * (f - CKC_NUM_DYN_FRAMES);
+}
+__device__ __forceinline__ ckc_pair_dev load_pair(const ckc_world_dev& w, int p) {
+    const int4* q = reinterpret_cast<const int4*>(w.pair_tab + p);
+    const int4 a = __ldg(q), b = __ldg(q + 1);
+    ckc_pair_dev r; r.node_a = a.x; r.node_b = a.y; r.tri_a = a.z; r.tri_b = a.w; r.frame_a = b.x; r.frame_b = b.y; r.pad0 = 0; r.pad1 = 0;
+    return r;
 }
 
 /* exact leaf test: triangle ta of mesh A vs tb of mesh B under the pair's poses, PQP_Tolerance conventions:
  * R = Ra^T Rb, T = Ra^T (Tb - Ta), triangle B transformed into A's frame, then TriDist */
-__device__ __forceinline__ double leaf_distance(const ckc_world_dev& w, const double* cfg_frames, const ckc_pair pr, int ta, int tb) {
+__device__ __forceinline__ double leaf_distance(const ckc_world_dev& w, const double* cfg_frames, const ckc_pair_dev pr, int ta, int tb) {
     const double* Fa = frame64(w, cfg_frames, pr.frame_a);
     const double* Fb = frame64(w, cfg_frames, pr.frame_b);
     double R[9], T[3];
@@ -163,8 +169,8 @@ __device__ __forceinline__ double leaf_distance(const ckc_world_dev& w, const do
         for (int j = 0; j < 3; j++) R[3 * i + j] = Fa[i] * Fb[j] + Fa[3 + i] * Fb[3 + j] + Fa[6 + i] * Fb[6 + j];
         T[i] = Fa[i] * tx + Fa[3 + i] * ty + Fa[6 + i] * tz;
     }
-    const double* pa = w.tris + 9 * (int64_t)(w.tri_off[pr.mesh_a] + ta);
-    const double* pb = w.tris + 9 * (int64_t)(w.tri_off[pr.mesh_b] + tb);
+    const double* pa = w.tris + 9 * (int64_t)(pr.tri_a + ta);
+    const double* pb = w.tris + 9 * (int64_t)(pr.tri_b + tb);
     v3 S[3], Tt[3];
 #pragma unroll
     for (int v = 0; v < 3; v++) {
@@ -207,7 +213,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
 
         /* stage this configuration's frames as FP32 in shared memory (static obstacle poses from the parameter bank) */
         for (int e = lane; e < CKC_NUM_FRAMES * 12; e += 32)
-            F[e] = e < CKC_FRAME_DOUBLES ? (float)cfg_frames[e] : (float)w.static_frames[(e - CKC_FRAME_DOUBLES) / 12][(e - CKC_FRAME_DOUBLES) % 12];
+            F[e] = e < CKC_FRAME_DOUBLES ? (float)cfg_frames[e] : (float)w.static_frames_dev[e - CKC_FRAME_DOUBLES];
         /* seed the stack with the root task of every table entry, first entry on top */
         int top = w.npairs;
         for (int p = lane; p < w.npairs; p += 32) stack[w.npairs - 1 - p] = (uint32_t)p << 22;
@@ -226,7 +232,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                 if (lane < cnt) {
                     t = triq[ntri - 1 - lane];
                     const int p = t >> 20;
-                    const double d = leaf_distance(w, cfg_frames, w.pairs[p], (t >> 10) & 1023, t & 1023);
+                    const double d = leaf_distance(w, cfg_frames, load_pair(w, p), (t >> 10) & 1023, t & 1023);
                     h = d <= w.tol;                                   /* PQP: closer_than_tolerance iff d <= tolerance */
                 }
                 n_tri += cnt;
@@ -246,12 +252,12 @@ k_collide(const ckc_world_dev w, const collide_args a) {
             if (active) {
                 const uint32_t t = stack[top - 1 - lane];
                 const int p = t >> 22, na = (t >> 11) & 2047, nb = t & 2047;
-                const ckc_pair pr = w.pairs[p];
+                const ckc_pair_dev pr = load_pair(w, p);
                 bool skip = false;
                 if (per_pair) skip = a.pair_flags[sample * CKC_MAX_PAIRS + p] != 0;      /* pair already decided */
                 if (!skip) {
-                    const box32 A = load_box(w.nodes + w.node_off[pr.mesh_a] + na);
-                    const box32 B = load_box(w.nodes + w.node_off[pr.mesh_b] + nb);
+                    const box32 A = load_box(w.nodes + pr.node_a + na);
+                    const box32 B = load_box(w.nodes + pr.node_b + nb);
                     const bool far = boxes_farther_than(A, F + 12 * pr.frame_a, B, F + 12 * pr.frame_b, w.cull_tol);
                     if (!far) {
                         if (A.child < 0 && B.child < 0) { leafpair = true; tt = ((uint32_t)p << 20) | ((uint32_t)(~A.child) << 10) | (uint32_t)(~B.child); }
@@ -425,52 +431,99 @@ void ckc_launch_transpose(const double* src, ckc_layout ls, double* dst, ckc_lay
 /* ================================================================================================================ */
 /* GD / RX flavours                                                                                                   */
 /* ================================================================================================================ */
-/* K5: one thread per sample -- Newton-Raphson closure projection on the 12-joint chain (kdl::GD), joint limits,
- * append of the surviving samples to the collision work list */
-__global__ void __launch_bounds__(128)
+/* K5: Newton-Raphson closure projection on the 12-joint chain (kdl::GD), joint limits, append of the surviving samples
+ * to the collision work list.  Persistent grid with LANE-level work stealing: a lane that has converged writes its
+ * result and takes the next sample (one warp-aggregated atomicAdd per refill), so the spread of the iteration count
+ * (median 9, max > 25) does not idle the other 31 lanes of its warp. */
+__global__ void __launch_bounds__(CKC_GD_BLOCK, 4)
 k_gd_project(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, ckc_layout li, uint64_t key, uint64_t i0, int seeded,
              double* __restrict__ q_out, ckc_layout lo, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ conv_out,
              int32_t* __restrict__ iters_out, uint8_t* __restrict__ valid_out, int32_t* __restrict__ list, int32_t* list_count,
-             ckc_counters_dev* ctr) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool ok = false;
+             unsigned long long* work_counter, ckc_counters_dev* ctr) {
+    __shared__ double sh_state[36 * CKC_GD_BLOCK];
+    const int lane = threadIdx.x & 31;
+    const gd_ref s = { sh_state + threadIdx.x };
+    int64_t i = -1;
     int it = 0;
-    if (i < n) {
-        double q[12];
-        if (seeded) {
+    bool active = false, exhausted = false;
+    unsigned long long iters_sum = 0, n_ok = 0;
+    for (;;) {
+        /* ---- refill idle lanes ---- */
+        const unsigned need = __ballot_sync(0xffffffffu, !active && !exhausted);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if (lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!active && !exhausted) {
+                i = (int64_t)(base + __popc(need & ((1u << lane) - 1)));
+                if (i < n) {
+                    double q[12];
+                    if (seeded) {
 #pragma unroll
-            for (int j = 0; j < 12; j++) q[j] = -CKC_PI_ + uniform01(key, i0 + (uint64_t)i, j) * (2 * CKC_PI_);   /* GD.cpp:60-61 */
-        } else {
+                        for (int j = 0; j < 12; j++) q[j] = -CKC_PI_ + uniform01(key, i0 + (uint64_t)i, j) * (2 * CKC_PI_);   /* GD.cpp:60-61 */
+                    } else {
 #pragma unroll
-            for (int j = 0; j < 12; j++) q[j] = q_in[i * li.stride_i + j * li.stride_j];
+                        for (int j = 0; j < 12; j++) q[j] = q_in[i * li.stride_i + j * li.stride_j];
+                    }
+                    gd_init(s, q);
+                    it = 0; active = true;
+                } else exhausted = true;
+            }
         }
-        const bool conv = gd_project(kin, q, 10000, &it);
-        ok = conv && within_limits(kin, q);                        /* kdl_class.cpp:130 */
-        if (q_out) {
-#pragma unroll
-            for (int j = 0; j < 12; j++) q_out[i * lo.stride_i + j * lo.stride_j] = q[j];
+        if (!__any_sync(0xffffffffu, active)) break;
+        /* ---- one Newton iteration on every busy lane ---- */
+        bool done = false, conv = false;
+        if (active) {
+            conv = gd_iterate(kin, s);
+            it++;
+            done = conv || it >= 10000;                                /* ChainIkSolverPos_NR(..., 10000, 1e-5) */
         }
-        if (ok_out) ok_out[i] = ok ? 1 : 0;
-        if (conv_out) conv_out[i] = conv ? 1 : 0;
-        if (iters_out) iters_out[i] = it;
-        if (valid_out) valid_out[i] = 0;
+        /* ---- retire finished lanes ---- */
+        if (__any_sync(0xffffffffu, done)) {
+            bool ok = false;
+            if (done) {
+                double q[12];
+                if (conv) { gd_finish(s, q); ok = within_limits(kin, q); }     /* kdl_class.cpp:110-130 */
+                else {
+#pragma unroll
+                    for (int j = 0; j < 12; j++) q[j] = seeded ? 0.0 : q_in[i * li.stride_i + j * li.stride_j];
+                }
+                if (q_out) {
+#pragma unroll
+                    for (int j = 0; j < 12; j++) q_out[i * lo.stride_i + j * lo.stride_j] = q[j];
+                }
+                if (ok_out) ok_out[i] = ok ? 1 : 0;
+                if (conv_out) conv_out[i] = conv ? 1 : 0;
+                if (iters_out) iters_out[i] = it;
+                if (valid_out) valid_out[i] = 0;
+                iters_sum += (unsigned long long)it; n_ok += ok ? 1 : 0;
+                active = false;
+            }
+            append_to_list(ok, (int32_t)i, list, list_count);
+        }
     }
-    append_to_list(ok, (int32_t)i, list, list_count);
     if (ctr) {
-        unsigned long long s = (unsigned long long)it;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&ctr->gd_iterations, s); if (m) atomicAdd(&ctr->ik_feasible, (unsigned long long)__popc(m)); }
+        for (int o = 16; o > 0; o >>= 1) { iters_sum += __shfl_xor_sync(0xffffffffu, iters_sum, o); n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o); }
+        if (lane == 0) { atomicAdd(&ctr->gd_iterations, iters_sum); if (n_ok) atomicAdd(&ctr->ik_feasible, n_ok); }
     }
 }
 
-void ckc_launch_gd_project(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded,
+void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const double* q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded,
                            double* q_out, ckc_layout lo, uint8_t* ok, uint8_t* converged, int32_t* iters, uint8_t* valid,
-                           int32_t* list, int32_t* list_count, ckc_counters_dev* ctr, cudaStream_t st) {
+                           int32_t* list, int32_t* list_count, unsigned long long* work_counter, ckc_counters_dev* ctr, cudaStream_t st) {
     if (n <= 0) return;
-    k_gd_project<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kin, n, q, li, mix64(seed), i0, seeded, q_out, lo, ok, converged, iters, valid,
-                                                              list, list_count, ctr);
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gd_project, CKC_GD_BLOCK, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 2;
+    }
+    int64_t blocks = (int64_t)num_sms * blocks_per_sm;
+    const int64_t needed = (n + CKC_GD_BLOCK - 1) / CKC_GD_BLOCK;
+    if (blocks > needed) blocks = needed;
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+    k_gd_project<<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, seeded, q_out, lo, ok, converged, iters, valid,
+                                                  list, list_count, work_counter, ctr);
 }
 
 /* RX: relaxed-constraint residual + joint limits; survivors go to the collision work list */
@@ -506,8 +559,9 @@ void ckc_launch_rx_check(const ckc_kin_dev& kin, int64_t n, const double* q, ckc
 /* ================================================================================================================ */
 /* flavour 0 = PCS (analytic projection of the passive arm), 1 = GD (Newton projection of all 12 joints) */
 template <int kFlavour>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(CKC_GD_BLOCK)
 k_rbs_expand(const ckc_kin_dev kin, const ckc_rbs_dev r, int nseg, int node_base) {
+    __shared__ double sh_state[kFlavour == 1 ? 36 * CKC_GD_BLOCK : 1];
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     bool cand = false;
     int my_node = -1;
@@ -532,7 +586,8 @@ k_rbs_expand(const ckc_kin_dev kin, const ckc_rbs_dev r, int nseg, int node_base
                         else { ok = project_passive(kin, m + 6, 1, sol, qp); if (ok) { for (int j = 0; j < 6; j++) m[j] = qp[j]; } }
                     } else {
                         int it;
-                        ok = gd_project(kin, m, 10000, &it) && within_limits(kin, m);
+                        const gd_ref gs = { sh_state + (kFlavour == 1 ? threadIdx.x : 0) };
+                        ok = gd_project(kin, gs, m, 10000, &it) && within_limits(kin, m);
                     }
                     if (ok) cand = true; else r.edge_ok[e] = 0;
                 }
@@ -599,8 +654,8 @@ void ckc_launch_rbs_init(const ckc_rbs_dev& r, int n_edges, cudaStream_t st) {
 }
 void ckc_launch_rbs_expand(const ckc_kin_dev& kin, const ckc_rbs_dev& r, int flavour, int nseg, int node_base, cudaStream_t st) {
     if (nseg <= 0) return;
-    if (flavour == 0) k_rbs_expand<0><<<(nseg + 127) / 128, 128, 0, st>>>(kin, r, nseg, node_base);
-    else k_rbs_expand<1><<<(nseg + 127) / 128, 128, 0, st>>>(kin, r, nseg, node_base);
+    if (flavour == 0) k_rbs_expand<0><<<(nseg + CKC_GD_BLOCK - 1) / CKC_GD_BLOCK, CKC_GD_BLOCK, 0, st>>>(kin, r, nseg, node_base);
+    else k_rbs_expand<1><<<(nseg + CKC_GD_BLOCK - 1) / CKC_GD_BLOCK, CKC_GD_BLOCK, 0, st>>>(kin, r, nseg, node_base);
 }
 void ckc_launch_rbs_push(const ckc_rbs_dev& r, int max_cand, const int32_t* d_ncand, const uint8_t* hit, cudaStream_t st) {
     if (max_cand <= 0) return;
