@@ -60,6 +60,7 @@ def load_library():
     L.ckc_spcs_validate_seeded_dev.argtypes = [vp, C.c_uint64, C.c_uint64, i64, dp, dp, dp, vp]
     L.ckc_measure_fma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.ckc_set_stage_timing.argtypes = [vp, C.c_int]
+    L.ckc_set_overlap.argtypes = [vp, C.c_int]
     L.ckc_get_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for name, args in (("ckc_pcs_check_motion_rbs", [vp, i64, dp, dp, dp, dp, dp, dp]),
                        ("ckc_gd_project", [vp, i64, dp, dp, dp, dp, dp]),
@@ -206,6 +207,9 @@ class Checker:
 
     def reset_stats(self):
         self._chk(self.L.ckc_reset_stats(self.ctx))
+
+    def set_overlap(self, on):
+        self._chk(self.L.ckc_set_overlap(self.ctx, 1 if on else 0))
 
     def set_stage_timing(self, on):
         self._chk(self.L.ckc_set_stage_timing(self.ctx, 1 if on else 0))

@@ -651,7 +651,7 @@ __device__ __forceinline__ bool gd_iterate(const ckc_kin_dev& k, const gd_ref& s
  * (each fix-up result is again the exactly representable true remainder).  Falls back to fmod() for huge arguments. */
 __device__ __forceinline__ double fmod_exact(double v, double P) {
     if (!(fabs(v) < 1e6)) return fmod(v, P);
-    const double kq = trunc(v / P);
+    const double kq = trunc(v * (1.0 / P));       /* reciprocal multiply: an off-by-one quotient is repaired below */
     double r = fma(-kq, P, v);
     if (v >= 0) { if (r < 0) r += P; else if (r >= P) r -= P; }
     else { if (r > 0) r -= P; else if (r <= -P) r += P; }

@@ -39,6 +39,20 @@ struct dev_buf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+#define CKC_NUM_LANES 4
+struct ckc_lane {
+    cudaStream_t st = nullptr;
+    cudaStream_t st_hi = nullptr;       /* high-priority stream for the collision stage of this lane's chunk */
+    cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_c = nullptr;
+    dev_buf qin, qout, ac, ik, ok, valid, list, frames, ovf, bigstack, flags, aux, aux2, small;
+    int32_t* list_count() const { return small.as<int32_t>(); }
+    int32_t* work_counter() const { return small.as<int32_t>() + 2; }      /* 2 ints */
+    int32_t* ovf_count() const { return small.as<int32_t>() + 4; }
+    int32_t* rbs_counts() const { return small.as<int32_t>() + 8; }        /* 2 ints */
+    unsigned long long* gd_counter() const { return (unsigned long long*)(small.as<int32_t>() + 12); }
+    void release() { dev_buf* b[] = { &qin, &qout, &ac, &ik, &ok, &valid, &list, &frames, &ovf, &bigstack, &flags, &aux, &aux2, &small }; for (dev_buf* x : b) x->release(); }
+};
+
 struct ckc_ctx {
     int env = 1, device = 0, num_sms = 148;
     std::string err;
@@ -48,10 +62,13 @@ struct ckc_ctx {
     cudaStream_t stream = nullptr;
     int64_t chunk = 1 << 20;            /* samples per internal batch */
     /* persistent device storage */
-    dev_buf d_nodes, d_tris, d_ctr, d_small, d_pairtab, d_static;           /* d_small: list_count, work counters, overflow count */
-    /* per-chunk work buffers */
-    dev_buf d_qin, d_qout, d_ac, d_ik, d_ok, d_valid, d_list, d_frames, d_ovf, d_bigstack, d_flags, d_aux, d_aux2;
-    dev_buf d_qb, d_edge;               /* RBS */
+    dev_buf d_nodes, d_tris, d_ctr, d_pairtab, d_static;           /* d_small: list_count, work counters, overflow count */
+    /* per-chunk work buffers: CKC_NUM_LANES independent sets, each with its own stream, so that the host entry points
+     * can overlap the H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 */
+    ckc_lane lanes[CKC_NUM_LANES];
+    int64_t pipe_chunk = 1 << 17;       /* samples per pipelined chunk of the host entry points */
+    bool overlap = true;                /* device-resident entry points fan out over the lanes */
+    cudaEvent_t ev_fork = nullptr;
     int64_t launches = 0;
     ckc_stats host_stats;
     /* optional per-stage CUDA-event timing */
@@ -369,8 +386,20 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return bail(CKC_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
     ctx->num_sms = prop.multiProcessorCount;
-    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) return bail(CKC_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    for (int l = 0; l < CKC_NUM_LANES; l++) {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        e = cudaStreamCreateWithPriority(&ctx->lanes[l].st, cudaStreamNonBlocking, prio_lo);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->lanes[l].st_hi, cudaStreamNonBlocking, prio_hi);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_p, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_c, cudaEventDisableTiming);
+        if (e == cudaSuccess && l == 0) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = ctx->lanes[l].small.reserve(256);
+        if (e == cudaSuccess) e = cudaMemset(ctx->lanes[l].small.p, 0, 256);
+        if (e != cudaSuccess) { std::string msg = std::string("lane setup: ") + cudaGetErrorString(e); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA; }
+    }
+    ctx->stream = ctx->lanes[0].st;
 
     /* concatenate and upload */
     std::vector<ckc_node> nodes; std::vector<double> tris;
@@ -380,10 +409,10 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
         tris.insert(tris.end(), ctx->meshes[m].tris.begin(), ctx->meshes[m].tris.end());
     }
     bool okc = ctx->d_nodes.reserve(nodes.size() * sizeof(ckc_node)) == cudaSuccess && ctx->d_tris.reserve(tris.size() * 8) == cudaSuccess &&
-               ctx->d_ctr.reserve(sizeof(ckc_counters_dev)) == cudaSuccess && ctx->d_small.reserve(64) == cudaSuccess;
+               ctx->d_ctr.reserve(sizeof(ckc_counters_dev)) == cudaSuccess;
     if (okc) okc = cudaMemcpy(ctx->d_nodes.p, nodes.data(), nodes.size() * sizeof(ckc_node), cudaMemcpyHostToDevice) == cudaSuccess &&
                    cudaMemcpy(ctx->d_tris.p, tris.data(), tris.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
-                   cudaMemset(ctx->d_ctr.p, 0, sizeof(ckc_counters_dev)) == cudaSuccess && cudaMemset(ctx->d_small.p, 0, 64) == cudaSuccess;
+                   cudaMemset(ctx->d_ctr.p, 0, sizeof(ckc_counters_dev)) == cudaSuccess;
     if (!okc) { std::string msg = std::string("device upload: ") + cudaGetErrorString(cudaGetLastError()); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA; }
     ctx->world.nodes = ctx->d_nodes.as<ckc_node>();
     ctx->world.tris = ctx->d_tris.as<double>();
@@ -404,6 +433,10 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
     }
     const char* ch = getenv("CKC_CHUNK");
     if (ch && atoll(ch) >= 1024) ctx->chunk = atoll(ch);
+    ch = getenv("CKC_OVERLAP");
+    if (ch) ctx->overlap = atoi(ch) != 0;
+    ch = getenv("CKC_PIPE_CHUNK");
+    if (ch && atoll(ch) >= 1024) ctx->pipe_chunk = atoll(ch);
     *out = ctx;
     return CKC_OK;
 }
@@ -411,17 +444,18 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
 extern "C" void ckc_destroy(ckc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    dev_buf* bufs[] = { &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_small, &ctx->d_qin, &ctx->d_qout, &ctx->d_ac, &ctx->d_ik, &ctx->d_ok,
-                        &ctx->d_valid, &ctx->d_list, &ctx->d_frames, &ctx->d_ovf, &ctx->d_bigstack, &ctx->d_flags, &ctx->d_aux, &ctx->d_aux2, &ctx->d_qb, &ctx->d_edge };
+    dev_buf* bufs[] = { &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr };
     for (dev_buf* b : bufs) b->release();
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (int l = 0; l < CKC_NUM_LANES; l++) { ctx->lanes[l].release(); if (ctx->lanes[l].ev_done) cudaEventDestroy(ctx->lanes[l].ev_done); if (ctx->lanes[l].ev_p) cudaEventDestroy(ctx->lanes[l].ev_p); if (ctx->lanes[l].ev_c) cudaEventDestroy(ctx->lanes[l].ev_c);
+        if (ctx->lanes[l].st_hi) cudaStreamDestroy(ctx->lanes[l].st_hi); if (ctx->lanes[l].st) cudaStreamDestroy(ctx->lanes[l].st); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
 
 extern "C" int ckc_synchronize(ckc_ctx* ctx) {
     if (!ctx) return CKC_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    for (int l = 0; l < CKC_NUM_LANES; l++) CU(cudaStreamSynchronize(ctx->lanes[l].st));
     return CKC_OK;
 }
 
@@ -458,108 +492,202 @@ extern "C" int ckc_reset_stats(ckc_ctx* ctx) {
 static const ckc_layout AOS = { 12, 1 };
 static ckc_layout soa(int64_t n) { ckc_layout l = { 1, n }; return l; }
 
-static int32_t* p_list_count(ckc_ctx* c) { return c->d_small.as<int32_t>(); }
-static int32_t* p_work_counter(ckc_ctx* c) { return c->d_small.as<int32_t>() + 2; }       /* 2 ints */
-static int32_t* p_ovf_count(ckc_ctx* c) { return c->d_small.as<int32_t>() + 4; }
-
-/* K2 + K3 on the configurations listed in d_list (count on the device) */
-static int run_collision_stage(ckc_ctx* ctx, int64_t m_max, const double* d_q, ckc_layout l, const int32_t* d_list, const int32_t* d_m,
+/* K2 + K3 on the configurations listed in d_list (count on the device), scratch of lane L, stream st */
+static int run_collision_stage(ckc_ctx* ctx, ckc_lane& L, int64_t m_max, const double* d_q, ckc_layout l, const int32_t* d_list, const int32_t* d_m,
                                uint8_t* d_hit, uint8_t* d_valid, uint8_t* d_pair_flags, cudaStream_t st) {
     if (m_max <= 0) return CKC_OK;
-    CU(ctx->d_frames.reserve((size_t)m_max * CKC_FRAME_DOUBLES * 8));
-    CU(ctx->d_ovf.reserve((size_t)m_max * 4));
-    CU(ctx->d_bigstack.reserve((size_t)16 * 8 * 65536 * 4));
+    CU(L.frames.reserve((size_t)m_max * CKC_FRAME_DOUBLES * 8));
+    CU(L.ovf.reserve((size_t)m_max * 4));
+    CU(L.bigstack.reserve((size_t)16 * 8 * 65536 * 4));
+    /* on the lane's own stream the collision stage moves to the lane's HIGH-PRIORITY stream: its blocks then win the SM slots
+     * that free up while the persistent projection kernels of the other lanes are still queued */
+    const bool hop = ctx->overlap && st == L.st && L.st_hi;
+    cudaStream_t lane_st = st;
+    if (hop) { CU(cudaEventRecord(L.ev_p, st)); CU(cudaStreamWaitEvent(L.st_hi, L.ev_p, 0)); st = L.st_hi; }
     { stage_scope ts(ctx, st, 1);
-      ckc_launch_link_frames(ctx->world, d_q, l, d_list, d_m, m_max, ctx->d_frames.as<double>(), st); }
+      ckc_launch_link_frames(ctx->world, d_q, l, d_list, d_m, m_max, L.frames.as<double>(), st); }
     ckc_launch_cfg cfg = { ctx->num_sms };
     { stage_scope ts(ctx, st, 2);
-      ckc_launch_collide(ctx->world, cfg, ctx->d_frames.as<double>(), d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, p_work_counter(ctx),
-                         ctx->d_ovf.as<int32_t>(), p_ovf_count(ctx), ctx->d_bigstack.as<uint32_t>(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
+      ckc_launch_collide(ctx->world, cfg, L.frames.as<double>(), d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, L.work_counter(),
+                         L.ovf.as<int32_t>(), L.ovf_count(), L.bigstack.as<uint32_t>(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
     ctx->launches += 3;
     CU(cudaGetLastError());
+    if (hop) { CU(cudaEventRecord(L.ev_c, st)); CU(cudaStreamWaitEvent(lane_st, L.ev_c, 0)); }
     return CKC_OK;
 }
 
 /* project (+ collide) one device-resident chunk */
-static int run_pcs_chunk(ckc_ctx* ctx, int64_t n, const double* d_q, ckc_layout li, const int8_t* d_ac, const int8_t* d_ik, uint64_t seed,
+static int run_pcs_chunk(ckc_ctx* ctx, ckc_lane& L, int64_t n, const double* d_q, ckc_layout li, const int8_t* d_ac, const int8_t* d_ik, uint64_t seed,
                          uint64_t i0, int seeded, double* d_qout, ckc_layout lo, uint8_t* d_ok, uint8_t* d_valid, bool collide, cudaStream_t st) {
-    CU(ctx->d_list.reserve((size_t)n * 4));
-    CU(cudaMemsetAsync(p_list_count(ctx), 0, 4, st));
+    CU(L.list.reserve((size_t)n * 4));
+    CU(cudaMemsetAsync(L.list_count(), 0, 4, st));
     { stage_scope ts(ctx, st, 0);
-      ckc_launch_pcs_project(ctx->kin, n, d_q, li, d_ac, d_ik, seed, i0, seeded, d_qout, lo, d_ok, d_valid, collide ? ctx->d_list.as<int32_t>() : nullptr,
-                             p_list_count(ctx), ctx->d_ctr.as<ckc_counters_dev>(), st); }
+      ckc_launch_pcs_project(ctx->kin, n, d_q, li, d_ac, d_ik, seed, i0, seeded, d_qout, lo, d_ok, d_valid, collide ? L.list.as<int32_t>() : nullptr,
+                             L.list_count(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
     ctx->launches += 1;
     ctx->host_stats.ik_calls += n;
     CU(cudaGetLastError());
-    if (collide) return run_collision_stage(ctx, n, d_qout, lo, ctx->d_list.as<int32_t>(), p_list_count(ctx), nullptr, d_valid, nullptr, st);
+    if (collide) return run_collision_stage(ctx, L, n, d_qout, lo, L.list.as<int32_t>(), L.list_count(), nullptr, d_valid, nullptr, st);
+    return CKC_OK;
+}
+
+static int run_gd_chunk(ckc_ctx* ctx, ckc_lane& L, int64_t n, const double* d_q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded, double* d_qout,
+                        ckc_layout lo, uint8_t* d_ok, uint8_t* d_conv, int32_t* d_iters, uint8_t* d_valid, bool collide, cudaStream_t st) {
+    CU(L.list.reserve((size_t)n * 4));
+    CU(cudaMemsetAsync(L.list_count(), 0, 4, st));
+    { stage_scope ts(ctx, st, 0);
+      ckc_launch_gd_project(ctx->kin, ctx->num_sms, n, d_q, li, seed, i0, seeded, d_qout, lo, d_ok, d_conv, d_iters, d_valid,
+                            collide ? L.list.as<int32_t>() : nullptr, L.list_count(), L.gd_counter(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
+    ctx->launches += 1;
+    ctx->host_stats.ik_calls += n;
+    CU(cudaGetLastError());
+    if (collide) return run_collision_stage(ctx, L, n, d_qout, lo, L.list.as<int32_t>(), L.list_count(), nullptr, d_valid, nullptr, st);
     return CKC_OK;
 }
 
 /* ---------------------------------------------------------------------------------------------------------------- */
-/* PCS entry points                                                                                                   */
+/* host entry points of the projection flavours: software pipeline over the lanes                                     */
+/*   chunk k runs entirely on lane k % CKC_NUM_LANES (H2D -> kernels -> D2H in stream order); the lanes' streams overlap */
+/*   each other, so copies in both directions and kernels of neighbouring chunks run concurrently (pinned host memory). */
 /* ---------------------------------------------------------------------------------------------------------------- */
-static int pcs_host(ckc_ctx* ctx, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out, uint8_t* ok, uint8_t* valid, bool collide) {
-    if (!ctx || n < 0 || (n > 0 && (!q || !ik))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out,
+                        uint8_t* ok, uint8_t* conv, int32_t* iters, uint8_t* valid, bool collide) {
+    if (!ctx || n < 0 || (n > 0 && (!q || (flavour == 0 && !ik)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    for (int64_t off = 0; off < n; off += ctx->chunk) {
-        const int64_t c = std::min(ctx->chunk, n - off);
-        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_qout.reserve((size_t)c * 96)); CU(ctx->d_ac.reserve((size_t)c)); CU(ctx->d_ik.reserve((size_t)c));
-        CU(ctx->d_ok.reserve((size_t)c)); CU(ctx->d_valid.reserve((size_t)c));
-        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
-        if (ac) CU(cudaMemcpyAsync(ctx->d_ac.p, ac + off, (size_t)c, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->d_ik.p, ik + off, (size_t)c, cudaMemcpyHostToDevice, st));
-        int rc = run_pcs_chunk(ctx, c, ctx->d_qin.as<double>(), AOS, ac ? ctx->d_ac.as<int8_t>() : nullptr, ctx->d_ik.as<int8_t>(), 0, 0, 0,
-                               ctx->d_qout.as<double>(), AOS, ctx->d_ok.as<uint8_t>(), ctx->d_valid.as<uint8_t>(), collide, st);
+    const int64_t C = n <= ctx->pipe_chunk ? std::max<int64_t>(n, 1) : ctx->pipe_chunk;
+    int k = 0;
+    for (int64_t off = 0; off < n; off += C, k++) {
+        const int64_t c = std::min(C, n - off);
+        ckc_lane& L = ctx->lanes[k % CKC_NUM_LANES];
+        cudaStream_t st = L.st;
+        CU(L.qin.reserve((size_t)C * 96)); CU(L.qout.reserve((size_t)C * 96)); CU(L.ok.reserve((size_t)C)); CU(L.valid.reserve((size_t)C));
+        CU(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        int rc;
+        if (flavour == 0) {
+            CU(L.ac.reserve((size_t)C)); CU(L.ik.reserve((size_t)C));
+            if (ac) CU(cudaMemcpyAsync(L.ac.p, ac + off, (size_t)c, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(L.ik.p, ik + off, (size_t)c, cudaMemcpyHostToDevice, st));
+            rc = run_pcs_chunk(ctx, L, c, L.qin.as<double>(), AOS, ac ? L.ac.as<int8_t>() : nullptr, L.ik.as<int8_t>(), 0, 0, 0, L.qout.as<double>(), AOS,
+                               L.ok.as<uint8_t>(), L.valid.as<uint8_t>(), collide, st);
+        } else {
+            CU(L.aux.reserve((size_t)C)); CU(L.aux2.reserve((size_t)C * 4));
+            rc = run_gd_chunk(ctx, L, c, L.qin.as<double>(), AOS, 0, 0, 0, L.qout.as<double>(), AOS, L.ok.as<uint8_t>(), L.aux.as<uint8_t>(),
+                              L.aux2.as<int32_t>(), L.valid.as<uint8_t>(), collide, st);
+        }
         if (rc) return rc;
-        if (q_out) CU(cudaMemcpyAsync(q_out + off * 12, ctx->d_qout.p, (size_t)c * 96, cudaMemcpyDeviceToHost, st));
-        if (ok) CU(cudaMemcpyAsync(ok + off, ctx->d_ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
-        if (valid) CU(cudaMemcpyAsync(valid + off, ctx->d_valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        if (q_out) CU(cudaMemcpyAsync(q_out + off * 12, L.qout.p, (size_t)c * 96, cudaMemcpyDeviceToHost, st));
+        if (ok) CU(cudaMemcpyAsync(ok + off, L.ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (conv) CU(cudaMemcpyAsync(conv + off, L.aux.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (iters) CU(cudaMemcpyAsync(iters + off, L.aux2.p, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+        if (valid) CU(cudaMemcpyAsync(valid + off, L.valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
     }
+    for (int l = 0; l < CKC_NUM_LANES; l++) CU(cudaStreamSynchronize(ctx->lanes[l].st));
     return CKC_OK;
 }
 
 extern "C" int ckc_pcs_project(ckc_ctx* ctx, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out, uint8_t* ok) {
-    return pcs_host(ctx, n, q, ac, ik, q_out, ok, nullptr, false);
+    return project_host(ctx, 0, n, q, ac, ik, q_out, ok, nullptr, nullptr, nullptr, false);
 }
 extern "C" int ckc_pcs_validate(ckc_ctx* ctx, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out, uint8_t* ok, uint8_t* valid) {
     if (!valid) return fail(ctx, CKC_ERR_ARG, "valid must not be NULL");
     if (ctx) ctx->host_stats.is_valid_calls += n;
-    return pcs_host(ctx, n, q, ac, ik, q_out, ok, valid, true);
+    return project_host(ctx, 0, n, q, ac, ik, q_out, ok, nullptr, nullptr, valid, true);
+}
+extern "C" int ckc_gd_project(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* ok, uint8_t* converged, int32_t* iters) {
+    return project_host(ctx, 1, n, q, nullptr, nullptr, q_out, ok, converged, iters, nullptr, false);
+}
+extern "C" int ckc_gd_validate(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* valid) {
+    if (!valid) return fail(ctx, CKC_ERR_ARG, "valid must not be NULL");
+    if (ctx) ctx->host_stats.is_valid_calls += n;
+    return project_host(ctx, 1, n, q, nullptr, nullptr, q_out, nullptr, nullptr, nullptr, valid, true);
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* device-resident entry points: fork / join over the lanes                                                           */
+/*   the batch is cut into up to CKC_NUM_LANES chunks that run on the lanes' own streams (forked from / joined to the   */
+/*   caller's stream with events), so the latency-bound collision kernel of one chunk overlaps the FP64-bound projection */
+/*   kernel of the next.  CKC_OVERLAP=0 (ckc_set_overlap) runs everything in order on the caller's stream instead.       */
+/* ---------------------------------------------------------------------------------------------------------------- */
+template <class F>
+static int dev_fanout(ckc_ctx* ctx, cudaStream_t user, int64_t n, bool fan, F body) {
+    if (n <= 0) return CKC_OK;
+    if (!fan || !ctx->overlap || n < (1 << 17)) {
+        for (int64_t off = 0; off < n; off += ctx->chunk) {
+            int rc = body(ctx->lanes[0], off, std::min(ctx->chunk, n - off), user);
+            if (rc) return rc;
+        }
+        return CKC_OK;
+    }
+    int64_t c = (n + CKC_NUM_LANES - 1) / CKC_NUM_LANES;
+    c = std::max<int64_t>(c, 1 << 16);
+    c = std::min<int64_t>(c, ctx->chunk);
+    CU(cudaEventRecord(ctx->ev_fork, user));
+    int used = 0, k = 0;
+    for (int64_t off = 0; off < n; off += c, k++) {
+        const int li = k % CKC_NUM_LANES;
+        ckc_lane& L = ctx->lanes[li];
+        if (k < CKC_NUM_LANES) { CU(cudaStreamWaitEvent(L.st, ctx->ev_fork, 0)); used = k + 1; }
+        int rc = body(L, off, std::min(c, n - off), L.st);
+        if (rc) return rc;
+    }
+    for (int li = 0; li < used; li++) {
+        CU(cudaEventRecord(ctx->lanes[li].ev_done, ctx->lanes[li].st));
+        CU(cudaStreamWaitEvent(user, ctx->lanes[li].ev_done, 0));
+    }
+    return CKC_OK;
+}
+
+extern "C" int ckc_set_overlap(ckc_ctx* ctx, int enable) {
+    if (!ctx) return CKC_ERR_ARG;
+    ctx->overlap = enable != 0;
+    return CKC_OK;
 }
 
 extern "C" int ckc_pcs_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, const int8_t* d_ac, const int8_t* d_ik, double* d_q_out,
                                     uint8_t* d_ok, uint8_t* d_valid, void* stream) {
     if (!ctx || n < 0 || !d_q || !d_ik || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    /* the projected configurations are needed by the collision stage: use the caller's buffer or an internal one */
-    double* qo = d_q_out;
-    if (!qo) { CU(ctx->d_qout.reserve((size_t)n * 96)); qo = ctx->d_qout.as<double>(); }
-    for (int64_t off = 0; off < n; off += ctx->chunk) {
-        const int64_t c = std::min(ctx->chunk, n - off);
-        ckc_layout l = { 1, n };                       /* SoA over the whole batch; chunk = index window */
-        int rc = run_pcs_chunk(ctx, c, d_q + off, l, d_ac ? d_ac + off : nullptr, d_ik + off, 0, 0, 0, qo + off, l, d_ok ? d_ok + off : nullptr,
-                               d_valid + off, true, st);
-        if (rc) return rc;
-    }
-    return CKC_OK;
+    return dev_fanout(ctx, (cudaStream_t)stream, n, true, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
+        /* the projected configurations are needed by the collision stage: the caller's buffer or an internal one */
+        double* qo; ckc_layout lo;
+        if (d_q_out) { qo = d_q_out + off; lo = soa(n); }
+        else { CU(L.qout.reserve((size_t)c * 96)); qo = L.qout.as<double>(); lo = soa(c); }
+        return run_pcs_chunk(ctx, L, c, d_q + off, soa(n), d_ac ? d_ac + off : nullptr, d_ik + off, 0, 0, 0, qo, lo, d_ok ? d_ok + off : nullptr,
+                             d_valid + off, true, st);
+    });
 }
 
 extern "C" int ckc_spcs_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out, uint8_t* d_ok, uint8_t* d_valid, void* stream) {
     if (!ctx || n < 0 || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    for (int64_t off = 0; off < n; off += ctx->chunk) {
-        const int64_t c = std::min(ctx->chunk, n - off);
+    return dev_fanout(ctx, (cudaStream_t)stream, n, true, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
         double* qo; ckc_layout l;
         if (d_q_out) { qo = d_q_out + off; l = soa(n); }
-        else { CU(ctx->d_qout.reserve((size_t)c * 96)); qo = ctx->d_qout.as<double>(); l = soa(c); }
-        int rc = run_pcs_chunk(ctx, c, nullptr, l, nullptr, nullptr, seed, i0 + (uint64_t)off, 1, qo, l, d_ok ? d_ok + off : nullptr, d_valid + off, true, st);
-        if (rc) return rc;
-    }
-    return CKC_OK;
+        else { CU(L.qout.reserve((size_t)c * 96)); qo = L.qout.as<double>(); l = soa(c); }
+        return run_pcs_chunk(ctx, L, c, nullptr, l, nullptr, nullptr, seed, i0 + (uint64_t)off, 1, qo, l, d_ok ? d_ok + off : nullptr, d_valid + off, true, st);
+    });
+}
+
+extern "C" int ckc_gd_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, double* d_q_out, uint8_t* d_valid, void* stream) {
+    if (!ctx || n < 0 || !d_q || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    return dev_fanout(ctx, (cudaStream_t)stream, n, false /* the persistent Newton kernel fills the GPU; chunk tails cost more than the overlap gains (measured) */, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
+        double* qo; ckc_layout lo;
+        if (d_q_out) { qo = d_q_out + off; lo = soa(n); }
+        else { CU(L.qout.reserve((size_t)c * 96)); qo = L.qout.as<double>(); lo = soa(c); }
+        return run_gd_chunk(ctx, L, c, d_q + off, soa(n), 0, 0, 0, qo, lo, nullptr, nullptr, nullptr, d_valid + off, true, st);
+    });
+}
+
+extern "C" int ckc_sgd_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out, uint8_t* d_ok, uint8_t* d_valid, void* stream) {
+    if (!ctx || n < 0 || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    return dev_fanout(ctx, (cudaStream_t)stream, n, false /* the persistent Newton kernel fills the GPU; chunk tails cost more than the overlap gains (measured) */, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
+        double* qo; ckc_layout l;
+        if (d_q_out) { qo = d_q_out + off; l = soa(n); }
+        else { CU(L.qout.reserve((size_t)c * 96)); qo = L.qout.as<double>(); l = soa(c); }
+        return run_gd_chunk(ctx, L, c, nullptr, l, seed, i0 + (uint64_t)off, 1, qo, l, d_ok ? d_ok + off : nullptr, nullptr, nullptr, d_valid + off, true, st);
+    });
 }
 
 /* ---------------------------------------------------------------------------------------------------------------- */
@@ -568,18 +696,19 @@ extern "C" int ckc_spcs_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_
 static int collide_host(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* hit, uint8_t* flags) {
     if (!ctx || n < 0 || (n > 0 && (!q || (!hit && !flags)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+    ckc_lane& L = ctx->lanes[0];
+    cudaStream_t st = L.st;
     const int64_t chunk = std::min<int64_t>(ctx->chunk, 1 << 18);
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t c = std::min(chunk, n - off);
-        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_ok.reserve((size_t)c));
-        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
-        if (flags) { CU(ctx->d_flags.reserve((size_t)c * CKC_MAX_PAIRS)); CU(cudaMemsetAsync(ctx->d_flags.p, 0, (size_t)c * CKC_MAX_PAIRS, st)); }
-        int rc = run_collision_stage(ctx, c, ctx->d_qin.as<double>(), AOS, nullptr, nullptr, ctx->d_ok.as<uint8_t>(), nullptr,
-                                     flags ? ctx->d_flags.as<uint8_t>() : nullptr, st);
+        CU(L.qin.reserve((size_t)c * 96)); CU(L.ok.reserve((size_t)c));
+        CU(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        if (flags) { CU(L.flags.reserve((size_t)c * CKC_MAX_PAIRS)); CU(cudaMemsetAsync(L.flags.p, 0, (size_t)c * CKC_MAX_PAIRS, st)); }
+        int rc = run_collision_stage(ctx, L, c, L.qin.as<double>(), AOS, nullptr, nullptr, L.ok.as<uint8_t>(), nullptr,
+                                     flags ? L.flags.as<uint8_t>() : nullptr, st);
         if (rc) return rc;
-        if (hit) CU(cudaMemcpyAsync(hit + off, ctx->d_ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
-        if (flags) CU(cudaMemcpyAsync(flags + off * CKC_MAX_PAIRS, ctx->d_flags.p, (size_t)c * CKC_MAX_PAIRS, cudaMemcpyDeviceToHost, st));
+        if (hit) CU(cudaMemcpyAsync(hit + off, L.ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (flags) CU(cudaMemcpyAsync(flags + off * CKC_MAX_PAIRS, L.flags.p, (size_t)c * CKC_MAX_PAIRS, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return CKC_OK;
@@ -591,15 +720,16 @@ extern "C" int ckc_collide_pairs(ckc_ctx* ctx, int64_t n, const double* q, uint8
 extern "C" int ckc_check_angle_limits(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* ok) {
     if (!ctx || n < 0 || (n > 0 && (!q || !ok))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+    ckc_lane& L = ctx->lanes[0];
+    cudaStream_t st = L.st;
     for (int64_t off = 0; off < n; off += ctx->chunk) {
         const int64_t c = std::min(ctx->chunk, n - off);
-        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_ok.reserve((size_t)c));
-        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
-        ckc_launch_limits(ctx->kin, c, ctx->d_qin.as<double>(), AOS, ctx->d_ok.as<uint8_t>(), st);
+        CU(L.qin.reserve((size_t)c * 96)); CU(L.ok.reserve((size_t)c));
+        CU(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        ckc_launch_limits(ctx->kin, c, L.qin.as<double>(), AOS, L.ok.as<uint8_t>(), st);
         ctx->launches++;
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(ok + off, ctx->d_ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ok + off, L.ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return CKC_OK;
@@ -608,15 +738,16 @@ extern "C" int ckc_check_angle_limits(ckc_ctx* ctx, int64_t n, const double* q, 
 extern "C" int ckc_identify_ik(ckc_ctx* ctx, int64_t n, const double* q, int8_t* ik01) {
     if (!ctx || n < 0 || (n > 0 && (!q || !ik01))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+    ckc_lane& L = ctx->lanes[0];
+    cudaStream_t st = L.st;
     for (int64_t off = 0; off < n; off += ctx->chunk) {
         const int64_t c = std::min(ctx->chunk, n - off);
-        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_aux.reserve((size_t)c * 2));
-        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
-        ckc_launch_identify_ik(ctx->kin, c, ctx->d_qin.as<double>(), AOS, ctx->d_aux.as<int8_t>(), st);
+        CU(L.qin.reserve((size_t)c * 96)); CU(L.aux.reserve((size_t)c * 2));
+        CU(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        ckc_launch_identify_ik(ctx->kin, c, L.qin.as<double>(), AOS, L.aux.as<int8_t>(), st);
         ctx->launches++;
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(ik01 + off * 2, ctx->d_aux.p, (size_t)c * 2, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ik01 + off * 2, L.aux.p, (size_t)c * 2, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return CKC_OK;
@@ -625,14 +756,15 @@ extern "C" int ckc_identify_ik(ckc_ctx* ctx, int64_t n, const double* q, int8_t*
 extern "C" int ckc_measure_fma_peak(ckc_ctx* ctx, int precision, double* tflops) {
     if (!ctx || !tflops || (precision != 32 && precision != 64)) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    CU(ctx->d_aux.reserve(64));
+    ckc_lane& L = ctx->lanes[0];
+    CU(L.aux.reserve(64));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     const int iters = precision == 64 ? 1 << 15 : 1 << 16;
     double best = 0;
     for (int rep = 0; rep < 4; rep++) {
         CU(cudaEventRecord(e0, ctx->stream));
-        ckc_launch_fma_peak(precision, ctx->num_sms, iters, ctx->d_aux.as<float>(), ctx->stream);
+        ckc_launch_fma_peak(precision, ctx->num_sms, iters, L.aux.as<float>(), ctx->stream);
         CU(cudaEventRecord(e1, ctx->stream));
         CU(cudaEventSynchronize(e1));
         float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
@@ -648,100 +780,25 @@ extern "C" int ckc_measure_fma_peak(ckc_ctx* ctx, int precision, double* tflops)
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* GD / RX entry points                                                                                               */
 /* ---------------------------------------------------------------------------------------------------------------- */
-static int run_gd_chunk(ckc_ctx* ctx, int64_t n, const double* d_q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded, double* d_qout,
-                        ckc_layout lo, uint8_t* d_ok, uint8_t* d_conv, int32_t* d_iters, uint8_t* d_valid, bool collide, cudaStream_t st) {
-    CU(ctx->d_list.reserve((size_t)n * 4));
-    CU(cudaMemsetAsync(p_list_count(ctx), 0, 4, st));
-    { stage_scope ts(ctx, st, 0);
-      ckc_launch_gd_project(ctx->kin, ctx->num_sms, n, d_q, li, seed, i0, seeded, d_qout, lo, d_ok, d_conv, d_iters, d_valid,
-                            collide ? ctx->d_list.as<int32_t>() : nullptr, p_list_count(ctx), (unsigned long long*)(ctx->d_small.as<int32_t>() + 12),
-                            ctx->d_ctr.as<ckc_counters_dev>(), st); }
-    ctx->launches += 1;
-    ctx->host_stats.ik_calls += n;
-    CU(cudaGetLastError());
-    if (collide) return run_collision_stage(ctx, n, d_qout, lo, ctx->d_list.as<int32_t>(), p_list_count(ctx), nullptr, d_valid, nullptr, st);
-    return CKC_OK;
-}
-
-static int gd_host(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* ok, uint8_t* conv, int32_t* iters, uint8_t* valid, bool collide) {
-    if (!ctx || n < 0 || (n > 0 && !q)) return fail(ctx, CKC_ERR_ARG, "bad argument");
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    for (int64_t off = 0; off < n; off += ctx->chunk) {
-        const int64_t c = std::min(ctx->chunk, n - off);
-        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_qout.reserve((size_t)c * 96)); CU(ctx->d_ok.reserve((size_t)c)); CU(ctx->d_valid.reserve((size_t)c));
-        CU(ctx->d_aux.reserve((size_t)c)); CU(ctx->d_aux2.reserve((size_t)c * 4));
-        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
-        int rc = run_gd_chunk(ctx, c, ctx->d_qin.as<double>(), AOS, 0, 0, 0, ctx->d_qout.as<double>(), AOS, ctx->d_ok.as<uint8_t>(), ctx->d_aux.as<uint8_t>(),
-                              ctx->d_aux2.as<int32_t>(), ctx->d_valid.as<uint8_t>(), collide, st);
-        if (rc) return rc;
-        if (q_out) CU(cudaMemcpyAsync(q_out + off * 12, ctx->d_qout.p, (size_t)c * 96, cudaMemcpyDeviceToHost, st));
-        if (ok) CU(cudaMemcpyAsync(ok + off, ctx->d_ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
-        if (conv) CU(cudaMemcpyAsync(conv + off, ctx->d_aux.p, (size_t)c, cudaMemcpyDeviceToHost, st));
-        if (iters) CU(cudaMemcpyAsync(iters + off, ctx->d_aux2.p, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
-        if (valid) CU(cudaMemcpyAsync(valid + off, ctx->d_valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    }
-    return CKC_OK;
-}
-
-extern "C" int ckc_gd_project(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* ok, uint8_t* converged, int32_t* iters) {
-    return gd_host(ctx, n, q, q_out, ok, converged, iters, nullptr, false);
-}
-extern "C" int ckc_gd_validate(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* valid) {
-    if (!valid) return fail(ctx, CKC_ERR_ARG, "valid must not be NULL");
-    if (ctx) ctx->host_stats.is_valid_calls += n;
-    return gd_host(ctx, n, q, q_out, nullptr, nullptr, nullptr, valid, true);
-}
-
-extern "C" int ckc_gd_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, double* d_q_out, uint8_t* d_valid, void* stream) {
-    if (!ctx || n < 0 || !d_q || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    double* qo = d_q_out;
-    if (!qo) { CU(ctx->d_qout.reserve((size_t)n * 96)); qo = ctx->d_qout.as<double>(); }
-    for (int64_t off = 0; off < n; off += ctx->chunk) {
-        const int64_t c = std::min(ctx->chunk, n - off);
-        ckc_layout l = { 1, n };
-        int rc = run_gd_chunk(ctx, c, d_q + off, l, 0, 0, 0, qo + off, l, nullptr, nullptr, nullptr, d_valid + off, true, st);
-        if (rc) return rc;
-    }
-    return CKC_OK;
-}
-
-extern "C" int ckc_sgd_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out, uint8_t* d_ok, uint8_t* d_valid, void* stream) {
-    if (!ctx || n < 0 || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    for (int64_t off = 0; off < n; off += ctx->chunk) {
-        const int64_t c = std::min(ctx->chunk, n - off);
-        double* qo; ckc_layout l;
-        if (d_q_out) { qo = d_q_out + off; l = soa(n); }
-        else { CU(ctx->d_qout.reserve((size_t)c * 96)); qo = ctx->d_qout.as<double>(); l = soa(c); }
-        int rc = run_gd_chunk(ctx, c, nullptr, l, seed, i0 + (uint64_t)off, 1, qo, l, d_ok ? d_ok + off : nullptr, nullptr, nullptr, d_valid + off, true, st);
-        if (rc) return rc;
-    }
-    return CKC_OK;
-}
-
 extern "C" int ckc_rx_validate(ckc_ctx* ctx, int64_t n, const double* q, double epsilon, uint8_t* valid, double* resid) {
     if (!ctx || n < 0 || (n > 0 && (!q || !valid))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+    ckc_lane& L = ctx->lanes[0];
+    cudaStream_t st = L.st;
     ctx->host_stats.is_valid_calls += n;
     for (int64_t off = 0; off < n; off += ctx->chunk) {
         const int64_t c = std::min(ctx->chunk, n - off);
-        CU(ctx->d_qin.reserve((size_t)c * 96)); CU(ctx->d_valid.reserve((size_t)c)); CU(ctx->d_aux2.reserve((size_t)c * 8)); CU(ctx->d_list.reserve((size_t)c * 4));
-        CU(cudaMemcpyAsync(ctx->d_qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
-        CU(cudaMemsetAsync(p_list_count(ctx), 0, 4, st));
-        ckc_launch_rx_check(ctx->kin, c, ctx->d_qin.as<double>(), AOS, epsilon, nullptr, ctx->d_aux2.as<double>(), ctx->d_valid.as<uint8_t>(),
-                            ctx->d_list.as<int32_t>(), p_list_count(ctx), st);
+        CU(L.qin.reserve((size_t)c * 96)); CU(L.valid.reserve((size_t)c)); CU(L.aux2.reserve((size_t)c * 8)); CU(L.list.reserve((size_t)c * 4));
+        CU(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(L.list_count(), 0, 4, st));
+        ckc_launch_rx_check(ctx->kin, c, L.qin.as<double>(), AOS, epsilon, nullptr, L.aux2.as<double>(), L.valid.as<uint8_t>(),
+                            L.list.as<int32_t>(), L.list_count(), st);
         ctx->launches++; ctx->host_stats.ik_calls += c;
         CU(cudaGetLastError());
-        int rc = run_collision_stage(ctx, c, ctx->d_qin.as<double>(), AOS, ctx->d_list.as<int32_t>(), p_list_count(ctx), nullptr, ctx->d_valid.as<uint8_t>(), nullptr, st);
+        int rc = run_collision_stage(ctx, L, c, L.qin.as<double>(), AOS, L.list.as<int32_t>(), L.list_count(), nullptr, L.valid.as<uint8_t>(), nullptr, st);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(valid + off, ctx->d_valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
-        if (resid) CU(cudaMemcpyAsync(resid + off, ctx->d_aux2.p, (size_t)c * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(valid + off, L.valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (resid) CU(cudaMemcpyAsync(resid + off, L.aux2.p, (size_t)c * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return CKC_OK;
@@ -768,7 +825,8 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
     if (!ctx || n_edges < 0 || n_edges > (1 << 28) || (n_edges > 0 && (!qa || !qb || !ok || (flavour == 0 && !ik)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     if (n_edges == 0) return CKC_OK;
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+    ckc_lane& L = ctx->lanes[0];
+    cudaStream_t st = L.st;
     const int ne = (int)n_edges;
     dev_buf seg[2], cand, pool, eok, nck, hit, eac, eik;
     struct cleanup { dev_buf* b[9]; ~cleanup() { for (dev_buf* x : b) x->release(); } } guard = { { &seg[0], &seg[1], &cand, &pool, &eok, &nck, &hit, &eac, &eik } };
@@ -781,7 +839,7 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
     CU(cudaMemcpy2DAsync((char*)pool.p + 96, 192, qb, 96, 96, ne, cudaMemcpyHostToDevice, st));
     if (ac) CU(cudaMemcpyAsync(eac.p, ac, ne, cudaMemcpyHostToDevice, st));
     if (ik) CU(cudaMemcpyAsync(eik.p, ik, ne, cudaMemcpyHostToDevice, st));
-    int32_t* d_cnt = ctx->d_small.as<int32_t>() + 8;       /* [0] candidates, [1] next segments */
+    int32_t* d_cnt = L.rbs_counts();                       /* [0] candidates, [1] next segments */
     int cur = 0;
     int64_t nseg = ne, nnodes = 2 * (int64_t)ne;
     auto make = [&](int c) {
@@ -819,7 +877,7 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
         CU(cudaStreamSynchronize(st));
         const int64_t sub = 1 << 21;
         for (int64_t off = 0; off < h[0]; off += sub) {
-            int rc = run_collision_stage(ctx, std::min<int64_t>(sub, h[0] - off), pool.as<double>(), AOS, r.cand_node + off, nullptr, hit.as<uint8_t>(), nullptr, nullptr, st);
+            int rc = run_collision_stage(ctx, L, std::min<int64_t>(sub, h[0] - off), pool.as<double>(), AOS, r.cand_node + off, nullptr, hit.as<uint8_t>(), nullptr, nullptr, st);
             if (rc) return rc;
         }
         { stage_scope ts(ctx, st, 3);
@@ -873,5 +931,21 @@ extern "C" int ckc_get_stage_times(ckc_ctx* ctx, double ms[4], int64_t launches[
     }
     ctx->pending.clear();
     for (int i = 0; i < 4; i++) { ms[i] = ctx->stage_ms[i]; launches[i] = ctx->stage_n[i]; }
+    return CKC_OK;
+}
+
+
+/* debug aid (not part of include/ckc.h): prints every pending stage interval relative to the first recorded event */
+extern "C" int ckc_debug_timeline(ckc_ctx* ctx) {
+    if (!ctx || ctx->pending.empty()) return CKC_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    for (int l = 0; l < CKC_NUM_LANES; l++) cudaStreamSynchronize(ctx->lanes[l].st);
+    cudaEvent_t base = ctx->pending[0].e0;
+    static const char* nm[4] = { "project", "frames", "collide", "rbs" };
+    for (auto& p : ctx->pending) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, base, p.e0); cudaEventElapsedTime(&b, base, p.e1);
+        fprintf(stderr, "  %-8s %8.3f -> %8.3f ms  (%.3f)\n", nm[p.stage], a, b, b - a);
+    }
     return CKC_OK;
 }

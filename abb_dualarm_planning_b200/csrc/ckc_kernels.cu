@@ -181,8 +181,11 @@ __device__ __forceinline__ double leaf_distance(const ckc_world_dev& w, const do
     return tri_dist(S, Tt);
 }
 
+#ifndef CKC_COLLIDE_MINBLOCKS
+#define CKC_COLLIDE_MINBLOCKS 4
+#endif
 template <bool kBigStack>
-__global__ void __launch_bounds__(CKC_COLLIDE_WARPS * 32)
+__global__ void __launch_bounds__(CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_MINBLOCKS)
 k_collide(const ckc_world_dev w, const collide_args a) {
     __shared__ float s_frames[CKC_COLLIDE_WARPS][CKC_NUM_FRAMES * 12];
     __shared__ uint32_t s_stack[kBigStack ? 1 : CKC_COLLIDE_WARPS][kBigStack ? 1 : CKC_STACK_CAP];
@@ -330,7 +333,7 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st);           /* work_counter[0] main pass, [1] overflow pass */
     cudaMemsetAsync(ovf_count, 0, sizeof(int32_t), st);
     int64_t blocks = (m_max + CKC_COLLIDE_WARPS - 1) / CKC_COLLIDE_WARPS;
-    const int64_t resident = (int64_t)cfg.num_sms * 6;
+    const int64_t resident = (int64_t)cfg.num_sms * CKC_COLLIDE_MINBLOCKS * 3;
     if (blocks > resident) blocks = resident;
     k_collide<false><<<(unsigned)blocks, CKC_COLLIDE_WARPS * 32, 0, st>>>(w, a);
     /* overflow pass: tiny grid, global-memory stacks; exits immediately when nothing overflowed */
@@ -519,7 +522,8 @@ void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gd_project, CKC_GD_BLOCK, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 2;
     }
     int64_t blocks = (int64_t)num_sms * blocks_per_sm;
-    const int64_t needed = (n + CKC_GD_BLOCK - 1) / CKC_GD_BLOCK;
+    /* at least ~6 samples per lane so that the lane-level work stealing can balance the iteration counts */
+    const int64_t needed = (n + 6 * CKC_GD_BLOCK - 1) / (6 * CKC_GD_BLOCK);
     if (blocks > needed) blocks = needed;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
     k_gd_project<<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, seeded, q_out, lo, ok, converged, iters, valid,

@@ -127,6 +127,10 @@ int ckc_spcs_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64
 int ckc_gd_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, double* d_q_out, uint8_t* d_valid, void* stream);
 int ckc_sgd_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out,
                                 uint8_t* d_ok, uint8_t* d_valid, void* stream);
+/* The device-resident entry points cut a batch into a few chunks that run on internal streams (forked from / joined to the
+ * caller's stream), overlapping the collision kernel of one chunk with the projection kernel of the next.  enable = 0 runs
+ * every kernel in order on the caller's stream (used when single kernels are timed).  Default: enabled. */
+int ckc_set_overlap(ckc_ctx* ctx, int enable);
 /* Per-stage device timing (CUDA events recorded on the launching stream around each kernel stage; resolved lazily).
  * stage 0 = projection kernel (PCS / GD / RX), 1 = link frames, 2 = collision (both passes), 3 = RBS expand/push.
  * ms[s] = accumulated device milliseconds, launches[s] = number of timed stage executions since the last reset. */
