@@ -227,7 +227,8 @@ __device__ __forceinline__ void box_to_world(const box32& b, const float* F, flo
     ax[2][2] = ax[0][0] * ax[1][1] - ax[0][1] * ax[1][0];
 }
 
-__device__ __forceinline__ bool boxes_farther_than(const box32& A, const float* Fa, const box32& B, const float* Fb, float tol) {
+/* gmax6 (out): largest gap along the 6 face axes -- a cheap lower bound of the box distance used as a traversal hint only */
+__device__ __forceinline__ bool boxes_farther_than(const box32& A, const float* Fa, const box32& B, const float* Fb, float tol, float& gmax6) {
     float ca[3], cb[3], ua[3][3], ub[3][3];
     box_to_world(A, Fa, ca, ua);
     box_to_world(B, Fb, cb, ub);
@@ -243,12 +244,15 @@ __device__ __forceinline__ bool boxes_farther_than(const box32& A, const float* 
         }
     }
     bool far = false;
+    float gm = -1e30f;
 #pragma unroll
     for (int i = 0; i < 3; i++)
-        far = far || (fabsf(t[i]) - (A.h[i] + B.h[0] * AR[i][0] + B.h[1] * AR[i][1] + B.h[2] * AR[i][2]) > tol);
+        gm = fmaxf(gm, fabsf(t[i]) - (A.h[i] + B.h[0] * AR[i][0] + B.h[1] * AR[i][1] + B.h[2] * AR[i][2]));
 #pragma unroll
     for (int j = 0; j < 3; j++)
-        far = far || (fabsf(t[0] * R[0][j] + t[1] * R[1][j] + t[2] * R[2][j]) - (B.h[j] + A.h[0] * AR[0][j] + A.h[1] * AR[1][j] + A.h[2] * AR[2][j]) > tol);
+        gm = fmaxf(gm, fabsf(t[0] * R[0][j] + t[1] * R[1][j] + t[2] * R[2][j]) - (B.h[j] + A.h[0] * AR[0][j] + A.h[1] * AR[1][j] + A.h[2] * AR[2][j]));
+    gmax6 = gm;
+    far = gm > tol;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;

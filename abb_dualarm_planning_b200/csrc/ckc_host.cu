@@ -62,7 +62,9 @@ struct ckc_ctx {
     cudaStream_t stream = nullptr;
     int64_t chunk = 1 << 20;            /* samples per internal batch */
     /* persistent device storage */
-    dev_buf d_nodes, d_tris, d_ctr, d_pairtab, d_static;           /* d_small: list_count, work counters, overflow count */
+    dev_buf d_nodes, d_tris, d_ctr, d_pairtab, d_static, d_pairhits, d_pairorder;
+    dev_buf rbs_seg[2], rbs_cand, rbs_pool, rbs_eok, rbs_nck, rbs_hit, rbs_eac, rbs_eik;      /* RBS frontier storage, kept between calls */
+    int64_t collide_launches = 0;           /* d_small: list_count, work counters, overflow count */
     /* per-chunk work buffers: CKC_NUM_LANES independent sets, each with its own stream, so that the host entry points
      * can overlap the H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 */
     ckc_lane lanes[CKC_NUM_LANES];
@@ -430,6 +432,19 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
         if (!okt) { std::string msg = std::string("device upload: ") + cudaGetErrorString(cudaGetLastError()); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA; }
         ctx->world.pair_tab = ctx->d_pairtab.as<ckc_pair_dev>();
         ctx->world.static_frames_dev = ctx->d_static.as<double>();
+        /* processing-order prior: obstacles, table, arm-arm, rod, self collision; refined on line from the hit statistics */
+        std::vector<unsigned int> prior(CKC_MAX_PAIRS, 0); std::vector<int> ord(CKC_MAX_PAIRS, 0);
+        for (int p = 0; p < ctx->world.npairs; p++) prior[p] = p >= 77 ? 4000 : (p >= 64 ? 2500 : (p >= 26 && p < 50 ? 1500 : (p >= 50 ? 800 : 400)));
+        std::vector<int> idx(ctx->world.npairs);
+        for (int p = 0; p < ctx->world.npairs; p++) idx[p] = p;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return prior[a] > prior[b]; });
+        for (int p = 0; p < ctx->world.npairs; p++) ord[p] = idx[p];
+        okt = ctx->d_pairhits.reserve(CKC_MAX_PAIRS * 4) == cudaSuccess && ctx->d_pairorder.reserve(CKC_MAX_PAIRS * 4) == cudaSuccess &&
+              cudaMemcpy(ctx->d_pairhits.p, prior.data(), CKC_MAX_PAIRS * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(ctx->d_pairorder.p, ord.data(), CKC_MAX_PAIRS * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!okt) { std::string msg = std::string("device upload: ") + cudaGetErrorString(cudaGetLastError()); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA; }
+        ctx->world.pair_hits = ctx->d_pairhits.as<unsigned int>();
+        ctx->world.pair_order = ctx->d_pairorder.as<int>();
     }
     const char* ch = getenv("CKC_CHUNK");
     if (ch && atoll(ch) >= 1024) ctx->chunk = atoll(ch);
@@ -444,7 +459,8 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
 extern "C" void ckc_destroy(ckc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    dev_buf* bufs[] = { &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr };
+    dev_buf* bufs[] = { &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_pairhits, &ctx->d_pairorder, &ctx->rbs_seg[0], &ctx->rbs_seg[1],
+                        &ctx->rbs_cand, &ctx->rbs_pool, &ctx->rbs_eok, &ctx->rbs_nck, &ctx->rbs_hit, &ctx->rbs_eac, &ctx->rbs_eik };
     for (dev_buf* b : bufs) b->release();
     for (int l = 0; l < CKC_NUM_LANES; l++) { ctx->lanes[l].release(); if (ctx->lanes[l].ev_done) cudaEventDestroy(ctx->lanes[l].ev_done); if (ctx->lanes[l].ev_p) cudaEventDestroy(ctx->lanes[l].ev_p); if (ctx->lanes[l].ev_c) cudaEventDestroy(ctx->lanes[l].ev_c);
         if (ctx->lanes[l].st_hi) cudaStreamDestroy(ctx->lanes[l].st_hi); if (ctx->lanes[l].st) cudaStreamDestroy(ctx->lanes[l].st); }
@@ -507,6 +523,8 @@ static int run_collision_stage(ckc_ctx* ctx, ckc_lane& L, int64_t m_max, const d
     { stage_scope ts(ctx, st, 1);
       ckc_launch_link_frames(ctx->world, d_q, l, d_list, d_m, m_max, L.frames.as<double>(), st); }
     ckc_launch_cfg cfg = { ctx->num_sms };
+    /* refresh the processing order from the hit statistics now and then (a 1-block kernel on the same stream) */
+    if ((ctx->collide_launches++ & 7) == 7) { ckc_launch_update_pair_order(ctx->world, ctx->d_pairorder.as<int>(), st); ctx->launches++; }
     { stage_scope ts(ctx, st, 2);
       ckc_launch_collide(ctx->world, cfg, L.frames.as<double>(), d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, L.work_counter(),
                          L.ovf.as<int32_t>(), L.ovf_count(), L.bigstack.as<uint32_t>(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
@@ -828,8 +846,8 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
     ckc_lane& L = ctx->lanes[0];
     cudaStream_t st = L.st;
     const int ne = (int)n_edges;
-    dev_buf seg[2], cand, pool, eok, nck, hit, eac, eik;
-    struct cleanup { dev_buf* b[9]; ~cleanup() { for (dev_buf* x : b) x->release(); } } guard = { { &seg[0], &seg[1], &cand, &pool, &eok, &nck, &hit, &eac, &eik } };
+    dev_buf (&seg)[2] = ctx->rbs_seg;
+    dev_buf &cand = ctx->rbs_cand, &pool = ctx->rbs_pool, &eok = ctx->rbs_eok, &nck = ctx->rbs_nck, &hit = ctx->rbs_hit, &eac = ctx->rbs_eac, &eik = ctx->rbs_eik;
     int64_t seg_cap = std::max<int64_t>(2 * (int64_t)ne, 1024);
     CU(seg[0].reserve((size_t)seg_cap * 16)); CU(seg[1].reserve((size_t)seg_cap * 16)); CU(cand.reserve((size_t)seg_cap * 8));
     CU(pool.reserve((size_t)(2 * (int64_t)ne + seg_cap) * 96));
@@ -863,25 +881,34 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
         /* capacity for this level: <= nseg new nodes / candidates, <= 2 nseg next segments */
         if ((int64_t)(seg[1 - cur].cap / 16) < 2 * nseg) { seg[1 - cur].release(); CU(seg[1 - cur].reserve((size_t)(2 * nseg + 1024) * 16)); }
         if ((int64_t)(cand.cap / 8) < nseg) { cand.release(); CU(cand.reserve((size_t)(nseg + 1024) * 8)); }
-        CU(reserve_keep(pool, (size_t)(nnodes + nseg) * 96, (size_t)nnodes * 96, st));
-        CU(hit.reserve((size_t)(nnodes + nseg)));
+        /* grow geometrically: a cudaMalloc / cudaFree pair per level would dominate the deep, thin tail of the frontier */
+        if ((size_t)(nnodes + nseg) * 96 > pool.cap) CU(reserve_keep(pool, (size_t)((nnodes + nseg) * 3 / 2 + 4096) * 96, (size_t)nnodes * 96, st));
+        if ((size_t)(nnodes + nseg) > hit.cap) CU(hit.reserve((size_t)((nnodes + nseg) * 3 / 2 + 4096)));
         ckc_rbs_dev r = make(cur);
         CU(cudaMemsetAsync(d_cnt, 0, 8, st));
         { stage_scope ts(ctx, st, 3);
           ckc_launch_rbs_expand(ctx->kin, r, flavour, (int)nseg, (int)nnodes, st); }
         ctx->launches++;
         CU(cudaGetLastError());
-        /* collision on the surviving midpoints (work list = candidate node ids), in bounded sub-batches */
+        /* collision on the surviving midpoints (work list = candidate node ids).  Small levels keep the count on the device
+         * (one host synchronisation per level); large levels read it back and run bounded sub-batches */
         int32_t h[2];
-        CU(cudaMemcpyAsync(h, d_cnt, 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        const int64_t sub = 1 << 21;
-        for (int64_t off = 0; off < h[0]; off += sub) {
-            int rc = run_collision_stage(ctx, L, std::min<int64_t>(sub, h[0] - off), pool.as<double>(), AOS, r.cand_node + off, nullptr, hit.as<uint8_t>(), nullptr, nullptr, st);
+        if (nseg <= (1 << 20)) {
+            int rc = run_collision_stage(ctx, L, nseg, pool.as<double>(), AOS, r.cand_node, d_cnt, hit.as<uint8_t>(), nullptr, nullptr, st);
             if (rc) return rc;
+            { stage_scope ts(ctx, st, 3);
+              ckc_launch_rbs_push(r, (int)nseg, d_cnt, hit.as<uint8_t>(), st); }
+        } else {
+            CU(cudaMemcpyAsync(h, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            const int64_t sub = 1 << 20;
+            for (int64_t off = 0; off < h[0]; off += sub) {
+                int rc = run_collision_stage(ctx, L, std::min<int64_t>(sub, h[0] - off), pool.as<double>(), AOS, r.cand_node + off, nullptr, hit.as<uint8_t>(), nullptr, nullptr, st);
+                if (rc) return rc;
+            }
+            { stage_scope ts(ctx, st, 3);
+              ckc_launch_rbs_push(r, h[0], d_cnt, hit.as<uint8_t>(), st); }
         }
-        { stage_scope ts(ctx, st, 3);
-          ckc_launch_rbs_push(r, h[0], d_cnt, hit.as<uint8_t>(), st); }
         ctx->launches++;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(h, d_cnt, 8, cudaMemcpyDeviceToHost, st));

@@ -37,6 +37,8 @@ struct ckc_world_dev {
     const ckc_node* nodes;              /* all meshes, concatenated */
     const ckc_pair_dev* pair_tab;       /* [npairs] in global memory: indexed per lane (a kernel-parameter array would be copied to local memory) */
     const double* static_frames_dev;    /* [3][12] obstacle poses in global memory (same values as static_frames) */
+    unsigned int* pair_hits;            /* [CKC_MAX_PAIRS] how often each table entry produced the first hit (decayed): adaptive processing order */
+    const int* pair_order;              /* [CKC_MAX_PAIRS] table entries sorted by decreasing pair_hits; any order yields the same boolean */
     const double*   tris;               /* all meshes, concatenated, 9 doubles per triangle (FP64, as parsed) */
     int node_off[CKC_NUM_MESHES];       /* first node of each mesh */
     int tri_off[CKC_NUM_MESHES];        /* first triangle of each mesh */
@@ -103,6 +105,7 @@ void ckc_launch_link_frames(const ckc_world_dev& w, const double* q, ckc_layout 
 void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const double* frames, const int32_t* list, const int32_t* d_m,
                         int64_t m_max, uint8_t* hit_out, uint8_t* valid_out, uint8_t* pair_flags, int32_t* work_counter,
                         int32_t* ovf_list, int32_t* ovf_count, uint32_t* big_stack, ckc_counters_dev* ctr, cudaStream_t st);
+void ckc_launch_update_pair_order(const ckc_world_dev& w, int* order_out, cudaStream_t st);
 void ckc_launch_limits(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, uint8_t* ok, cudaStream_t st);
 void ckc_launch_identify_ik(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, int8_t* ik01, cudaStream_t st);
 void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const double* q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded,

@@ -149,6 +149,11 @@ struct collide_args {
 __device__ __forceinline__ const double* frame64(const ckc_world_dev& w, const double* cfg_frames, int f) {
     return f < CKC_NUM_DYN_FRAMES ? cfg_frames + 12 * f : w.static_frames_dev + 12 * (f - CKC_NUM_DYN_FRAMES);
 }
+__device__ __forceinline__ ckc_pair_dev smem_pair(const int4* sp, int p) {
+    const int4 a = sp[2 * p], b = sp[2 * p + 1];
+    ckc_pair_dev r; r.node_a = a.x; r.node_b = a.y; r.tri_a = a.z; r.tri_b = a.w; r.frame_a = b.x; r.frame_b = b.y; r.pad0 = 0; r.pad1 = 0;
+    return r;
+}
 __device__ __forceinline__ ckc_pair_dev load_pair(const ckc_world_dev& w, int p) {
     const int4* q = reinterpret_cast<const int4*>(w.pair_tab + p);
     const int4 a = __ldg(q), b = __ldg(q + 1);
@@ -190,6 +195,9 @@ k_collide(const ckc_world_dev w, const collide_args a) {
     __shared__ float s_frames[CKC_COLLIDE_WARPS][CKC_NUM_FRAMES * 12];
     __shared__ uint32_t s_stack[kBigStack ? 1 : CKC_COLLIDE_WARPS][kBigStack ? 1 : CKC_STACK_CAP];
     __shared__ uint32_t s_triq[CKC_COLLIDE_WARPS][CKC_TRIQ_CAP];
+    __shared__ int4 s_pairs[CKC_MAX_PAIRS * 2];       /* the pair table, once per block (32 bytes per entry) */
+    for (int e = threadIdx.x; e < w.npairs * 2; e += blockDim.x) s_pairs[e] = __ldg(reinterpret_cast<const int4*>(w.pair_tab) + e);
+    __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -218,16 +226,19 @@ k_collide(const ckc_world_dev w, const collide_args a) {
         for (int e = lane; e < CKC_NUM_FRAMES * 12; e += 32)
             F[e] = e < CKC_FRAME_DOUBLES ? (float)cfg_frames[e] : (float)w.static_frames_dev[e - CKC_FRAME_DOUBLES];
         /* seed the stack with the root task of every table entry, first entry on top */
+        /* processing order = table entries by decreasing (decayed) first-hit frequency: a colliding configuration usually
+         * reaches its hit inside the first 32 root tasks and leaves through the ballot early-out */
         int top = w.npairs;
-        for (int p = lane; p < w.npairs; p += 32) stack[w.npairs - 1 - p] = (uint32_t)p << 22;
+        for (int k2 = lane; k2 < w.npairs; k2 += 32) stack[w.npairs - 1 - k2] = (uint32_t)__ldg(w.pair_order + k2) << 22;
         int ntri = 0;
-        bool hit = false, overflow = false;
+        bool hit = false, overflow = false, hot = false;      /* hot: a queued triangle pair looks like a hit -> test it now */
         /* env 2: "path not from above" rule, collisionDetection.cpp:427-428 */
         if (w.env == 2 && (cfg_frames[7 * 12 + 11] > 800.0 || cfg_frames[15 * 12 + 11] > 800.0)) { hit = true; top = 0; }
         __syncwarp();
 
         while (!hit) {
-            if (ntri >= 32 || (top == 0 && ntri > 0)) {
+            if (ntri >= 32 || (ntri > 0 && (top == 0 || hot))) {
+                hot = false;
                 /* ---- exact triangle tests, up to 32 at a time ---- */
                 const int cnt = ntri < 32 ? ntri : 32;
                 bool h = false;
@@ -235,14 +246,20 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                 if (lane < cnt) {
                     t = triq[ntri - 1 - lane];
                     const int p = t >> 20;
-                    const double d = leaf_distance(w, cfg_frames, load_pair(w, p), (t >> 10) & 1023, t & 1023);
+                    const double d = leaf_distance(w, cfg_frames, smem_pair(s_pairs, p), (t >> 10) & 1023, t & 1023);
                     h = d <= w.tol;                                   /* PQP: closer_than_tolerance iff d <= tolerance */
                 }
                 n_tri += cnt;
                 ntri -= cnt;
                 if (per_pair) {
                     if (h) a.pair_flags[sample * CKC_MAX_PAIRS + (t >> 20)] = 1;
-                } else if (__any_sync(0xffffffffu, h)) hit = true;
+                } else {
+                    const unsigned hm = __ballot_sync(0xffffffffu, h);
+                    if (hm) {
+                        hit = true;
+                        if (lane == __ffs(hm) - 1) atomicAdd(w.pair_hits + (t >> 20), 1u);
+                    }
+                }
                 __syncwarp();
                 continue;
             }
@@ -250,20 +267,24 @@ k_collide(const ckc_world_dev w, const collide_args a) {
             /* ---- box tests, one task per lane ---- */
             const int cnt = top < 32 ? top : 32;
             const bool active = lane < cnt;
-            bool expand = false, leafpair = false;
+            bool expand = false, leafpair = false, likely = false;
             uint32_t c0 = 0, c1 = 0, tt = 0;
             if (active) {
                 const uint32_t t = stack[top - 1 - lane];
                 const int p = t >> 22, na = (t >> 11) & 2047, nb = t & 2047;
-                const ckc_pair_dev pr = load_pair(w, p);
+                const ckc_pair_dev pr = smem_pair(s_pairs, p);
                 bool skip = false;
                 if (per_pair) skip = a.pair_flags[sample * CKC_MAX_PAIRS + p] != 0;      /* pair already decided */
                 if (!skip) {
                     const box32 A = load_box(w.nodes + pr.node_a + na);
                     const box32 B = load_box(w.nodes + pr.node_b + nb);
-                    const bool far = boxes_farther_than(A, F + 12 * pr.frame_a, B, F + 12 * pr.frame_b, w.cull_tol);
+                    float gap6;
+                    const bool far = boxes_farther_than(A, F + 12 * pr.frame_a, B, F + 12 * pr.frame_b, w.cull_tol, gap6);
                     if (!far) {
-                        if (A.child < 0 && B.child < 0) { leafpair = true; tt = ((uint32_t)p << 20) | ((uint32_t)(~A.child) << 10) | (uint32_t)(~B.child); }
+                        if (A.child < 0 && B.child < 0) {
+                            leafpair = true; tt = ((uint32_t)p << 20) | ((uint32_t)(~A.child) << 10) | (uint32_t)(~B.child);
+                            likely = gap6 < 0.25f * w.cull_tol;       /* the two triangles' boxes are within ~2 mm along every face axis */
+                        }
                         else {
                             expand = true;
                             if (B.child < 0 || (A.child >= 0 && A.size2 > B.size2)) {       /* descend the larger box */
@@ -280,6 +301,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
             n_bv += cnt;
             top -= cnt;
             __syncwarp();
+            if (!per_pair && __any_sync(0xffffffffu, likely)) hot = true;
             const unsigned mt = __ballot_sync(0xffffffffu, leafpair);
             const unsigned me = __ballot_sync(0xffffffffu, expand);
             if (leafpair) triq[ntri + __popc(mt & lt_mask)] = tt;
@@ -321,6 +343,23 @@ k_collide(const ckc_world_dev w, const collide_args a) {
         atomicAdd(&a.ctr->collisions, n_hit);
         if (kBigStack) atomicAdd(&a.ctr->queue_overflows, n_cfg);
     }
+}
+
+/* rank sort of the (decayed) first-hit counters -> processing order for the next launches; one tiny block */
+__global__ void k_update_pair_order(unsigned int* hits, int* order, int npairs) {
+    __shared__ unsigned int h[CKC_MAX_PAIRS];
+    const int i = threadIdx.x;
+    if (i < npairs) h[i] = hits[i];
+    __syncthreads();
+    if (i < npairs) {
+        int rank = 0;
+        for (int j = 0; j < npairs; j++) rank += (h[j] > h[i]) || (h[j] == h[i] && j < i);
+        order[rank] = i;
+        hits[i] = h[i] - (h[i] >> 6);          /* slow exponential decay keeps the statistics adaptive */
+    }
+}
+void ckc_launch_update_pair_order(const ckc_world_dev& w, int* order_out, cudaStream_t st) {
+    k_update_pair_order<<<1, 128, 0, st>>>(w.pair_hits, order_out, w.npairs);
 }
 
 void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const double* frames, const int32_t* list, const int32_t* d_m,

@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="gd", choices=["gd", "pcs", "rbs"])
-    ap.add_argument("--samples", type=int, default=0, help="units per GPU per step (default: 1e6 samples; 2e4 edges for rbs)")
+    ap.add_argument("--samples", type=int, default=0, help="units per GPU per step (default: 1e6 samples; 1e5 edges for rbs = BASELINE configs[2])")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary PCS / RBS measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     return ap.parse_args()
@@ -146,7 +146,7 @@ def run_native(args):
     ck = Checker(env=1, device=local_rank)
     stream = torch.cuda.current_stream().cuda_stream
     wl = args.workload
-    n = args.samples or (20000 if wl == "rbs" else 1_000_000)
+    n = args.samples or (100000 if wl == "rbs" else 1_000_000)
     K, W = args.steps, max(args.warmup, 0)
 
     def barrier():
@@ -289,7 +289,7 @@ def run_native(args):
         # ---- RBS: n edges per step per rank ----
         qa, qb, iks = make_rbs_edges(ck, sampling, n, 7000 + rank)
         for w in range(max(W, 1)):
-            ck.pcs_check_motion_rbs(qa[: max(n // 8, 1)], qb[: max(n // 8, 1)], 0, iks[: max(n // 8, 1)])
+            ck.pcs_check_motion_rbs(qa, qb, 0, iks)
         barrier()
         ck.reset_stats(); ck.set_stage_timing(True)
         sampler = ClockSampler(local_rank); sampler.start()
@@ -365,9 +365,9 @@ def extra_measurements(ck, sampling, torch, dev, stream):
     e1.record(); torch.cuda.synchronize()
     ex["pcs_seeded_configs_per_s"] = reps * n / (e0.elapsed_time(e1) * 1e-3)
     ex["pcs_seeded_note"] = "S-PCS samples generated on the device from the counter-based generator (no input traffic), %d samples x %d" % (n, reps)
-    ne = 20000
+    ne = 100000
     qa, qb, iks = make_rbs_edges(ck, sampling, ne, 4242)
-    ck.pcs_check_motion_rbs(qa[:2000], qb[:2000], 0, iks[:2000])
+    ck.pcs_check_motion_rbs(qa, qb, 0, iks)                 # warm-up at full size (frontier buffers grow once)
     t0 = time.perf_counter()
     ok, nc = ck.pcs_check_motion_rbs(qa, qb, 0, iks)
     t = time.perf_counter() - t0
@@ -444,7 +444,7 @@ def run_reference(args):
         return
     wl = args.workload
     cores = os.cpu_count() or 1
-    n = args.samples or (20000 if wl == "rbs" else 1_000_000)
+    n = args.samples or (100000 if wl == "rbs" else 1_000_000)
     K, W = args.steps, args.warmup
     budget = max(2.0, min(12.0, 150.0 / max(K + W, 1)))          # whole run stays within a few minutes
     for _ in range(min(W, 1)):

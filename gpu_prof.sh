@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 1 --no-extra --no-cpu"
-$CMD > gpurun_out/plain_gd2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_gd_project -s 1 -c 1 -o gpurun_out/r1_prof_gd_project_v3 $CMD > gpurun_out/ncu_gd2.log 2>&1
-echo "gd full rc=$?"
+CMD2="python bench.py --workload pcs --steps 2 --warmup 1 --no-extra --no-cpu"
+$CMD2 > gpurun_out/plain_pcs.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_collide -s 6 -c 1 -o gpurun_out/r1_prof_collide_v2 $CMD2 > gpurun_out/ncu_pcs.log 2>&1
+echo "collide full rc=$?"
