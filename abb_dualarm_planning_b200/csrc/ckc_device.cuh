@@ -679,6 +679,23 @@ __device__ __forceinline__ void gd_finish(const gd_ref& s, double* q) {
     q[6] = -q[6];
 }
 
+/* the same post-processing on a register copy of the raw chain-order joints */
+__device__ __forceinline__ void gd_finish_regs(const double* raw, double* q) {
+    double qc[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        double v = raw[i];
+        v = (fabs(v) < 1e-4) ? 0.0 : v;
+        v = fmod_exact(v, 2 * CKC_PI_);
+        if (v > CKC_PI_) v -= 2 * CKC_PI_;
+        if (v < -CKC_PI_) v += 2 * CKC_PI_;
+        qc[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { q[i] = qc[i]; q[6 + i] = qc[11 - i]; }
+    q[6] = -q[6];
+}
+
 /* kdl::GD as a plain per-thread loop (used by the RBS frontier).  q: user order in/out.  returns converged */
 __device__ __forceinline__ bool gd_project(const ckc_kin_dev& k, const gd_ref& s, double* q, int max_iter, int* iters) {
     gd_init(s, q);

@@ -44,13 +44,13 @@ struct ckc_lane {
     cudaStream_t st = nullptr;
     cudaStream_t st_hi = nullptr;       /* high-priority stream for the collision stage of this lane's chunk */
     cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_c = nullptr;
-    dev_buf qin, qout, ac, ik, ok, valid, list, frames, ovf, bigstack, flags, aux, aux2, small;
+    dev_buf qin, qout, ac, ik, ok, valid, list, frames, ovf, bigstack, flags, aux, aux2, small, gdstate;
     int32_t* list_count() const { return small.as<int32_t>(); }
     int32_t* work_counter() const { return small.as<int32_t>() + 2; }      /* 2 ints */
     int32_t* ovf_count() const { return small.as<int32_t>() + 4; }
     int32_t* rbs_counts() const { return small.as<int32_t>() + 8; }        /* 2 ints */
     unsigned long long* gd_counter() const { return (unsigned long long*)(small.as<int32_t>() + 12); }
-    void release() { dev_buf* b[] = { &qin, &qout, &ac, &ik, &ok, &valid, &list, &frames, &ovf, &bigstack, &flags, &aux, &aux2, &small }; for (dev_buf* x : b) x->release(); }
+    void release() { dev_buf* b[] = { &qin, &qout, &ac, &ik, &ok, &valid, &list, &frames, &ovf, &bigstack, &flags, &aux, &aux2, &small, &gdstate }; for (dev_buf* x : b) x->release(); }
 };
 
 struct ckc_ctx {
@@ -552,11 +552,12 @@ static int run_pcs_chunk(ckc_ctx* ctx, ckc_lane& L, int64_t n, const double* d_q
 static int run_gd_chunk(ckc_ctx* ctx, ckc_lane& L, int64_t n, const double* d_q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded, double* d_qout,
                         ckc_layout lo, uint8_t* d_ok, uint8_t* d_conv, int32_t* d_iters, uint8_t* d_valid, bool collide, cudaStream_t st) {
     CU(L.list.reserve((size_t)n * 4));
+    CU(L.gdstate.reserve((size_t)n * 4));
     CU(cudaMemsetAsync(L.list_count(), 0, 4, st));
     { stage_scope ts(ctx, st, 0);
       ckc_launch_gd_project(ctx->kin, ctx->num_sms, n, d_q, li, seed, i0, seeded, d_qout, lo, d_ok, d_conv, d_iters, d_valid,
-                            collide ? L.list.as<int32_t>() : nullptr, L.list_count(), L.gd_counter(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
-    ctx->launches += 1;
+                            collide ? L.list.as<int32_t>() : nullptr, L.list_count(), L.gdstate.as<int32_t>(), L.gd_counter(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
+    ctx->launches += 2;
     ctx->host_stats.ik_calls += n;
     CU(cudaGetLastError());
     if (collide) return run_collision_stage(ctx, L, n, d_qout, lo, L.list.as<int32_t>(), L.list_count(), nullptr, d_valid, nullptr, st);

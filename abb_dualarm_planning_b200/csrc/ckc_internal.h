@@ -110,7 +110,7 @@ void ckc_launch_limits(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_l
 void ckc_launch_identify_ik(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, int8_t* ik01, cudaStream_t st);
 void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const double* q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded,
                            double* q_out, ckc_layout lo, uint8_t* ok, uint8_t* converged, int32_t* iters, uint8_t* valid,
-                           int32_t* list, int32_t* list_count, unsigned long long* work_counter, ckc_counters_dev* ctr, cudaStream_t st);
+                           int32_t* list, int32_t* list_count, int32_t* state_scratch, unsigned long long* work_counter, ckc_counters_dev* ctr, cudaStream_t st);
 void ckc_launch_rx_check(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, double eps, uint8_t* ok, double* resid,
                          uint8_t* valid, int32_t* list, int32_t* list_count, cudaStream_t st);
 void ckc_launch_fma_peak(int precision, int num_sms, int iters, float* sink, cudaStream_t st);

@@ -479,16 +479,13 @@ void ckc_launch_transpose(const double* src, ckc_layout ls, double* dst, ckc_lay
  * (median 9, max > 25) does not idle the other 31 lanes of its warp. */
 __global__ void __launch_bounds__(CKC_GD_BLOCK, 4)
 k_gd_project(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, ckc_layout li, uint64_t key, uint64_t i0, int seeded,
-             double* __restrict__ q_out, ckc_layout lo, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ conv_out,
-             int32_t* __restrict__ iters_out, uint8_t* __restrict__ valid_out, int32_t* __restrict__ list, int32_t* list_count,
-             unsigned long long* work_counter, ckc_counters_dev* ctr) {
+             double* __restrict__ q_raw, ckc_layout lo, int32_t* __restrict__ state_out, unsigned long long* work_counter) {
     __shared__ double sh_state[36 * CKC_GD_BLOCK];
     const int lane = threadIdx.x & 31;
     const gd_ref s = { sh_state + threadIdx.x };
     int64_t i = -1;
     int it = 0;
     bool active = false, exhausted = false;
-    unsigned long long iters_sum = 0, n_ok = 0;
     for (;;) {
         /* ---- refill idle lanes ---- */
         const unsigned need = __ballot_sync(0xffffffffu, !active && !exhausted);
@@ -515,46 +512,64 @@ k_gd_project(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, 
         }
         if (!__any_sync(0xffffffffu, active)) break;
         /* ---- one Newton iteration on every busy lane ---- */
-        bool done = false, conv = false;
         if (active) {
-            conv = gd_iterate(kin, s);
+            const bool conv = gd_iterate(kin, s);
             it++;
-            done = conv || it >= 10000;                                /* ChainIkSolverPos_NR(..., 10000, 1e-5) */
-        }
-        /* ---- retire finished lanes ---- */
-        if (__any_sync(0xffffffffu, done)) {
-            bool ok = false;
-            if (done) {
-                double q[12];
-                if (conv) { gd_finish(s, q); ok = within_limits(kin, q); }     /* kdl_class.cpp:110-130 */
-                else {
+            if (conv || it >= 10000) {                                 /* ChainIkSolverPos_NR(..., 10000, 1e-5) */
+                /* retire: the raw chain-order joints + (iterations | converged << 31); k_gd_finish post-processes densely */
 #pragma unroll
-                    for (int j = 0; j < 12; j++) q[j] = seeded ? 0.0 : q_in[i * li.stride_i + j * li.stride_j];
-                }
-                if (q_out) {
-#pragma unroll
-                    for (int j = 0; j < 12; j++) q_out[i * lo.stride_i + j * lo.stride_j] = q[j];
-                }
-                if (ok_out) ok_out[i] = ok ? 1 : 0;
-                if (conv_out) conv_out[i] = conv ? 1 : 0;
-                if (iters_out) iters_out[i] = it;
-                if (valid_out) valid_out[i] = 0;
-                iters_sum += (unsigned long long)it; n_ok += ok ? 1 : 0;
+                for (int j = 0; j < 12; j++) q_raw[i * lo.stride_i + j * lo.stride_j] = s.qc(j);
+                state_out[i] = it | (conv ? (int)0x80000000 : 0);
                 active = false;
             }
-            append_to_list(ok, (int32_t)i, list, list_count);
         }
     }
-    if (ctr) {
+}
+
+/* dense post-pass of kdl::GD (kdl_class.cpp:110-130): zero snap, fmod / wrap, user joint order, joint limits, outputs and
+ * the warp-aggregated append of the surviving samples to the collision work list (one thread per sample, coalesced) */
+__global__ void __launch_bounds__(256)
+k_gd_finish(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, ckc_layout li, int seeded, double* __restrict__ q_io, ckc_layout lo,
+            const int32_t* __restrict__ state, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ conv_out, int32_t* __restrict__ iters_out,
+            uint8_t* __restrict__ valid_out, int32_t* __restrict__ list, int32_t* list_count, ckc_counters_dev* ctr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    int it = 0;
+    if (i < n) {
+        const int st = state[i];
+        const bool conv = st < 0;
+        it = st & 0x7fffffff;
+        double q[12];
+        if (conv) {
+            double qc[12];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { iters_sum += __shfl_xor_sync(0xffffffffu, iters_sum, o); n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o); }
-        if (lane == 0) { atomicAdd(&ctr->gd_iterations, iters_sum); if (n_ok) atomicAdd(&ctr->ik_feasible, n_ok); }
+            for (int j = 0; j < 12; j++) qc[j] = q_io[i * lo.stride_i + j * lo.stride_j];
+            gd_finish_regs(qc, q);
+            ok = within_limits(kin, q);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; j++) q[j] = seeded ? 0.0 : q_in[i * li.stride_i + j * li.stride_j];
+        }
+#pragma unroll
+        for (int j = 0; j < 12; j++) q_io[i * lo.stride_i + j * lo.stride_j] = q[j];
+        if (ok_out) ok_out[i] = ok ? 1 : 0;
+        if (conv_out) conv_out[i] = conv ? 1 : 0;
+        if (iters_out) iters_out[i] = it;
+        if (valid_out) valid_out[i] = 0;
+    }
+    append_to_list(ok, (int32_t)i, list, list_count);
+    if (ctr) {
+        unsigned long long sum = (unsigned long long)it;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0) { if (sum) atomicAdd(&ctr->gd_iterations, sum); if (m) atomicAdd(&ctr->ik_feasible, (unsigned long long)__popc(m)); }
     }
 }
 
 void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const double* q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded,
                            double* q_out, ckc_layout lo, uint8_t* ok, uint8_t* converged, int32_t* iters, uint8_t* valid,
-                           int32_t* list, int32_t* list_count, unsigned long long* work_counter, ckc_counters_dev* ctr, cudaStream_t st) {
+                           int32_t* list, int32_t* list_count, int32_t* state_scratch, unsigned long long* work_counter, ckc_counters_dev* ctr, cudaStream_t st) {
     if (n <= 0) return;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
@@ -565,8 +580,8 @@ void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const
     const int64_t needed = (n + 6 * CKC_GD_BLOCK - 1) / (6 * CKC_GD_BLOCK);
     if (blocks > needed) blocks = needed;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
-    k_gd_project<<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, seeded, q_out, lo, ok, converged, iters, valid,
-                                                  list, list_count, work_counter, ctr);
+    k_gd_project<<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, seeded, q_out, lo, state_scratch, work_counter);
+    k_gd_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kin, n, q, li, seeded, q_out, lo, state_scratch, ok, converged, iters, valid, list, list_count, ctr);
 }
 
 /* RX: relaxed-constraint residual + joint limits; survivors go to the collision work list */

@@ -407,14 +407,63 @@ def _ref_worker(args):
     return secs, int(valid.sum())
 
 
+def _cpu_rbs_edges(orc, seed, n_edges):
+    """S-RBS edges built with the CPU oracle (untimed): valid endpoint A, B = A + s (U - A) projected on A's branch and valid"""
+    import numpy as np
+    from abb_dualarm_planning_b200 import sampling
+    lo = np.append(np.array([-165, -110, -110, -160, -120]) * 3.1416 / 180, -3.1416)
+    hi = np.append(np.array([165, 110, 70, 160, 120]) * 3.1416 / 180, 3.1416)
+    qa, qb, iks, i0, have = [], [], [], 0, 0
+    while have < n_edges:
+        m = 200000
+        q, ik = sampling.sample_pcs(seed, i0, m)
+        ok, valid, qo = orc.pcs_validate(q, 0, ik)
+        idx = np.nonzero(valid)[0]
+        a = qo[idx]
+        u = np.stack([sampling.uniform(seed + 1000, i0, m, k)[idx] for k in range(6)], axis=1)
+        s = 0.01 + 0.99 * sampling.uniform(seed + 1000, i0, m, 6)[idx]
+        b = a.copy(); b[:, :6] = a[:, :6] + s[:, None] * ((lo + u * (hi - lo)) - a[:, :6])
+        okb, vb, qbo = orc.pcs_validate(b, 0, ik[idx])
+        keep = vb == 1
+        qa.append(a[keep]); qb.append(qbo[keep]); iks.append(ik[idx][keep]); have += int(keep.sum()); i0 += m
+    return np.concatenate(qa)[:n_edges], np.concatenate(qb)[:n_edges], np.concatenate(iks)[:n_edges]
+
+
+def _rbs_worker(args):
+    """one process: checkMotionRBS on its own S-RBS edges -- the reference's compiled code when oracle/_ref exists, else the port"""
+    seed, n_edges, use_ref = args
+    from oracle import lib as olib, refshim
+    orc = olib.Oracle(1)
+    qa, qb, iks = _cpu_rbs_edges(orc, seed, n_edges)
+    if use_ref:
+        ok, nodes, secs = refshim.rbs(qa, qb, 0, iks, count_nodes=False)
+        return secs, int(ok.sum())
+    t0 = time.perf_counter()
+    ok, nc = orc.pcs_check_motion_rbs(qa, qb, 0, iks)
+    return time.perf_counter() - t0, int(ok.sum())
+
+
 def cpu_baseline(wl, cores, budget_s):
     """bounded sample of the same workload on `cores` host processes"""
     import multiprocessing as mp
     from oracle import refshim
     if wl == "rbs":
-        wl_eff = "pcs"
-    else:
-        wl_eff = wl
+        use_ref = refshim.available()
+        m = max(int(budget_s / (3.0e-3 if use_ref else 0.4e-3)), 50)
+        jobs = [(7000 + c, m, use_ref) for c in range(cores)]
+        t0 = time.perf_counter()
+        if cores == 1:
+            res = [_rbs_worker(jobs[0])]
+        else:
+            with mp.get_context("fork").Pool(cores) as pool:
+                res = pool.map(_rbs_worker, jobs)
+        wall = time.perf_counter() - t0
+        busy = max(r[0] for r in res)
+        return {"value": cores * m / busy, "unit": "edges/s", "cores": cores, "kind": "reference" if use_ref else "port",
+                "sample": "%d S-RBS edges per core, checkMotionRBS compute time of the slowest core %.2f s (edge construction untimed, wall %.2f s); %s" % (
+                    m, busy, wall, "the reference's own compiled code (tests/trbspcs via oracle/_ref)" if use_ref else "oracle/ C++ restatement"),
+                "n_ok": sum(r[1] for r in res)}
+    wl_eff = wl
     use_ref = wl_eff == "pcs" and refshim.available()
     # per-unit CPU cost (measured on this image): GD port ~90 us, PCS port ~3 us, PCS reference binary ~36 us
     per_unit = {"gd": 95e-6, "pcs": 36e-6 if use_ref else 3.5e-6}[wl_eff]
@@ -458,13 +507,14 @@ def run_reference(args):
     wall = time.perf_counter() - t0
     value = sum(vals) / len(vals)
     base["value"] = value
-    line = {"impl": "reference", "metric": "validated closed-chain configs/s (project + FK/limits + collide)", "value": value, "unit": "configs/s",
+    unit = "edges/s" if wl == "rbs" else "configs/s"
+    line = {"impl": "reference", "metric": "RBS edges/s (checkMotionRBS, PCS)" if wl == "rbs" else "validated closed-chain configs/s (project + FK/limits + collide)", "value": value, "unit": unit,
             "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "same generator and workload as the native arm (%s), each step a bounded sample sized for ~%.0f s on %d host cores" % (wl, budget, cores),
                        "units_per_gpu_per_step": n},
             "cpu_baseline": base,
-            "e2e": {"value": value, "unit": "configs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
