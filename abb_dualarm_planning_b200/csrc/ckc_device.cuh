@@ -368,6 +368,104 @@ __device__ __noinline__ double tri_dist(const v3* S, const v3* T) {
     return shown_disjoint ? sqrt(mindd) : 0.0;
 }
 
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* Warp-cooperative TriDist: NINE lanes per triangle pair (one per edge pair (i, j), i = e / 3, j = e % 3), three pairs per    */
+/* warp step, everything in registers.  The sequential PQP loop visits the edge pairs in order k = 0..8 and                 */
+/*   - "updates" at k when dd_k <= min(init, dd_0..dd_{k-1})   (init = |S0 - T0|^2 + 1)                                    */
+/*   - returns sqrt(dd_k) at the FIRST updating k with a_k <= 0 and b_k >= 0                                                */
+/*   - otherwise ORs (p_k - max(a_k,0) + min(b_k,0) > 0) over the updating k into shown_disjoint and keeps the prefix min. */
+/* Each dd_k, a_k, b_k, p_k is produced by exactly the arithmetic of the scalar routine, so prefix-min + ballots reproduce    */
+/* its result bit for bit; the vertex-face cases and the final "shown_disjoint ? sqrt(mindd) : 0" run on lane e = 0.         */
+/* ALL 32 lanes must call this (shuffles inside); lanes with act == false carry dummy data.                                  */
+/* ---------------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void seg_points_inl(v3& VEC, v3& X, v3& Y, const v3& P, const v3& A, const v3& Q, const v3& B) {
+    v3 T = Q - P;
+    const double AA = dot(A, A), BB = dot(B, B), AB = dot(A, B), AT = dot(A, T), BT = dot(B, T);
+    const double denom = AA * BB - AB * AB;
+    double t = (AT * BB - BT * AB) / denom;
+    if ((t < 0) || isnan(t)) t = 0; else if (t > 1) t = 1;
+    const double u = (t * AB - BT) / BB;
+    if ((u <= 0) || isnan(u)) {
+        Y = Q;
+        t = AT / AA;
+        if ((t <= 0) || isnan(t)) { X = P; VEC = Q - P; }
+        else if (t >= 1) { X = P + A; VEC = Q - X; }
+        else { X = madd(P, A, t); VEC = cross(A, cross(T, A)); }
+    } else if (u >= 1) {
+        Y = Q + B;
+        t = (AB + AT) / AA;
+        if ((t <= 0) || isnan(t)) { X = P; VEC = Y - P; }
+        else if (t >= 1) { X = P + A; VEC = Y - X; }
+        else { X = madd(P, A, t); T = Y - P; VEC = cross(A, cross(T, A)); }
+    } else {
+        Y = madd(Q, B, u);
+        if ((t <= 0) || isnan(t)) { X = P; VEC = cross(B, cross(T, B)); }
+        else if (t >= 1) { X = P + A; T = Q - X; VEC = cross(B, cross(T, B)); }
+        else {
+            X = madd(P, A, t);
+            VEC = cross(A, B);
+            if (dot(VEC, T) < 0) { VEC.x = -VEC.x; VEC.y = -VEC.y; VEC.z = -VEC.z; }
+        }
+    }
+}
+
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+
+__device__ __noinline__ double face_and_final(const v3 S0, const v3 S1, const v3 S2, const v3 T0, const v3 T1, const v3 T2, bool shown_disjoint, double mindd) {
+    const v3 S[3] = { S0, S1, S2 }, T[3] = { T0, T1, T2 };
+    const v3 Sv[3] = { S1 - S0, S2 - S1, S0 - S2 }, Tv[3] = { T1 - T0, T2 - T1, T0 - T2 };
+    double d;
+    if (face_case(S, Sv, T, shown_disjoint, d)) return d;
+    if (face_case(T, Tv, S, shown_disjoint, d)) return d;
+    return shown_disjoint ? sqrt(mindd) : 0.0;
+}
+
+/* S0..S2: triangle of mesh A; T0..T2: triangle of mesh B already in A's frame (identical values on the 9 lanes of a group) */
+__device__ __forceinline__ double tri_dist_coop(bool act, int lane, const v3& S0, const v3& S1, const v3& S2, const v3& T0, const v3& T1, const v3& T2) {
+    const int g = lane / 9, e = lane - 9 * g;
+    const int i = e / 3, j = e - 3 * i;
+    /* this lane's edge pair: edge i of S = (Si, Si+1), opposite vertex Si+2; edge j of T likewise */
+    const v3 Sa = i == 0 ? S0 : (i == 1 ? S1 : S2), Sb = i == 0 ? S1 : (i == 1 ? S2 : S0), Sc = i == 0 ? S2 : (i == 1 ? S0 : S1);
+    const v3 Ta = j == 0 ? T0 : (j == 1 ? T1 : T2), Tb = j == 0 ? T1 : (j == 1 ? T2 : T0), Tc = j == 0 ? T2 : (j == 1 ? T0 : T1);
+    v3 VEC, P, Q;
+    seg_points_inl(VEC, P, Q, Sa, Sb - Sa, Ta, Tb - Ta);
+    const v3 V = Q - P;
+    const double dd = dot(V, V);
+    double a = dot(Sc - P, VEC);
+    double b = dot(Tc - Q, VEC);
+    const bool ret = (a <= 0) && (b >= 0);
+    const double pp = dot(V, VEC);
+    if (a < 0) a = 0;
+    if (b > 0) b = 0;
+    const bool sd = (pp - a + b) > 0;
+    /* prefix minimum in edge-pair order over the 9 lanes of the group */
+    double m;
+    { const v3 d0 = S0 - T0; m = dot(d0, d0) + 1; }            /* mindd initialisation of the scalar routine */
+    const int base = 9 * g;
+    bool upd = false;
+    double mall = m;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+        const int src = base + t > 31 ? 31 : base + t;
+        const double dt = shfl_f64(dd, src);
+        if (t == e) upd = dd <= mall;                           /* compares with min(init, dd_0..dd_{e-1}) */
+        mall = (dt <= mall) ? dt : mall;                        /* running minimum exactly as "if (dd <= mindd) mindd = dd" */
+    }
+    const unsigned grp = (g < 3) ? (0x1ffu << base) : 0u;
+    const unsigned m_ret = __ballot_sync(0xffffffffu, act && upd && ret) & grp;
+    const unsigned m_sd = __ballot_sync(0xffffffffu, act && upd && sd) & grp;
+    /* every shuffle below is executed by all 32 lanes (group-specific source lanes, no divergent *_sync) */
+    const int src_first = m_ret ? (__ffs(m_ret) - 1) : (base > 31 ? 31 : base);     /* first updating edge pair with the early-return condition */
+    const double dd_first = shfl_f64(dd, src_first);
+    double result = 0;
+    if (m_ret) result = sqrt(dd_first);                       /* shown_disjoint contributions after `first` are irrelevant: the routine has returned */
+    else if (act && e == 0) result = face_and_final(S0, S1, S2, T0, T1, T2, m_sd != 0, mall);
+    result = shfl_f64(result, base > 31 ? 31 : base);         /* lane e = 0 of the group holds the value in both cases */
+    return result;
+}
+
 }  // namespace ckc
 
 /* ================================================================================================================ */
@@ -490,6 +588,36 @@ __constant__ double c_kdl_tip[2][13][3] = {
       { 66, 0, 0 }, { 152.4, 0, 0 }, { 149.6, 0, -70 }, { 0, 0, -270 }, { 0, 0, -124 }, { 0, 0, -166 } },
     { { 0, 0, 166 }, { 0, 0, 124 }, { 0, 0, 270 }, { 149.6, 0, 70 }, { 152.4, 0, 0 }, { 66, 0, 0 }, { 2 * 66 + 500.0, 0, 0 },
       { 66, 0, 0 }, { 152.4, 0, 0 }, { 149.6, 0, -70 }, { 0, 0, -270 }, { 0, 0, -124 }, { 0, 0, -166 } } };
+/* sin / cos for the Newton loop with every coefficient a constant-bank operand of its FMA (libdevice's sincos materialises
+ * its 64-bit coefficients with two moves each inside the joint loop).  Cody-Waite reduction by pi/2 in two FMAs (exact
+ * product, |x| < 1e4), fdlibm minimax kernels on [-pi/4, pi/4] (< 1 ulp); larger arguments take the library path. */
+__constant__ double c_sc[16] = {
+    6.36619772367581382433e-01,      /* 0: 2/pi */
+    1.57079632679489655800e+00,      /* 1: pi/2 high */
+    6.12323399573676603587e-17,      /* 2: pi/2 low */
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,        /* 3..8: S1..S6 */
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,         /* 9..14: C1..C6 */
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11, 0.0 };
+
+__device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
+    if (!(fabs(x) < 1.0e4)) { sincos(x, sn, cs); return; }
+    const double kd = rint(x * c_sc[0]);
+    const int k = (int)kd;
+    double r = fma(-kd, c_sc[1], x);
+    r = fma(-kd, c_sc[2], r);
+    const double z = r * r;
+    double ps = fma(z, c_sc[8], c_sc[7]);
+    ps = fma(z, ps, c_sc[6]); ps = fma(z, ps, c_sc[5]); ps = fma(z, ps, c_sc[4]); ps = fma(z, ps, c_sc[3]);
+    const double s0 = fma(r * z, ps, r);                               /* r + r^3 (S1 + z (S2 + ...)) */
+    double pc = fma(z, c_sc[14], c_sc[13]);
+    pc = fma(z, pc, c_sc[12]); pc = fma(z, pc, c_sc[11]); pc = fma(z, pc, c_sc[10]); pc = fma(z, pc, c_sc[9]);
+    const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));               /* 1 - z/2 + z^2 (C1 + z (C2 + ...)) */
+    const double ss = (k & 1) ? c0 : s0, cc = (k & 1) ? s0 : c0;
+    *sn = (k & 2) ? -ss : ss;
+    *cs = ((k + 1) & 2) ? -cc : cc;
+}
+
 struct gd_ref {                     /* view of one thread's column of the block's shared state array [36][CKC_GD_BLOCK] */
     double* b;
     __device__ __forceinline__ double& qc(int j) const { return b[j * CKC_GD_BLOCK]; }
@@ -549,7 +677,7 @@ __device__ __forceinline__ bool gd_iterate(const ckc_kin_dev& k, const gd_ref& s
 #pragma unroll
             for (int b = 0; b <= a; b++) A[a][b] += col[a] * col[b];
         double sj, cj;
-        sincos(s.qc(j), &sj, &cj);
+        sincos_fast(s.qc(j), &sj, &cj);
         s.cs(j) = cj; s.sn(j) = sj;
         rot_by_axis(ax, R, cj, sj);
         const double tx = c_kdl_tip[e][j + 1][0], ty = c_kdl_tip[e][j + 1][1], tz = c_kdl_tip[e][j + 1][2];

@@ -161,9 +161,10 @@ __device__ __forceinline__ ckc_pair_dev load_pair(const ckc_world_dev& w, int p)
     return r;
 }
 
-/* exact leaf test: triangle ta of mesh A vs tb of mesh B under the pair's poses, PQP_Tolerance conventions:
- * R = Ra^T Rb, T = Ra^T (Tb - Ta), triangle B transformed into A's frame, then TriDist */
-__device__ __forceinline__ double leaf_distance(const ckc_world_dev& w, const double* cfg_frames, const ckc_pair_dev pr, int ta, int tb) {
+/* leaf operands with PQP_Tolerance's conventions: R = Ra^T Rb, T = Ra^T (Tb - Ta); triangle ta of mesh A as stored, triangle tb
+ * of mesh B transformed into A's frame */
+__device__ __forceinline__ void load_leaf_pair(const ckc_world_dev& w, const double* cfg_frames, const ckc_pair_dev pr, int ta, int tb,
+                                               v3& S0, v3& S1, v3& S2, v3& T0, v3& T1, v3& T2) {
     const double* Fa = frame64(w, cfg_frames, pr.frame_a);
     const double* Fb = frame64(w, cfg_frames, pr.frame_b);
     double R[9], T[3];
@@ -176,18 +177,17 @@ __device__ __forceinline__ double leaf_distance(const ckc_world_dev& w, const do
     }
     const double* pa = w.tris + 9 * (int64_t)(pr.tri_a + ta);
     const double* pb = w.tris + 9 * (int64_t)(pr.tri_b + tb);
-    v3 S[3], Tt[3];
+    S0 = { pa[0], pa[1], pa[2] }; S1 = { pa[3], pa[4], pa[5] }; S2 = { pa[6], pa[7], pa[8] };
+    v3* Tt[3] = { &T0, &T1, &T2 };
 #pragma unroll
     for (int v = 0; v < 3; v++) {
-        S[v] = { pa[3 * v], pa[3 * v + 1], pa[3 * v + 2] };
         const double x = pb[3 * v], y = pb[3 * v + 1], z = pb[3 * v + 2];
-        Tt[v] = { R[0] * x + R[1] * y + R[2] * z + T[0], R[3] * x + R[4] * y + R[5] * z + T[1], R[6] * x + R[7] * y + R[8] * z + T[2] };
+        *Tt[v] = { R[0] * x + R[1] * y + R[2] * z + T[0], R[3] * x + R[4] * y + R[5] * z + T[1], R[6] * x + R[7] * y + R[8] * z + T[2] };
     }
-    return tri_dist(S, Tt);
 }
 
 #ifndef CKC_COLLIDE_MINBLOCKS
-#define CKC_COLLIDE_MINBLOCKS 4
+#define CKC_COLLIDE_MINBLOCKS 2
 #endif
 template <bool kBigStack>
 __global__ void __launch_bounds__(CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_MINBLOCKS)
@@ -231,26 +231,29 @@ k_collide(const ckc_world_dev w, const collide_args a) {
         int top = w.npairs;
         for (int k2 = lane; k2 < w.npairs; k2 += 32) stack[w.npairs - 1 - k2] = (uint32_t)__ldg(w.pair_order + k2) << 22;
         int ntri = 0;
-        bool hit = false, overflow = false, hot = false;      /* hot: a queued triangle pair looks like a hit -> test it now */
+        bool hit = false, overflow = false, hot = false, draining = false;      /* hot: a queued triangle pair looks like a hit -> test it now */
         /* env 2: "path not from above" rule, collisionDetection.cpp:427-428 */
         if (w.env == 2 && (cfg_frames[7 * 12 + 11] > 800.0 || cfg_frames[15 * 12 + 11] > 800.0)) { hit = true; top = 0; }
         __syncwarp();
 
         while (!hit) {
-            if (ntri >= 32 || (ntri > 0 && (top == 0 || hot))) {
-                hot = false;
-                /* ---- exact triangle tests, up to 32 at a time ---- */
-                const int cnt = ntri < 32 ? ntri : 32;
-                bool h = false;
+            if (ntri > 0 && (draining || ntri >= 6 || top == 0 || hot)) {
+                hot = false; draining = ntri > 3;
+                /* ---- exact triangle tests: three pairs per step, nine lanes (one per edge pair) each ---- */
+                const int g = lane / 9;
+                const int take = ntri < 3 ? ntri : 3;
+                const bool act = g < take;
                 uint32_t t = 0;
-                if (lane < cnt) {
-                    t = triq[ntri - 1 - lane];
-                    const int p = t >> 20;
-                    const double d = leaf_distance(w, cfg_frames, smem_pair(s_pairs, p), (t >> 10) & 1023, t & 1023);
-                    h = d <= w.tol;                                   /* PQP: closer_than_tolerance iff d <= tolerance */
+                v3 S0 = { 0, 0, 0 }, S1 = S0, S2 = S0, T0 = S0, T1 = S0, T2 = S0;
+                if (act) {
+                    t = triq[ntri - 1 - g];
+                    const ckc_pair_dev pr = smem_pair(s_pairs, t >> 20);
+                    load_leaf_pair(w, cfg_frames, pr, (t >> 10) & 1023, t & 1023, S0, S1, S2, T0, T1, T2);
                 }
-                n_tri += cnt;
-                ntri -= cnt;
+                const double d = tri_dist_coop(act, lane, S0, S1, S2, T0, T1, T2);
+                const bool h = act && (lane - 9 * g) == 0 && d <= w.tol;      /* PQP: closer_than_tolerance iff d <= tolerance */
+                n_tri += take;
+                ntri -= take;
                 if (per_pair) {
                     if (h) a.pair_flags[sample * CKC_MAX_PAIRS + (t >> 20)] = 1;
                 } else {
