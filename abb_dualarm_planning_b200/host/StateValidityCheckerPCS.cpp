@@ -246,3 +246,93 @@ void StateValidityChecker::LogPerf2file() {                   /* 16 lines, fixed
       << nodes_in_trees << std::endl << local_connection_time << std::endl << local_connection_count << std::endl << local_connection_success_count << std::endl
       << sampling_time << std::endl << sampling_counter[0] << std::endl << sampling_counter[1] << std::endl;
 }
+
+#ifdef CKC_FLAVOUR_HB
+/* ---- hybrid flavour: GD members (StateValidityCheckerHB.cpp:109-147 + kdl_class.cpp:68-140) ---- */
+bool StateValidityChecker::GD(State q) {
+    IK_counter++;
+    double qo[12]; uint8_t ok = 0, conv = 0; int32_t it = 0;
+    ckc_gd_project(ckc_.ctx(), 1, q.data(), qo, &ok, &conv, &it);
+    if (conv) q_solution.assign(qo, qo + 12);
+    return ok != 0;
+}
+bool StateValidityChecker::IKproject(State& q) {
+    double qo[12]; uint8_t v = 0;
+    IK_counter++;
+    ckc_gd_validate(ckc_.ctx(), 1, q.data(), qo, &v);
+    if (v) q.assign(qo, qo + 12);
+    return v != 0;
+}
+bool StateValidityChecker::IKproject(const ob::State* state) {
+    State q1(6), q2(6); retrieveStateVector(state, q1, q2);
+    State q = join_Vectors(q1, q2);
+    if (!IKproject(q)) return false;
+    seperate_Vector(q, q1, q2); updateStateVector(state, q1, q2);
+    return true;
+}
+State StateValidityChecker::sample_q_gd() {
+    const int B = 1024; std::vector<double> q(12 * B), qo(12 * B); std::vector<uint8_t> v(B);
+    for (;;) {
+        for (int i = 0; i < 12 * B; i++) q[i] = -PI_ + (double)rand() / RAND_MAX * 2 * PI_;
+        ckc_gd_validate(ckc_.ctx(), B, q.data(), qo.data(), v.data());
+        IK_counter += B;
+        for (int i = 0; i < B; i++) { if (v[i]) { sampling_counter[0]++; return State(qo.begin() + 12 * i, qo.begin() + 12 * i + 12); } sampling_counter[1]++; }
+    }
+}
+#endif
+
+#ifdef CKC_FLAVOUR_RSS
+/* ---- RSS flavour ---- */
+bool StateValidityChecker::sampleSingular(ob::State* state) {
+    State q1(6), q2(6), q2_mode(6), q2_add(6);
+    const int sMode = rand() % 3;                                  /* RSS.cpp:260-275 */
+    switch (sMode) {
+    case 0: q2_mode = { 1, 1, 0, 1, 0, 1 }; q2_add = { 0, 0, -PI_ / 2, 0, 0, 0 }; break;
+    case 1: q2_mode = { 1, 1, 1, 1, 0, 1 }; q2_add = { 0, 0, 0, 0, 0, 0 }; break;
+    default: q2_mode = { 1, 1, 0, 1, 1, 1 }; q2_add = { 0, 0, -PI_ / 2, 0, 0, 0 };
+    }
+    for (;;) {
+        for (int i = 0; i < 6; i++) {
+            q1[i] = ((double)rand() / (RAND_MAX)) * 2 * PI_ - PI_;
+            q2[i] = ((double)rand() / (RAND_MAX)) * 2 * PI_ - PI_;
+            q2[i] = q2[i] * q2_mode[i] + q2_add[i];               /* make the passive chain's sample singular */
+        }
+        /* IsRobotsFeasible_R2 + calc_all_IK_solutions_1 (apc_class.cpp:249-262, :407-421): the 8 branches in one batch */
+        double q[8 * 12], qo[8 * 12]; int8_t ac[8], ik[8]; uint8_t ok[8];
+        for (int s = 0; s < 8; s++) { for (int j = 0; j < 6; j++) { q[12 * s + j] = 0; q[12 * s + 6 + j] = q2[j]; } ac[s] = 1; ik[s] = (int8_t)s; }
+        ckc_pcs_project(ckc_.ctx(), 8, q, ac, ik, qo, ok);
+        IK_counter += 8;
+        int feas[8]; countSolutions = 0;
+        for (int s = 0; s < 8; s++) if (ok[s]) feas[countSolutions++] = s;
+        if (countSolutions == 0) continue;
+        const int pick = feas[rand() % countSolutions];
+        q1.assign(qo + 12 * pick, qo + 12 * pick + 6);
+        updateStateVector(state, q1, q2);
+        State idk = identify_state_ik(state);
+        if (idk[1] == -1) continue;
+        if (!collision_state(getPMatrix(), q1, q2)) return true;
+    }
+}
+bool StateValidityChecker::checkMotionRBS(const ob::State* s1, const ob::State* s2, int sg, int active_chain, int ik_sol) {
+    State qa1(6), qa2(6), qb1(6), qb2(6);
+    retrieveStateVector(s1, qa1, qa2); retrieveStateVector(s2, qb1, qb2);
+    if (sg == 1) return checkMotionRBS(qa1, qa2, qb1, qb2, qa1, qa2, active_chain, ik_sol, 0, 0);
+    return checkMotionRBS(qa1, qa2, qb1, qb2, qb1, qb2, active_chain, ik_sol, 0, 0);
+}
+bool StateValidityChecker::checkMotionRBS(State qa1, State qa2, State qb1, State qb2, State qsg1, State qsg2, int active_chain, int ik_sol,
+                                          int recursion_depth, int ndc) {
+    /* RSS.cpp:586-613.  The singular stop rule only exists at this level: the two recursive calls of the reference go to the
+     * plain 8-argument overload, i.e. two ordinary RBS edges -- submitted as one batch of two */
+    State q1(6), q2(6);
+    if (normDistanceDuo(qa1, qa2, qb1, qb2) < RBS_tol) return true;
+    if (recursion_depth > RBS_max_depth) return false;
+    midpoint(qa1, qa2, qb1, qb2, q1, q2);
+    if (!isValidRBS(q1, q2, active_chain, ik_sol)) return false;
+    if (normDistanceDuo(q1, q2, qsg1, qsg2) < 15 * RBS_tol) return true;
+    std::vector<State> a = { join_Vectors(qa1, qa2), join_Vectors(q1, q2) }, b = { join_Vectors(q1, q2), join_Vectors(qb1, qb2) };
+    std::vector<unsigned char> ok;
+    checkMotionRBSBatch(a, b, { active_chain, active_chain }, { ik_sol, ik_sol }, ok);
+    (void)ndc;
+    return ok[0] && ok[1];
+}
+#endif

@@ -68,6 +68,23 @@ public:
     void initiate_log_parameters();
     void LogPerf2file();
 
+#ifdef CKC_FLAVOUR_HB
+    /* ---- hybrid checker (validity_checkers/StateValidityCheckerHB.{h,cpp}): sampling / projection by the KDL Newton
+     *      projection, local connection by the APC bisection ---- */
+    bool GD(State q);                                                            /* kdl_class.cpp:68-140 */
+    State get_GD_result() { return q_solution; }
+    bool IKproject(const ob::State*);                                            /* HB.cpp:109-122 */
+    bool IKproject(State&);                                                      /* GD projection of all 12 joints + collision */
+    State sample_q_gd();                                                         /* HB.cpp sample_q: GD from uniform seeds */
+#endif
+#ifdef CKC_FLAVOUR_RSS
+    /* ---- random singular sampling checker (validity_checkers/StateValidityCheckerRSS.{h,cpp}) ---- */
+    bool sampleSingular(ob::State*);                                             /* RSS.cpp:255-306 */
+    bool checkMotionRBS(const ob::State*, const ob::State*, int sg, int active_chain, int ik_sol);          /* RSS.cpp:566-583 */
+    bool checkMotionRBS(State, State, State, State, State, State, int, int, int, int);                      /* RSS.cpp:586-613 */
+    int get_countSolutions() { return countSolutions; }
+#endif
+
     /* ---- batch forms (new): what a planner calls to submit whole batches ---- */
     /** n configurations (q[i] = 12 joints), per-sample active chain / IK branch; returns valid flags, projects q in place */
     void isValidBatch(std::vector<State>& q, const std::vector<int>& ac, const std::vector<int>& ik, std::vector<unsigned char>& valid);
@@ -80,7 +97,8 @@ private:
     void init(int env);
     ob::SpaceInformation* mysi_;
     CkcContext ckc_;
-    State q_IK_solution_1, q_IK_solution_2;
+    State q_IK_solution_1, q_IK_solution_2, q_solution;
+    int countSolutions = 0;
     double L;
     Matrix Q, P;
     bool withObs = true;

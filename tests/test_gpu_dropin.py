@@ -83,3 +83,39 @@ def test_gd_dropin_class(tmp_path, oracle):
     assert d.max() < 2e-5
     batch = np.array([int(x) for x in lines[len(q)].split()[1:]])
     assert (batch == valid_o).all()
+
+
+def _singular_rbs_oracle(oracle, a, b, ac, ik):
+    """RSS.cpp:586-613 restated with oracle primitives: singular stop rule at the top level only"""
+    if np.linalg.norm(a - b) < 0.05:
+        return True
+    m = (a + b) / 2
+    ok, valid, mq = oracle.pcs_validate(m[None], ac, ik)
+    if not valid[0]:
+        return False
+    if np.linalg.norm(mq[0] - a) < 15 * 0.05:
+        return True
+    r, _ = oracle.pcs_check_motion_rbs(np.stack([a, mq[0]]), np.stack([mq[0], b]), ac, ik)
+    return bool(r[0] and r[1])
+
+
+def test_rss_dropin_class(tmp_path, oracle):
+    """sampleSingular + the singular-endpoint RBS variant of StateValidityCheckerRSS"""
+    out = str(tmp_path / "out.txt")
+    env = dict(os.environ, CKC_MESH_PATH=PACK)
+    r = subprocess.run([os.path.join(HOST, "test_dropin_rss"), out], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = np.array([[float(x) for x in ln.split()] for ln in open(out).read().strip().split("\n")])
+    assert len(rows) == 12
+    n_rbs = 0
+    for row in rows:
+        ida, proj, rbs = row[0:2].astype(int), int(row[2]), int(row[3])
+        a, b = row[4:16], row[16:28]
+        # the singular sample: passive arm singular (q5 = 0 or the q3 = -PI_/2 modes), closed and collision free
+        assert (np.abs(a[10]) < 1e-12) or (np.abs(a[8] + 3.1416 / 2) < 1e-12)
+        assert (oracle.identify_state_ik(a[None])[0] == ida).all() and ida[1] >= 0
+        assert oracle.collision_state(a[None])[0] == 0
+        if proj:
+            assert rbs == int(_singular_rbs_oracle(oracle, a, b, 1, ida[1]))
+            n_rbs += 1
+    assert n_rbs >= 1
