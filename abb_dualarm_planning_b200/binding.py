@@ -53,6 +53,8 @@ def load_library():
     L.ckc_pcs_project.argtypes = [vp, i64, dp, dp, dp, dp, dp]
     L.ckc_pcs_validate.argtypes = [vp, i64, dp, dp, dp, dp, dp, dp]
     L.ckc_identify_ik.argtypes = [vp, i64, dp, dp]
+    L.ckc_pcs_validate_compact.argtypes = [vp, i64, dp, dp, dp, dp, C.POINTER(C.c_int64), dp, dp, i64]
+    L.ckc_gd_validate_compact.argtypes = [vp, i64, dp, dp, C.POINTER(C.c_int64), dp, dp, i64]
     L.ckc_check_angle_limits.argtypes = [vp, i64, dp, dp]
     L.ckc_collide.argtypes = [vp, i64, dp, dp]
     L.ckc_collide_pairs.argtypes = [vp, i64, dp, dp]
@@ -170,6 +172,18 @@ class Checker:
         q, n = _q(q); qo = np.empty_like(q); valid = np.zeros(n, np.uint8)
         self._chk(self.L.ckc_gd_validate(self.ctx, n, _ptr(q), _ptr(qo), _ptr(valid)))
         return valid, qo
+
+    def gd_validate_compact(self, q, cap=None):
+        q, n = _q(q); cap = cap or max(n // 8, 1024)
+        valid = np.zeros(n, np.uint8); idx = np.zeros(cap, np.int32); qv = np.zeros((cap, 12)); nv = C.c_int64()
+        self._chk(self.L.ckc_gd_validate_compact(self.ctx, n, _ptr(q), _ptr(valid), C.byref(nv), _ptr(idx), _ptr(qv), cap))
+        return valid, idx[:nv.value], qv[:nv.value]
+
+    def pcs_validate_compact(self, q, ac, ik, cap=None):
+        q, n = _q(q); ac = _i8(ac, n); ik = _i8(ik, n); cap = cap or max(n // 8, 1024)
+        valid = np.zeros(n, np.uint8); idx = np.zeros(cap, np.int32); qv = np.zeros((cap, 12)); nv = C.c_int64()
+        self._chk(self.L.ckc_pcs_validate_compact(self.ctx, n, _ptr(q), _ptr(ac), _ptr(ik), _ptr(valid), C.byref(nv), _ptr(idx), _ptr(qv), cap))
+        return valid, idx[:nv.value], qv[:nv.value]
 
     def gd_check_motion_rbs(self, qa, qb):
         qa, n = _q(qa); qb, _ = _q(qb); ok = np.zeros(n, np.uint8); nc = np.zeros(n, np.int32)

@@ -63,6 +63,8 @@ struct ckc_ctx {
     int64_t chunk = 1 << 20;            /* samples per internal batch */
     /* persistent device storage */
     dev_buf d_nodes, d_tris, d_ctr, d_pairtab, d_static, d_pairhits, d_pairorder;
+    dev_buf d_cidx, d_cq, d_ccount;                     /* compact outputs of the *_compact entry points (per chunk regions) */
+    void* h_stage = nullptr; size_t h_stage_cap = 0;    /* pinned staging of the compact outputs */
     dev_buf rbs_seg[2], rbs_cand, rbs_pool, rbs_eok, rbs_nck, rbs_hit, rbs_eac, rbs_eik;      /* RBS frontier storage, kept between calls */
     int64_t collide_launches = 0;           /* d_small: list_count, work counters, overflow count */
     /* per-chunk work buffers: CKC_NUM_LANES independent sets, each with its own stream, so that the host entry points
@@ -465,6 +467,8 @@ extern "C" void ckc_destroy(ckc_ctx* ctx) {
     for (int l = 0; l < CKC_NUM_LANES; l++) { ctx->lanes[l].release(); if (ctx->lanes[l].ev_done) cudaEventDestroy(ctx->lanes[l].ev_done); if (ctx->lanes[l].ev_p) cudaEventDestroy(ctx->lanes[l].ev_p); if (ctx->lanes[l].ev_c) cudaEventDestroy(ctx->lanes[l].ev_c);
         if (ctx->lanes[l].st_hi) cudaStreamDestroy(ctx->lanes[l].st_hi); if (ctx->lanes[l].st) cudaStreamDestroy(ctx->lanes[l].st); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    ctx->d_cidx.release(); ctx->d_cq.release(); ctx->d_ccount.release();
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     delete ctx;
 }
 
@@ -569,11 +573,33 @@ static int run_gd_chunk(ckc_ctx* ctx, ckc_lane& L, int64_t n, const double* d_q,
 /*   chunk k runs entirely on lane k % CKC_NUM_LANES (H2D -> kernels -> D2H in stream order); the lanes' streams overlap */
 /*   each other, so copies in both directions and kernels of neighbouring chunks run concurrently (pinned host memory). */
 /* ---------------------------------------------------------------------------------------------------------------- */
+struct compact_out { int64_t* n_valid; int32_t* idx; double* q_valid; int64_t cap; };
+
 static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out,
-                        uint8_t* ok, uint8_t* conv, int32_t* iters, uint8_t* valid, bool collide) {
-    if (!ctx || n < 0 || (n > 0 && (!q || (flavour == 0 && !ik)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+                        uint8_t* ok, uint8_t* conv, int32_t* iters, uint8_t* valid, bool collide, const compact_out* co = nullptr) {
+    if (!ctx || n < 0 || n > 0x7fffffff || (n > 0 && (!q || (flavour == 0 && !ik)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     const int64_t C = n <= ctx->pipe_chunk ? std::max<int64_t>(n, 1) : ctx->pipe_chunk;
+    /* compact mode: each chunk appends its valid (index, configuration) pairs to its own device region; a fixed-size prefix
+     * (5 % of the chunk + 1024 entries) of every region is copied back inside the pipeline, the rare overflow afterwards */
+    const int64_t nchunks = n > 0 ? (n + C - 1) / C : 0;
+    const int64_t ccopy = C / 20 + 1024;
+    int32_t* h_cnt = nullptr; int32_t* h_idx = nullptr; double* h_q = nullptr;
+    if (co && n > 0) {
+        CU(ctx->d_cidx.reserve((size_t)n * 4)); CU(ctx->d_cq.reserve((size_t)n * 96)); CU(ctx->d_ccount.reserve((size_t)nchunks * 4));
+        const size_t need = (size_t)nchunks * (16 + (size_t)ccopy * 4 + (size_t)ccopy * 96);
+        if (need > ctx->h_stage_cap) {
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+            CU(cudaMallocHost(&ctx->h_stage, need));
+            ctx->h_stage_cap = need;
+        }
+        h_cnt = (int32_t*)ctx->h_stage;
+        h_q = (double*)((char*)ctx->h_stage + (size_t)nchunks * 16);
+        h_idx = (int32_t*)((char*)h_q + (size_t)nchunks * ccopy * 96);
+        CU(cudaMemsetAsync(ctx->d_ccount.p, 0, (size_t)nchunks * 4, ctx->lanes[0].st));
+        CU(cudaStreamSynchronize(ctx->lanes[0].st));
+    }
     int k = 0;
     for (int64_t off = 0; off < n; off += C, k++) {
         const int64_t c = std::min(C, n - off);
@@ -599,8 +625,37 @@ static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, co
         if (conv) CU(cudaMemcpyAsync(conv + off, L.aux.p, (size_t)c, cudaMemcpyDeviceToHost, st));
         if (iters) CU(cudaMemcpyAsync(iters + off, L.aux2.p, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
         if (valid) CU(cudaMemcpyAsync(valid + off, L.valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (co) {
+            int32_t* dci = ctx->d_cidx.as<int32_t>() + off; double* dcq = ctx->d_cq.as<double>() + off * 12; int32_t* dcc = ctx->d_ccount.as<int32_t>() + k;
+            ckc_launch_compact_valid(c, (int32_t)off, L.valid.as<uint8_t>(), L.qout.as<double>(), AOS, dci, dcq, dcc, st);
+            ctx->launches++;
+            CU(cudaGetLastError());
+            const int64_t cc = std::min(ccopy, c);
+            CU(cudaMemcpyAsync(h_cnt + k, dcc, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_idx + (size_t)k * ccopy, dci, (size_t)cc * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_q + (size_t)k * ccopy * 12, dcq, (size_t)cc * 96, cudaMemcpyDeviceToHost, st));
+        }
     }
     for (int l = 0; l < CKC_NUM_LANES; l++) CU(cudaStreamSynchronize(ctx->lanes[l].st));
+    if (co) {
+        int64_t total = 0;
+        for (int64_t kk = 0; kk < nchunks; kk++) {
+            const int64_t cnt = h_cnt[kk], off = kk * C;
+            const int64_t room = std::max<int64_t>(0, std::min(cnt, co->cap - total));
+            const int64_t staged = std::min(room, ccopy);
+            if (staged > 0) {
+                memcpy(co->idx + total, h_idx + (size_t)kk * ccopy, (size_t)staged * 4);
+                memcpy(co->q_valid + total * 12, h_q + (size_t)kk * ccopy * 12, (size_t)staged * 96);
+            }
+            if (room > staged) {          /* more valid samples in this chunk than the staged prefix: fetch the rest directly */
+                CU(cudaMemcpy(co->idx + total + staged, ctx->d_cidx.as<int32_t>() + off + staged, (size_t)(room - staged) * 4, cudaMemcpyDeviceToHost));
+                CU(cudaMemcpy(co->q_valid + (total + staged) * 12, ctx->d_cq.as<double>() + (off + staged) * 12, (size_t)(room - staged) * 96, cudaMemcpyDeviceToHost));
+            }
+            total += cnt;
+        }
+        *co->n_valid = total;
+        if (total > co->cap) return fail(ctx, CKC_ERR_CAPACITY, "compact output capacity too small");
+    }
     return CKC_OK;
 }
 
@@ -614,6 +669,21 @@ extern "C" int ckc_pcs_validate(ckc_ctx* ctx, int64_t n, const double* q, const 
 }
 extern "C" int ckc_gd_project(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* ok, uint8_t* converged, int32_t* iters) {
     return project_host(ctx, 1, n, q, nullptr, nullptr, q_out, ok, converged, iters, nullptr, false);
+}
+extern "C" int ckc_pcs_validate_compact(ckc_ctx* ctx, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, uint8_t* valid,
+                                        int64_t* n_valid, int32_t* idx, double* q_valid, int64_t cap) {
+    if (!n_valid || !idx || !q_valid || cap < 0) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    if (ctx) ctx->host_stats.is_valid_calls += n;
+    *n_valid = 0;
+    compact_out co = { n_valid, idx, q_valid, cap };
+    return project_host(ctx, 0, n, q, ac, ik, nullptr, nullptr, nullptr, nullptr, valid, true, &co);
+}
+extern "C" int ckc_gd_validate_compact(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* valid, int64_t* n_valid, int32_t* idx, double* q_valid, int64_t cap) {
+    if (!n_valid || !idx || !q_valid || cap < 0) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    if (ctx) ctx->host_stats.is_valid_calls += n;
+    *n_valid = 0;
+    compact_out co = { n_valid, idx, q_valid, cap };
+    return project_host(ctx, 1, n, q, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, valid, true, &co);
 }
 extern "C" int ckc_gd_validate(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* valid) {
     if (!valid) return fail(ctx, CKC_ERR_ARG, "valid must not be NULL");

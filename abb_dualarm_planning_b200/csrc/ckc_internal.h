@@ -114,6 +114,8 @@ void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const
 void ckc_launch_rx_check(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, double eps, uint8_t* ok, double* resid,
                          uint8_t* valid, int32_t* list, int32_t* list_count, cudaStream_t st);
 void ckc_launch_fma_peak(int precision, int num_sms, int iters, float* sink, cudaStream_t st);
+void ckc_launch_compact_valid(int64_t n, int32_t index_base, const uint8_t* valid, const double* q, ckc_layout l, int32_t* idx_out, double* q_out,
+                              int32_t* count, cudaStream_t st);
 void ckc_launch_transpose(const double* src, ckc_layout ls, double* dst, ckc_layout ld, int64_t n, cudaStream_t st);
 
 #endif

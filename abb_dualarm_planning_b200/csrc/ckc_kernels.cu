@@ -462,6 +462,31 @@ void ckc_launch_fma_peak(int precision, int num_sms, int iters, float* sink, cud
     else k_fma_peak<float><<<num_sms * 2, 1024, 0, st>>>(iters, sink);
 }
 
+/* valid samples of one chunk -> (index, projected configuration) pairs, warp-aggregated append; order unspecified */
+__global__ void __launch_bounds__(256)
+k_compact_valid(int64_t n, int32_t index_base, const uint8_t* __restrict__ valid, const double* __restrict__ q, ckc_layout l,
+                int32_t* __restrict__ idx_out, double* __restrict__ q_out, int32_t* count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool v = i < n && valid[i] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (v) {
+        const int pos = base + __popc(m & ((1u << lane) - 1));
+        idx_out[pos] = index_base + (int32_t)i;
+#pragma unroll
+        for (int j = 0; j < 12; j++) q_out[(int64_t)pos * 12 + j] = q[i * l.stride_i + j * l.stride_j];
+    }
+}
+void ckc_launch_compact_valid(int64_t n, int32_t index_base, const uint8_t* valid, const double* q, ckc_layout l, int32_t* idx_out, double* q_out,
+                              int32_t* count, cudaStream_t st) {
+    if (n <= 0) return;
+    k_compact_valid<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, index_base, valid, q, l, idx_out, q_out, count);
+}
+
 __global__ void k_transpose(const double* __restrict__ src, ckc_layout ls, double* __restrict__ dst, ckc_layout ld, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

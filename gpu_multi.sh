@@ -1,5 +1,11 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_gd_n2.json 2> gpurun_out/bench_gd_n2.err; echo "rc=$?"; tail -c 1500 gpurun_out/bench_gd_n2.json; tail -3 gpurun_out/bench_gd_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 1 --impl reference 2>&1 | tail -2 | cut -c1-600
+nvidia-smi topo -m 2>&1 | head -14
+N=8
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 10 --warmup 3 --no-extra > gpurun_out/bench_gd_n$N.json 2> gpurun_out/bench_gd_n$N.err; echo "N=$N rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_gd_n8.json').read().strip().split('\n')[-1])
+print('gd 8 value %.3e e2e %.3e ms/step %.3f numa %s'%(d['value'],d['e2e']['value'],d['ms_per_step'],d['config'].get('numa_node_rank0')))
+PY

@@ -186,3 +186,23 @@ def test_stats_counters(ck, oracle):
     s = ck.stats()
     assert s["ik_calls"] == 5000 and s["ik_feasible"] == int(ok.sum()) and s["collision_calls"] == int(ok.sum())
     assert s["collisions"] == int(ok.sum() - valid.sum()) and s["bv_tests"] > 0 and s["kernel_launches"] >= 3
+
+
+def test_compact_result_equals_full_result(ck, oracle):
+    """ckc_*_validate_compact returns exactly the valid subset of ckc_*_validate (entry order unspecified)"""
+    from abb_dualarm_planning_b200 import sampling
+    q, ik = sampling.sample_pcs(17, 0, 400000)           # several pipeline chunks
+    ok, valid, qo = ck.pcs_validate(q, 0, ik)
+    v2, idx, qv = ck.pcs_validate_compact(q, 0, ik)
+    assert (v2 == valid).all() and len(idx) == valid.sum()
+    order = np.argsort(idx)
+    assert (idx[order] == np.nonzero(valid)[0]).all()
+    assert (qv[order] == qo[valid == 1]).all()
+    g = sampling.sample_gd(17, 0, 300000)
+    valid, qo = ck.gd_validate(g)
+    v2, idx, qv = ck.gd_validate_compact(g)
+    order = np.argsort(idx)
+    assert (v2 == valid).all() and (idx[order] == np.nonzero(valid)[0]).all() and (qv[order] == qo[valid == 1]).all()
+    # capacity error is reported, the count still comes back
+    with pytest.raises(Exception):
+        ck.gd_validate_compact(g, cap=10)
