@@ -137,6 +137,23 @@ void StateValidityChecker::checkMotionRBSBatch(const std::vector<State>& a, cons
 }
 #endif
 
+bool StateValidityChecker::checkMotion(const ob::State* s1, const ob::State* s2) {
+    /* GD.cpp:136-175: nd = |q1 - q2| / dq, points i / (nd - 1), i = 1..nd-1, each validated independently -> one batch */
+    State q1(12), q2(12); retrieveStateVector(s1, q1); retrieveStateVector(s2, q2);
+    const double dq = 0.05;
+    const int nd = (int)(normDistance(q1, q2) / dq);
+    if (nd <= 2) return true;
+    std::vector<State> pts; std::vector<unsigned char> valid;
+    for (int i = 1; i < nd; i++) {
+        const double t = (double)i / (double)(nd - 1);
+        State q(12);
+        for (int j = 0; j < 12; j++) q[j] = q1[j] + (q2[j] - q1[j]) * t;
+        pts.push_back(q);
+    }
+    isValidBatch(pts, valid);
+    for (unsigned char v : valid) if (!v) return false;
+    return true;
+}
 bool StateValidityChecker::checkMotionRBS(const ob::State* s1, const ob::State* s2) {
     State q1(12), q2(12); retrieveStateVector(s1, q1); retrieveStateVector(s2, q2);
     return checkMotionRBS(q1, q2, 0, 0);

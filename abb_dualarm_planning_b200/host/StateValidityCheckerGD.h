@@ -41,6 +41,7 @@ public:
     bool IKproject(const ob::State*, bool = true);                 /* GD.cpp:82-94 */
     bool IKproject(State&, bool = true);                           /* GD.cpp:96-110 */
 #endif
+    bool checkMotion(const ob::State*, const ob::State*);          /* GD.cpp:136-175 / RX.cpp:157-196 */
     bool checkMotionRBS(const ob::State*, const ob::State*);       /* GD.cpp:199-211 */
     bool checkMotionRBS(State, State, int, int);                   /* GD.cpp:214-241 */
     State sample_q();                                              /* GD.cpp:53-80 / RX.cpp:53-70 */

@@ -130,6 +130,26 @@ void StateValidityChecker::isValidBatch(std::vector<State>& q, const std::vector
 }
 
 /* ---- local connection ---- */
+bool StateValidityChecker::checkMotion(const ob::State* s1, const ob::State* s2, int active_chain, int ik_sol) {
+    /* PCS.cpp:389-432: fixed grid nd = d / RBS_tol, interior points m / nd visited in bisection order until the first invalid
+     * one; the boolean is "all interior grid points valid", so the whole grid is one batch */
+    State a1(6), a2(6), b1(6), b2(6);
+    retrieveStateVector(s1, a1, a2); retrieveStateVector(s2, b1, b2);
+    const State a = join_Vectors(a1, a2), b = join_Vectors(b1, b2);
+    const int nd = (int)(stateDistance(s1, s2) / RBS_tol);
+    if (nd < 2) return true;
+    std::vector<State> pts; std::vector<int> ac(nd - 1, active_chain), ik(nd - 1, ik_sol); std::vector<unsigned char> valid;
+    for (int m = 1; m < nd; m++) {
+        const double t = (double)m / (double)nd;
+        State q(12);
+        for (int j = 0; j < 12; j++) q[j] = a[j] + (b[j] - a[j]) * t;      /* RealVectorStateSpace::interpolate */
+        pts.push_back(q);
+    }
+    isValidBatch(pts, ac, ik, valid);
+    for (unsigned char v : valid) if (!v) return false;
+    return true;
+}
+
 bool StateValidityChecker::checkMotionRBS(const ob::State* s1, const ob::State* s2, int active_chain, int ik_sol) {
     State qa1(6), qa2(6), qb1(6), qb2(6);
     retrieveStateVector(s1, qa1, qa2); retrieveStateVector(s2, qb1, qb2);

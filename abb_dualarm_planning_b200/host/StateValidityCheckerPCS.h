@@ -35,6 +35,7 @@ public:
     bool isValid(const ob::State*);                                              /* PCS.cpp:323-357 */
     bool isValid(const ob::State*, int, int);                                    /* PCS.cpp:360-387 */
     bool isValidRBS(State&, State&, int, int);                                   /* PCS.cpp:455-466 */
+    bool checkMotion(const ob::State*, const ob::State*, int, int);              /* PCS.cpp:389-432 */
     bool checkMotionRBS(const ob::State*, const ob::State*, int, int);           /* PCS.cpp:470-483 */
     bool checkMotionRBS(State, State, State, State, int, int, int, int);         /* PCS.cpp:486-511 */
     bool reconstructRBS(const ob::State*, const ob::State*, Matrix&, int, int);  /* PCS.cpp:531-543 */

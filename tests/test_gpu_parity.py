@@ -167,10 +167,14 @@ def test_rx_validate_vs_oracle_and_fixtures(oracle, gold):
     c1.close()
 
 
-def test_env2_collision_vs_oracle(oracle_env2):
-    from abb_dualarm_planning_b200 import Checker
+def test_env2_collision_vs_oracle(oracle_env2, gold):
+    from abb_dualarm_planning_b200 import Checker, sampling
     c2 = Checker(env=2)
     assert c2.num_pairs == 103
+    g = gold("spcs_env2_seed4_60k_mask.npz")              # masks produced by the reference binary with env = 2
+    qg, ikg = sampling.sample_pcs(4, 0, int(g["n"]))
+    okg, validg, _ = c2.pcs_validate(qg, 0, ikg)
+    assert (okg == np.unpackbits(g["ok_bits"])[:len(okg)]).all() and (validg == np.unpackbits(g["valid_bits"])[:len(okg)]).all()
     q, ik = oracle_env2.sample_pcs(4, 0, 40000)
     ok_o, valid_o, q_o = oracle_env2.pcs_validate(q, 0, ik)
     ok, valid, qo = c2.pcs_validate(q, 0, ik)

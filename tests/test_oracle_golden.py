@@ -152,3 +152,12 @@ def test_gd_projection_statistics(oracle):
 def test_work_model_fixture():
     wm = json.load(open(os.path.join(GOLD, "work_model.json")))
     assert 0.02 < wm["f_ik"] < 0.03 and wm["n_bv_mean"] > 100
+
+
+def test_env2_mask_vs_binary(oracle_env2, gold):
+    g = gold("spcs_env2_seed4_60k_mask.npz")
+    n = int(g["n"])
+    q, ik = oracle_env2.sample_pcs(4, 0, n)
+    ok, valid, _ = oracle_env2.pcs_validate(q, 0, ik)
+    assert (ok == np.unpackbits(g["ok_bits"])[:n]).all() and (valid == np.unpackbits(g["valid_bits"])[:n]).all()
+    assert ok.sum() == 749 and valid.sum() == 314

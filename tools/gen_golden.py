@@ -108,6 +108,13 @@ def main():
     ikid = refshim.identify_ik(qc)
     np.savez_compressed(os.path.join(GOLD, "identify_ik.npz"), q=qc, ik=ikid)
 
+    # 6b. env 2 (cones, D = 1200, L = 500, "T7z > 800" rule): masks of 60000 S-PCS samples from the genuine binary
+    O2 = lib.Oracle(2)
+    q2, ik2 = O2.sample_pcs(4, 0, 60000)
+    ok2, valid2, _, _ = refshim.pcs_validate(q2, 0, ik2, env=2)
+    np.savez_compressed(os.path.join(GOLD, "spcs_env2_seed4_60k_mask.npz"), seed=4, n=60000, ok_bits=np.packbits(ok2), valid_bits=np.packbits(valid2))
+    print("env 2: feasible %d valid %d" % (ok2.sum(), valid2.sum()))
+
     # 7. reference fixture files (data): solved path, RX accepted configurations
     path = np.loadtxt(os.path.join(REFROOT, "paths", "path.txt"), skiprows=1)
     cs, _ = refshim.collide(path)
