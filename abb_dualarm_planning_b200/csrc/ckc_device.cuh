@@ -600,8 +600,10 @@ __constant__ double c_sc[16] = {
     4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,         /* 9..14: C1..C6 */
     -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11, 0.0 };
 
+__device__ __noinline__ void sincos_lib(double x, double* sn, double* cs) { sincos(x, sn, cs); }     /* cold: |x| >= 1e4 */
+
 __device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
-    if (!(fabs(x) < 1.0e4)) { sincos(x, sn, cs); return; }
+    if (!(fabs(x) < 1.0e4)) { sincos_lib(x, sn, cs); return; }
     const double kd = rint(x * c_sc[0]);
     const int k = (int)kd;
     double r = fma(-kd, c_sc[1], x);

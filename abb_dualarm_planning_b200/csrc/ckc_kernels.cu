@@ -505,8 +505,12 @@ void ckc_launch_transpose(const double* src, ckc_layout ls, double* dst, ckc_lay
  * to the collision work list.  Persistent grid with LANE-level work stealing: a lane that has converged writes its
  * result and takes the next sample (one warp-aggregated atomicAdd per refill), so the spread of the iteration count
  * (median 9, max > 25) does not idle the other 31 lanes of its warp. */
-__global__ void __launch_bounds__(CKC_GD_BLOCK, 4)
-k_gd_project(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, ckc_layout li, uint64_t key, uint64_t i0, int seeded,
+#ifndef CKC_GD_MINBLOCKS
+#define CKC_GD_MINBLOCKS 4
+#endif
+template <bool seeded>
+__global__ void __launch_bounds__(CKC_GD_BLOCK, CKC_GD_MINBLOCKS)
+k_gd_project(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, ckc_layout li, uint64_t key, uint64_t i0,
              double* __restrict__ q_raw, ckc_layout lo, int32_t* __restrict__ state_out, unsigned long long* work_counter) {
     __shared__ double sh_state[36 * CKC_GD_BLOCK];
     const int lane = threadIdx.x & 31;
@@ -601,14 +605,15 @@ void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const
     if (n <= 0) return;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gd_project, CKC_GD_BLOCK, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gd_project<false>, CKC_GD_BLOCK, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 2;
     }
     int64_t blocks = (int64_t)num_sms * blocks_per_sm;
     /* at least ~6 samples per lane so that the lane-level work stealing can balance the iteration counts */
     const int64_t needed = (n + 6 * CKC_GD_BLOCK - 1) / (6 * CKC_GD_BLOCK);
     if (blocks > needed) blocks = needed;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
-    k_gd_project<<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, seeded, q_out, lo, state_scratch, work_counter);
+    if (seeded) k_gd_project<true><<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, q_out, lo, state_scratch, work_counter);
+    else k_gd_project<false><<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, q_out, lo, state_scratch, work_counter);
     k_gd_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kin, n, q, li, seeded, q_out, lo, state_scratch, ok, converged, iters, valid, list, list_count, ctr);
 }
 
