@@ -262,7 +262,7 @@ __device__ __forceinline__ bool boxes_farther_than(const box32& A, const float* 
             const float len2 = 1.0f - R[i][j] * R[i][j];             /* |a_i x b_j|^2 */
             const float g = fabsf(t[i2] * R[i1][j] - t[i1] * R[i2][j]) - (A.h[i1] * AR[i2][j] + A.h[i2] * AR[i1][j]) -
                             (B.h[j1] * AR[i][j2] + B.h[j2] * AR[i][j1]);
-            far = far || (len2 > 1e-3f && g > 0.0f && g * g > tol * tol * len2);
+            far = far | ((len2 > 1e-3f) & (g > 0.0f) & (g * g > tol * tol * len2));       /* bitwise: no short-circuit branches */
         }
     }
     return far;

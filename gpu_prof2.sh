@@ -3,5 +3,5 @@ cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 1 --no-extra --no-cpu"
 $CMD > gpurun_out/plain_gd3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_collide -s 2 -c 1 -o gpurun_out/r1_prof_collide_final $CMD > gpurun_out/ncu_gd3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_collide -s 2 -c 1 -o gpurun_out/r1_prof_collide_coop $CMD > gpurun_out/ncu_gd3.log 2>&1
 echo "collide full rc=$?"
