@@ -7,7 +7,7 @@
  *   ik_arm            two_robots::IKsolve_rob          proj_classes/apc_class.cpp:114-245
  *   project_passive   calc_specific_IK_solution_R1/R2  proj_classes/apc_class.cpp:356-389
  *   robot_frames      collision_state link frames      validity_checkers/collisionDetection.cpp:72-260
- *   tri_dist          PQP v1.3 TriDist / SegPoints (external library used by collision_state)
+ *   tri_dist_coop     PQP v1.3 TriDist / SegPoints (external library used by collision_state), warp-cooperative
  */
 #ifndef CKC_DEVICE_CUH_
 #define CKC_DEVICE_CUH_
@@ -278,38 +278,6 @@ __device__ __forceinline__ v3 madd(const v3& a, const v3& b, double s) { return 
 __device__ __forceinline__ double dot(const v3& a, const v3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ v3 cross(const v3& a, const v3& b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
 
-/* closest points X (on P + tA) and Y (on Q + uB), t,u in [0,1]; VEC: separating direction that survives X == Y */
-__device__ __noinline__ void seg_points(v3& VEC, v3& X, v3& Y, const v3& P, const v3& A, const v3& Q, const v3& B) {
-    v3 T = Q - P;
-    const double AA = dot(A, A), BB = dot(B, B), AB = dot(A, B), AT = dot(A, T), BT = dot(B, T);
-    const double denom = AA * BB - AB * AB;
-    double t = (AT * BB - BT * AB) / denom;
-    if ((t < 0) || isnan(t)) t = 0; else if (t > 1) t = 1;
-    const double u = (t * AB - BT) / BB;
-    if ((u <= 0) || isnan(u)) {
-        Y = Q;
-        t = AT / AA;
-        if ((t <= 0) || isnan(t)) { X = P; VEC = Q - P; }
-        else if (t >= 1) { X = P + A; VEC = Q - X; }
-        else { X = madd(P, A, t); VEC = cross(A, cross(T, A)); }
-    } else if (u >= 1) {
-        Y = Q + B;
-        t = (AB + AT) / AA;
-        if ((t <= 0) || isnan(t)) { X = P; VEC = Y - P; }
-        else if (t >= 1) { X = P + A; VEC = Y - X; }
-        else { X = madd(P, A, t); T = Y - P; VEC = cross(A, cross(T, A)); }
-    } else {
-        Y = madd(Q, B, u);
-        if ((t <= 0) || isnan(t)) { X = P; VEC = cross(B, cross(T, B)); }
-        else if (t >= 1) { X = P + A; T = Q - X; VEC = cross(B, cross(T, B)); }
-        else {
-            X = madd(P, A, t);
-            VEC = cross(A, B);
-            if (dot(VEC, T) < 0) { VEC.x = -VEC.x; VEC.y = -VEC.y; VEC.z = -VEC.z; }
-        }
-    }
-}
-
 /* vertex-vs-face case of TriDist: the vertices V[] of one triangle against the plane of the other (F0.., edges E[], normal N) */
 __device__ __forceinline__ bool face_case(const v3* F, const v3* E, const v3* V, bool& shown_disjoint, double& out_d) {
     const v3 N = cross(E[0], E[1]);
@@ -332,40 +300,6 @@ __device__ __forceinline__ bool face_case(const v3* F, const v3* E, const v3* V,
         return true;
     }
     return false;
-}
-
-__device__ __noinline__ double tri_dist(const v3* S, const v3* T) {
-    v3 Sv[3], Tv[3];
-    Sv[0] = S[1] - S[0]; Sv[1] = S[2] - S[1]; Sv[2] = S[0] - S[2];
-    Tv[0] = T[1] - T[0]; Tv[1] = T[2] - T[1]; Tv[2] = T[0] - T[2];
-    bool shown_disjoint = false;
-    double mindd;
-    { const v3 d0 = S[0] - T[0]; mindd = dot(d0, d0) + 1; }
-#pragma unroll 1
-    for (int i = 0; i < 3; i++) {
-#pragma unroll 1
-        for (int j = 0; j < 3; j++) {
-            v3 VEC, P, Q;
-            seg_points(VEC, P, Q, S[i], Sv[i], T[j], Tv[j]);
-            const v3 V = Q - P;
-            const double dd = dot(V, V);
-            if (dd <= mindd) {
-                mindd = dd;
-                const int i2 = (i + 2) % 3, j2 = (j + 2) % 3;
-                double a = dot(S[i2] - P, VEC);
-                double b = dot(T[j2] - Q, VEC);
-                if ((a <= 0) && (b >= 0)) return sqrt(dd);
-                const double p = dot(V, VEC);
-                if (a < 0) a = 0;
-                if (b > 0) b = 0;
-                if ((p - a + b) > 0) shown_disjoint = true;
-            }
-        }
-    }
-    double d;
-    if (face_case(S, Sv, T, shown_disjoint, d)) return d;      /* a vertex of T above the interior of S */
-    if (face_case(T, Tv, S, shown_disjoint, d)) return d;      /* a vertex of S above the interior of T */
-    return shown_disjoint ? sqrt(mindd) : 0.0;
 }
 
 /* ---------------------------------------------------------------------------------------------------------------- */

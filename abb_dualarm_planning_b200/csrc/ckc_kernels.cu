@@ -6,8 +6,12 @@
  *   k_link_frames   K2  one thread per feasible configuration: the 18 configuration-dependent link frames (FP64).
  *   k_collide       K3  one WARP per feasible configuration: warp-cooperative traversal of the OBB hierarchies of
  *                       the pair table with a shared-memory task stack; FP32 conservative box culling (guard band),
- *                       FP64 PQP-exact triangle distance at the leaves, __ballot_sync early-out on the first hit.
- *   k_limits, k_identify_ik, k_fma_peak, k_transpose: small helpers.
+ *                       warp-cooperative FP64 PQP-exact triangle distance at the leaves (9 lanes per triangle pair),
+ *                       __ballot_sync early-out on the first hit, adaptive pair order.
+ *   k_gd_project    K5  persistent grid with lane-level work stealing: Jacobian-free two-walk Newton iteration (kdl::GD);
+ *   k_gd_finish         dense post-processing, joint limits, work-list append.
+ *   k_rbs_expand / k_rbs_push  K4: one level of the recursive-bisection frontier.
+ *   k_rx_check, k_limits, k_identify_ik, k_compact_valid, k_update_pair_order, k_fma_peak, k_transpose: helpers.
  */
 #include "ckc_device.cuh"
 
@@ -154,13 +158,6 @@ __device__ __forceinline__ ckc_pair_dev smem_pair(const int4* sp, int p) {
     ckc_pair_dev r; r.node_a = a.x; r.node_b = a.y; r.tri_a = a.z; r.tri_b = a.w; r.frame_a = b.x; r.frame_b = b.y; r.pad0 = 0; r.pad1 = 0;
     return r;
 }
-__device__ __forceinline__ ckc_pair_dev load_pair(const ckc_world_dev& w, int p) {
-    const int4* q = reinterpret_cast<const int4*>(w.pair_tab + p);
-    const int4 a = __ldg(q), b = __ldg(q + 1);
-    ckc_pair_dev r; r.node_a = a.x; r.node_b = a.y; r.tri_a = a.z; r.tri_b = a.w; r.frame_a = b.x; r.frame_b = b.y; r.pad0 = 0; r.pad1 = 0;
-    return r;
-}
-
 /* leaf operands with PQP_Tolerance's conventions: R = Ra^T Rb, T = Ra^T (Tb - Ta); triangle ta of mesh A as stored, triangle tb
  * of mesh B transformed into A's frame */
 __device__ __forceinline__ void load_leaf_pair(const ckc_world_dev& w, const double* cfg_frames, const ckc_pair_dev pr, int ta, int tb,
