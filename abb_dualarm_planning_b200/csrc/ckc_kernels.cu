@@ -369,8 +369,9 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     collide_args a;
     a.frames = frames; a.list = list; a.d_m = d_m; a.m_max = m_max; a.hit_out = hit_out; a.valid_out = valid_out; a.pair_flags = pair_flags;
     a.work_counter = work_counter; a.ovf_list = ovf_list; a.ovf_count = ovf_count; a.big_stack = big_stack; a.ctr = ctr;
-    cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st);           /* work_counter[0] main pass, [1] overflow pass */
-    cudaMemsetAsync(ovf_count, 0, sizeof(int32_t), st);
+    /* work_counter[0] main pass, [1] overflow pass; the overflow count sits right behind them in the lanes' scratch block */
+    if (ovf_count == work_counter + 2) cudaMemsetAsync(work_counter, 0, 3 * sizeof(int32_t), st);
+    else { cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st); cudaMemsetAsync(ovf_count, 0, sizeof(int32_t), st); }
     int64_t blocks = (m_max + CKC_COLLIDE_WARPS - 1) / CKC_COLLIDE_WARPS;
     const int64_t resident = (int64_t)cfg.num_sms * CKC_COLLIDE_MINBLOCKS * 3;
     if (blocks > resident) blocks = resident;

@@ -1,4 +1,5 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -30
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+python tools/latency_probe.py

@@ -210,3 +210,21 @@ def test_compact_result_equals_full_result(ck, oracle):
     # capacity error is reported, the count still comes back
     with pytest.raises(Exception):
         ck.gd_validate_compact(g, cap=10)
+
+
+def test_tris_directory_loader_equals_packed_meshes(oracle):
+    """ckc_create accepts the reference's own ./simulator directory of .tris files (collisionDetection.cpp:502-518); the packed
+    mesh file shipped with the repo holds the same doubles, so both contexts must agree flag for flag."""
+    import os
+    from conftest import REPO
+    from abb_dualarm_planning_b200 import Checker, sampling
+    tris_dir = os.path.join(REPO, "oracle", "_ref", "simulator")
+    if not os.path.exists(os.path.join(tris_dir, "obs.tris")):
+        pytest.skip("oracle/_ref/simulator (.tris files copied from the reference by `make -C oracle ref`) is not present")
+    a = Checker(env=1, mesh_path=tris_dir)
+    b = Checker(env=1)
+    q, ik = sampling.sample_pcs(23, 0, 200000)
+    ra = a.pcs_validate(q, 0, ik); rb = b.pcs_validate(q, 0, ik)
+    assert (ra[0] == rb[0]).all() and (ra[1] == rb[1]).all() and (ra[2] == rb[2]).all()
+    assert ra[1].sum() > 1000
+    a.close(); b.close()
