@@ -81,3 +81,22 @@ def test_rbs_is_symmetric_and_monotone(ck, gold):
     ok_l, _ = ck.pcs_check_motion_rbs(g["qa"][good], qm, 0, g["ik"][good])
     ok_r, _ = ck.pcs_check_motion_rbs(qm, g["qb"][good], 0, g["ik"][good])
     assert ok_l.all() and ok_r.all()
+
+
+def test_pcs_four_million_mask_vs_oracle(ck, oracle):
+    """a second, larger seed set (seed 77, 4e6 S-PCS samples, ~95 k collision checks): the device-generated masks against the
+    CPU oracle -- any FP32 box-culling error inside the 8 mm band or any traversal bug would show up as a flipped flag."""
+    import torch
+    from abb_dualarm_planning_b200 import sampling
+    n = 4_000_000
+    st = torch.cuda.current_stream().cuda_stream
+    ok = torch.empty(n, dtype=torch.uint8, device="cuda"); valid = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ck.spcs_validate_seeded_dev(77, 0, n, None, ok.data_ptr(), valid.data_ptr(), st)
+    torch.cuda.synchronize()
+    ok = ok.cpu().numpy(); valid = valid.cpu().numpy()
+    for i0 in range(0, n, 500_000):
+        q, ik = sampling.sample_pcs(77, i0, 500_000)
+        ok_o, valid_o, _ = oracle.pcs_validate(q, 0, ik)
+        assert (ok[i0:i0 + 500_000] == ok_o).all()
+        assert (valid[i0:i0 + 500_000] == valid_o).all()
+    assert 90_000 < ok.sum() < 100_000
