@@ -53,6 +53,7 @@ def load_library():
     L.ckc_pcs_project.argtypes = [vp, i64, dp, dp, dp, dp, dp]
     L.ckc_pcs_validate.argtypes = [vp, i64, dp, dp, dp, dp, dp, dp]
     L.ckc_identify_ik.argtypes = [vp, i64, dp, dp]
+    L.ckc_pcs_is_valid.argtypes = [vp, i64, dp, dp]
     L.ckc_pcs_validate_compact.argtypes = [vp, i64, dp, dp, dp, dp, C.POINTER(C.c_int64), dp, dp, i64]
     L.ckc_gd_validate_compact.argtypes = [vp, i64, dp, dp, C.POINTER(C.c_int64), dp, dp, i64]
     L.ckc_check_angle_limits.argtypes = [vp, i64, dp, dp]
@@ -141,6 +142,11 @@ class Checker:
         q, n = _q(q); out = np.zeros((n, 2), np.int8)
         self._chk(self.L.ckc_identify_ik(self.ctx, n, _ptr(q), _ptr(out)))
         return out
+
+    def pcs_is_valid(self, q):
+        q, n = _q(q); valid = np.zeros(n, np.uint8)
+        self._chk(self.L.ckc_pcs_is_valid(self.ctx, n, _ptr(q), _ptr(valid)))
+        return valid
 
     def check_angle_limits(self, q):
         q, n = _q(q); ok = np.zeros(n, np.uint8)

@@ -842,6 +842,35 @@ extern "C" int ckc_identify_ik(ckc_ctx* ctx, int64_t n, const double* q, int8_t*
     return CKC_OK;
 }
 
+/* isValid(const ob::State*)  StateValidityCheckerPCS.cpp:323-357 */
+extern "C" int ckc_pcs_is_valid(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* valid) {
+    if (!ctx || n < 0 || (n > 0 && (!q || !valid))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    ckc_lane& L = ctx->lanes[0];
+    cudaStream_t st = L.st;
+    ctx->host_stats.is_valid_calls += n;
+    const int64_t chunk = std::min<int64_t>(ctx->chunk, 1 << 17);          /* two collision jobs per sample */
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t c = std::min(chunk, n - off);
+        CU(L.qin.reserve((size_t)c * 96)); CU(L.qout.reserve((size_t)c * 192)); CU(L.ok.reserve((size_t)c)); CU(L.valid.reserve((size_t)c));
+        CU(L.aux.reserve((size_t)c * 2)); CU(L.list.reserve((size_t)c * 8));
+        CU(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(L.list_count(), 0, 4, st));
+        CU(cudaMemsetAsync(L.aux.p, 0, (size_t)c * 2, st));
+        ckc_launch_isvalid_prepare(ctx->kin, c, L.qin.as<double>(), AOS, L.qout.as<double>(), L.ok.as<uint8_t>(), L.list.as<int32_t>(), L.list_count(), st);
+        ctx->launches++; ctx->host_stats.ik_calls += 2 * c;
+        CU(cudaGetLastError());
+        int rc = run_collision_stage(ctx, L, 2 * c, L.qout.as<double>(), AOS, L.list.as<int32_t>(), L.list_count(), L.aux.as<uint8_t>(), nullptr, nullptr, st);
+        if (rc) return rc;
+        ckc_launch_isvalid_combine(c, L.ok.as<uint8_t>(), L.aux.as<uint8_t>(), L.valid.as<uint8_t>(), st);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(valid + off, L.valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return CKC_OK;
+}
+
 extern "C" int ckc_measure_fma_peak(ckc_ctx* ctx, int precision, double* tflops) {
     if (!ctx || !tflops || (precision != 32 && precision != 64)) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));

@@ -108,6 +108,9 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
 void ckc_launch_update_pair_order(const ckc_world_dev& w, int* order_out, cudaStream_t st);
 void ckc_launch_limits(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, uint8_t* ok, cudaStream_t st);
 void ckc_launch_identify_ik(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, int8_t* ik01, cudaStream_t st);
+void ckc_launch_isvalid_prepare(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, double* jobs, uint8_t* pre, int32_t* list,
+                                int32_t* list_count, cudaStream_t st);
+void ckc_launch_isvalid_combine(int64_t n, const uint8_t* pre, const uint8_t* hit, uint8_t* valid, cudaStream_t st);
 void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const double* q, ckc_layout li, uint64_t seed, uint64_t i0, int seeded,
                            double* q_out, ckc_layout lo, uint8_t* ok, uint8_t* converged, int32_t* iters, uint8_t* valid,
                            int32_t* list, int32_t* list_count, int32_t* state_scratch, unsigned long long* work_counter, ckc_counters_dev* ctr, cudaStream_t st);

@@ -399,14 +399,8 @@ void ckc_launch_limits(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_l
 }
 
 /* identify_state_ik (StateValidityCheckerPCS.cpp:275-316): 2 FK + up to 16 IK branches per configuration, one thread each */
-__global__ void __launch_bounds__(128)
-k_identify_ik(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q, ckc_layout l, int8_t* __restrict__ ik01) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double qq[12];
-#pragma unroll
-    for (int j = 0; j < 12; j++) qq[j] = q[i * l.stride_i + j * l.stride_j];
-    int ik0 = -1, ik1 = -1;
+__device__ __forceinline__ void identify_ik(const ckc_kin_dev& kin, const double* qq, int& ik0, int& ik1) {
+    ik0 = -1; ik1 = -1;
     double R[9], p[3], Rt[9], pt[3], cand[6];
     fk_arm(kin, qq, 0, R, p);
 #pragma unroll
@@ -434,8 +428,71 @@ k_identify_ik(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q, ck
             if (sqrt(d2) < 1e-1) { ik1 = s; break; }
         }
     }
+}
+
+__global__ void __launch_bounds__(128)
+k_identify_ik(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q, ckc_layout l, int8_t* __restrict__ ik01) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double qq[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) qq[j] = q[i * l.stride_i + j * l.stride_j];
+    int ik0, ik1;
+    identify_ik(kin, qq, ik0, ik1);
     ik01[2 * i] = (int8_t)ik0;
     ik01[2 * i + 1] = (int8_t)ik1;
+}
+
+/* isValid(const ob::State*) (StateValidityCheckerPCS.cpp:323-357), first half: identify both branches, re-project each arm
+ * from the other one, apply the 0.05 / 0.12 rad agreement tests and emit the two collision jobs (q1, IK(q1)) and
+ * (IK(q2), q2) of the samples that got that far.  jobs[2i], jobs[2i+1] are AoS configurations. */
+__global__ void __launch_bounds__(128)
+k_isvalid_prepare(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q, ckc_layout l, double* __restrict__ jobs,
+                  uint8_t* __restrict__ pre, int32_t* __restrict__ list, int32_t* list_count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (i < n) {
+        double qq[12], pa[6], pb[6];
+#pragma unroll
+        for (int j = 0; j < 12; j++) qq[j] = q[i * l.stride_i + j * l.stride_j];
+        int ik0, ik1;
+        identify_ik(kin, qq, ik0, ik1);
+        /* an unidentified branch (-1) indexes the reference's branch tables out of range (:331/:342): defined as invalid here */
+        if (ik0 >= 0 && ik1 >= 0 && project_passive(kin, qq, 0, ik0, pa)) {
+            double d2 = 0;
+#pragma unroll
+            for (int j = 0; j < 6; j++) { const double d = qq[6 + j] - pa[j]; d2 += d * d; }
+            if (!(sqrt(d2) > 0.5e-1) && project_passive(kin, qq + 6, 1, ik1, pb)) {
+                d2 = 0;
+#pragma unroll
+                for (int j = 0; j < 6; j++) { const double d = qq[j] - pb[j]; d2 += d * d; }
+                ok = !(sqrt(d2) > 0.12);
+            }
+        }
+        if (ok) {
+            double* o = jobs + i * 24;
+#pragma unroll
+            for (int j = 0; j < 6; j++) { o[j] = qq[j]; o[6 + j] = pa[j]; o[12 + j] = pb[j]; o[18 + j] = qq[6 + j]; }
+        }
+        pre[i] = ok ? 1 : 0;
+    }
+    append_to_list(ok, (int32_t)(2 * i), list, list_count);
+    append_to_list(ok, (int32_t)(2 * i + 1), list, list_count);
+}
+
+__global__ void __launch_bounds__(256)
+k_isvalid_combine(int64_t n, const uint8_t* __restrict__ pre, const uint8_t* __restrict__ hit, uint8_t* __restrict__ valid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) valid[i] = (pre[i] && !hit[2 * i] && !hit[2 * i + 1]) ? 1 : 0;
+}
+void ckc_launch_isvalid_prepare(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, double* jobs, uint8_t* pre, int32_t* list,
+                                int32_t* list_count, cudaStream_t st) {
+    if (n <= 0) return;
+    k_isvalid_prepare<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kin, n, q, l, jobs, pre, list, list_count);
+}
+void ckc_launch_isvalid_combine(int64_t n, const uint8_t* pre, const uint8_t* hit, uint8_t* valid, cudaStream_t st) {
+    if (n <= 0) return;
+    k_isvalid_combine<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, pre, hit, valid);
 }
 void ckc_launch_identify_ik(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout l, int8_t* ik01, cudaStream_t st) {
     if (n <= 0) return;

@@ -93,19 +93,22 @@ State StateValidityChecker::identify_state_ik(State q1, State q2, State ik) {
 
 /* ---- validity ---- */
 bool StateValidityChecker::isValid(const ob::State* state) {
+    /* :323-357 -- identify both branches, re-project each arm from the other (0.05 / 0.12 rad agreement), collide both
+     * reconstructed configurations: one device pass (ckc_pcs_is_valid) instead of four round trips */
     isValid_counter++;
     State q1(6), q2(6); retrieveStateVector(state, q1, q2);
-    State ik = identify_state_ik(q1, q2);
-    if (ik[0] < 0 || ik[1] < 0) return false;
-    if (!calc_specific_IK_solution_R1(Q, q1, (int)ik[0])) return false;
-    State q_IK = get_IK_solution_q2();
-    if (normDistance(q2, q_IK) > 0.5e-1) return false;
-    if (withObs && collision_state(P, q1, q_IK)) return false;
-    if (!calc_specific_IK_solution_R2(Q, q2, (int)ik[1])) return false;
-    q_IK = get_IK_solution_q1();
-    if (normDistance(q1, q_IK) > 0.12) return false;
-    if (withObs && collision_state(P, q_IK, q2)) return false;
-    return true;
+    double q[12]; unsigned char v = 0;
+    for (int i = 0; i < 6; i++) { q[i] = q1[i]; q[6 + i] = q2[i]; }
+    if (!withObs) {
+        State ik = identify_state_ik(q1, q2);
+        if (ik[0] < 0 || ik[1] < 0) return false;
+        if (!calc_specific_IK_solution_R1(Q, q1, (int)ik[0])) return false;
+        if (normDistance(q2, get_IK_solution_q2()) > 0.5e-1) return false;
+        if (!calc_specific_IK_solution_R2(Q, q2, (int)ik[1])) return false;
+        return !(normDistance(q1, get_IK_solution_q1()) > 0.12);
+    }
+    if (ckc_pcs_is_valid(ckc_.ctx(), 1, q, &v) != CKC_OK) { std::cerr << "ckc: " << ckc_last_error(ckc_.ctx()) << std::endl; exit(-1); }
+    return v != 0;
 }
 bool StateValidityChecker::isValid(const ob::State* state, int active_chain, int IK_sol) {
     State q1(6), q2(6); retrieveStateVector(state, q1, q2);

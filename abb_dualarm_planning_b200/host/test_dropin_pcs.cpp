@@ -29,6 +29,13 @@ int main(int argc, char** argv) {
         if (valid && svc.isValidRBS(e1, e2, 0, ik)) rbs = svc.checkMotionRBS(v1, v2, e1, e2, 0, ik, 0, 0);   /* :63-67 */
         out << proj << " " << coll << " " << id[0] << " " << id[1] << " " << valid << " " << rbs;
         for (int j = 0; j < 6; j++) out << " " << a2[j];
+        /* the OMPL-facing isValid(state) on the projected configuration and on a slightly opened one */
+        ob::RealVectorStateSpace::StateType st(12);
+        svc.updateStateVector(&st, a1, a2);
+        out << " " << svc.isValid(&st);
+        State o2 = a2; o2[1] += 0.004;
+        svc.updateStateVector(&st, a1, o2);
+        out << " " << svc.isValid(&st);
         out << "\n";
     }
     /* sampler + batch forms */

@@ -92,6 +92,13 @@ int ckc_gd_validate_compact(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* v
  * ik01[2*i] = branch for arm-1-active, ik01[2*i+1] = branch for arm-2-active, -1 = none. */
 int ckc_identify_ik(ckc_ctx* ctx, int64_t n, const double* q, int8_t* ik01);
 
+/* isValid(const ob::State*)  -- validity_checkers/StateValidityCheckerPCS.cpp:323-357 (the ob::StateValidityChecker
+ * override OMPL calls on arbitrary states): identify both IK branches (:328), re-project arm 2 from arm 1 (branch ik[0])
+ * and require ||q2 - IK|| <= 0.05 and no collision of (q1, IK) (:331-338), then the same from arm 2 with 0.12 (:342-349).
+ * valid[i] = 1/0.  A sample whose branches cannot be identified (-1) is invalid: the reference indexes its branch tables
+ * with -1 there (undefined behaviour). */
+int ckc_pcs_is_valid(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* valid);
+
 /* check_angle_limits(State q)  apc_class.cpp:304-334 / kdl_class.cpp:213-242 */
 int ckc_check_angle_limits(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* ok);
 

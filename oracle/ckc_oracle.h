@@ -103,6 +103,10 @@ double ckco_min_pair_distance(const ckco_world* w, const double q[12]);
 /* ---- checker-level functions ---- */
 /* isValidRBS PCS.cpp:455-466 (project passive arm, then collision_state). q in/out */
 int ckco_pcs_is_valid_rbs(const ckco_kin* k, const ckco_world* w, double q[12], int ac, int ik);
+/* isValid(const ob::State*) PCS.cpp:323-357: identify both IK branches, both active-chain projections must reproduce the
+ * other arm within 0.05 / 0.12 rad (Euclid) and be collision free.  A configuration whose branches cannot be identified
+ * is invalid (the reference indexes its branch tables with -1 there: undefined behaviour) */
+int ckco_pcs_is_valid_full(const ckco_kin* k, const ckco_world* w, const double q[12]);
 /* checkMotionRBS PCS.cpp:486-511. nchecks (may be NULL) counts isValidRBS calls (isValid_counter) */
 int ckco_pcs_check_motion_rbs(const ckco_kin* k, const ckco_world* w, const double qa[12], const double qb[12],
                               int ac, int ik, int64_t* nchecks);

@@ -19,6 +19,24 @@ extern "C" int ckco_pcs_is_valid_rbs(const ckco_kin* k, const ckco_world* w, dou
     return 0;
 }
 
+extern "C" int ckco_pcs_is_valid_full(const ckco_kin* k, const ckco_world* w, const double q[12]) {
+    int ik[2];
+    ckco_identify_state_ik(k, q, ik);                               /* PCS.cpp:328 */
+    if (ik[0] < 0 || ik[1] < 0) return 0;
+    double c[12], out[6], s;
+    if (!ckco_project_r1(k, q, ik[0], out)) return 0;               /* :331 */
+    s = 0; for (int i = 0; i < 6; i++) s += pow(q[6 + i] - out[i], 2);
+    if (sqrt(s) > 0.5e-1) return 0;                                 /* :333 */
+    memcpy(c, q, 48); memcpy(c + 6, out, 48);
+    if (ckco_collision_state(w, c, 1, NULL, NULL)) return 0;        /* :335 */
+    if (!ckco_project_r2(k, q + 6, ik[1], out)) return 0;           /* :342 */
+    s = 0; for (int i = 0; i < 6; i++) s += pow(q[i] - out[i], 2);
+    if (sqrt(s) > 0.12) return 0;                                   /* :344 */
+    memcpy(c, out, 48); memcpy(c + 6, q + 6, 48);
+    if (ckco_collision_state(w, c, 1, NULL, NULL)) return 0;        /* :346 */
+    return 1;
+}
+
 static double norm12(const double* a, const double* b) {          /* normDistanceDuo PCS.cpp:513-518 */
     double sum = 0;
     for (int i = 0; i < 6; i++) sum += pow(a[i] - b[i], 2) + pow(a[i + 6] - b[i + 6], 2);

@@ -183,6 +183,10 @@ class Oracle:
             return ok, valid, qo, (st.bv_tests, st.tri_tests, st.pairs_hit)
         return ok, valid, qo
 
+    def pcs_is_valid_full(self, q):
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, 12)
+        return np.array([self.L.ckco_pcs_is_valid_full(C.byref(self.kin), self._w, _p(r)) for r in q], np.uint8)
+
     def pcs_check_motion_rbs(self, qa, qb, ac, ik):
         qa = np.ascontiguousarray(qa, np.float64).reshape(-1, 12); qb = np.ascontiguousarray(qb, np.float64).reshape(-1, 12); n = len(qa)
         ac = np.broadcast_to(np.asarray(ac, np.int8), (n,)); ik = np.broadcast_to(np.asarray(ik, np.int8), (n,))

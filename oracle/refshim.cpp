@@ -36,7 +36,7 @@ typedef std::vector<double> State;
 typedef std::vector<std::vector<double> > Matrix;
 
 enum { OP_PCS_PROJECT = 1, OP_COLLIDE = 2, OP_PCS_VALIDATE = 3, OP_RBS = 4, OP_TRIDIST = 5, OP_PAIR_COUNTERS = 6,
-       OP_IDENTIFY_IK = 7, OP_MIN_DISTANCE = 8, OP_FK = 9, OP_IK = 10, OP_SPCS_SEEDED = 11 };
+       OP_IDENTIFY_IK = 7, OP_MIN_DISTANCE = 8, OP_FK = 9, OP_IK = 10, OP_SPCS_SEEDED = 11, OP_ISVALID_FULL = 12 };
 
 /* ---------------- symbol resolution from the executable's .symtab ---------------- */
 static const char* g_map; static size_t g_map_len;
@@ -72,10 +72,12 @@ typedef int (*mbegin_t)(void*, int);
 typedef int (*madd_t)(void*, const double*, const double*, const double*, int);
 typedef int (*mend_t)(void*);
 typedef int (*tol_t)(void*, double (*)[3], double*, void*, double (*)[3], double*, void*, double, int);
+typedef bool (*isvalid_t)(void*, const void*);
 typedef int (*dist_t)(void*, double (*)[3], double*, void*, double (*)[3], double*, void*, double, double, int);
 
 static ctor_t f_ctor; static ikR_t f_r1, f_r2; static getq_t f_getq1, f_getq2; static coll_t f_coll; static vrbs_t f_vrbs;
 static rbs_t f_rbs; static ident_t f_ident; static tridist_t f_tridist; static fk_t f_fk; static getT_t f_getT1, f_getT2; static ik_t f_ik;
+static isvalid_t f_isvalid;
 static mctor_t f_mctor; static mbegin_t f_mbegin; static madd_t f_madd; static mend_t f_mend; static tol_t f_tol; static dist_t f_dist;
 
 static void resolve_all() {
@@ -93,6 +95,7 @@ static void resolve_all() {
     f_getT1 = (getT_t)sym("_ZN10two_robots18get_FK_solution_T1Ev");
     f_getT2 = (getT_t)sym("_ZN10two_robots18get_FK_solution_T2Ev");
     f_ik = (ik_t)sym("_ZN10two_robots11IKsolve_robESt6vectorIS0_IdSaIdEESaIS2_EEii");
+    f_isvalid = (isvalid_t)sym("_ZN20StateValidityChecker7isValidEPKN4ompl4base5StateE");
     f_mctor = (mctor_t)sym("_ZN9PQP_ModelC1Ev");
     f_mbegin = (mbegin_t)sym("_ZN9PQP_Model10BeginModelEi");
     f_madd = (madd_t)sym("_ZN9PQP_Model6AddTriEPKdS1_S1_i");
@@ -254,6 +257,19 @@ static int shim_main(int, char**, char**) {
             f_ident(&res, g_self, &q1, &q2, &ik0); r[2 * i] = (int32_t)res[0]; r[2 * i + 1] = (int32_t)res[1];
         }
         secs = now() - t0; put(out, r.data(), r.size());
+    } else if (op == OP_ISVALID_FULL) {
+        /* isValid(const ob::State*): a RealVectorStateSpace::StateType is { vptr, double* values } (offset 8, read from the
+         * binary's own retrieveStateVector); the function never makes a virtual call on the state */
+        const double* q = (const double*)pay; std::vector<uint8_t> r(n);
+        struct fake_state { void* vptr; double* values; } fs = { nullptr, nullptr };
+        double t0 = now();
+        for (int i = 0; i < n; i++) {
+            double v[12]; memcpy(v, q + 12 * i, sizeof(v)); fs.values = v;
+            fflush(stdout); int so2 = dup(1); int dn2 = open("/dev/null", O_WRONLY); dup2(dn2, 1);      /* it prints on one failure path */
+            r[i] = f_isvalid(g_self, &fs);
+            fflush(stdout); dup2(so2, 1); close(dn2); close(so2);
+        }
+        secs = now() - t0; put(out, r.data(), n);
     } else if (op == OP_FK) {
         /* payload: n*6 joints, n int8 robot (1/2) -> n*16 */
         const double* q = (const double*)pay; const int8_t* rb = (const int8_t*)(pay + (size_t)n * 48); std::vector<double> T((size_t)n * 16);

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(_HERE, "_ref")
 OPS = dict(pcs_project=1, collide=2, pcs_validate=3, rbs=4, tridist=5, pair_counters=6, identify_ik=7, min_distance=8,
-           fk=9, ik=10, spcs_seeded=11)
+           fk=9, ik=10, spcs_seeded=11, isvalid_full=12)
 MAX_PAIRS = 116
 
 
@@ -106,6 +106,12 @@ def identify_ik(q, env=1):
     q = _q(q); n = len(q)
     d, s = _run("identify_ik", n, env, 0, q.tobytes())
     return np.frombuffer(d, np.int32).reshape(n, 2).copy()
+
+
+def isvalid_full(q, env=1):
+    q = _q(q); n = len(q)
+    d, s = _run("isvalid_full", n, env, 0, q.tobytes())
+    return np.frombuffer(d[:n], np.uint8).copy()
 
 
 def fk(q6, robot, env=1):

@@ -50,6 +50,10 @@ def test_pcs_dropin_class(tmp_path, oracle, gold):
     assert (res[m][:, 2:4] == id_o).all()
     _, valid_o, _ = oracle.pcs_validate(qq, 0, kk)
     assert (res[:, 4] == valid_o).all()
+    # isValid(const ob::State*) on the projected configuration and on one opened by 4 mrad in q2[1]
+    full = q_o[m].copy(); opened = q_o[m].copy(); opened[:, 7] += 0.004
+    assert (res[m][:, 12] == oracle.pcs_is_valid_full(full)).all() and res[m][:, 12].sum() >= n // 2
+    assert (res[m][:, 13] == oracle.pcs_is_valid_full(opened)).all()
     # RBS on rows whose two endpoints are valid
     _, vb, qbo = oracle.pcs_validate(qb, 0, kk)
     both = (valid_o == 1) & (vb == 1)

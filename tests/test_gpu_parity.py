@@ -78,6 +78,24 @@ def test_million_sample_mask_vs_reference(ck, gold):
     assert valid.sum() == 11514
 
 
+def test_is_valid_full(ck, oracle, gold):
+    """ckc_pcs_is_valid == the binary's isValid(const ob::State*) on the golden set, == the oracle on 20000 random near-closed samples"""
+    g = gold("isvalid_full.npz")
+    ident = (g["ik"] >= 0).all(1)
+    v = ck.pcs_is_valid(g["q"])
+    assert (v[ident] == g["valid"][ident]).all() and (v[~ident] == 0).all()
+    from abb_dualarm_planning_b200 import sampling
+    q, ik = sampling.sample_pcs(77, 0, 400000)
+    ok, qo = ck.pcs_project(q, 0, ik)
+    qc = qo[ok == 1][:20000].copy()
+    rng = np.random.default_rng(5)
+    qc[5000:] += rng.normal(size=qc[5000:].shape) * 0.01
+    v = ck.pcs_is_valid(qc)
+    vo = oracle.pcs_is_valid_full(qc)
+    assert (v == vo).all() and 500 < v.sum() < len(qc)
+    assert ck.pcs_is_valid(np.zeros((0, 12))).shape == (0,)
+
+
 def test_identify_ik_and_limits(ck, oracle, gold):
     g = gold("identify_ik.npz")
     assert (ck.identify_ik(g["q"]) == g["ik"]).all()

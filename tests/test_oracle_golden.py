@@ -110,6 +110,15 @@ def test_reference_path_fixture(oracle, gold):
         assert np.abs(T[:3, :3] - np.eye(3)).max() < 2e-3
 
 
+def test_is_valid_full_vs_binary(oracle, gold):
+    """isValid(const ob::State*) PCS.cpp:323-357 run through the genuine binary; unidentified branches (-1) are UB there"""
+    g = gold("isvalid_full.npz")
+    ident = (g["ik"] >= 0).all(1)
+    v = oracle.pcs_is_valid_full(g["q"])
+    assert (v[ident] == g["valid"][ident]).all() and ident.sum() > 500 and g["valid"].sum() > 300
+    assert (v[~ident] == 0).all()
+
+
 def test_identify_state_ik_vs_binary(oracle, gold):
     g = gold("identify_ik.npz")
     assert (oracle.identify_state_ik(g["q"]) == g["ik"]).all()

@@ -108,6 +108,15 @@ def main():
     ikid = refshim.identify_ik(qc)
     np.savez_compressed(os.path.join(GOLD, "identify_ik.npz"), q=qc, ik=ikid)
 
+    # 6c. isValid(const ob::State*) (PCS.cpp:323-357) through the binary on closed, perturbed and valid configurations
+    gi, gr = np.load(os.path.join(GOLD, "identify_ik.npz")), np.load(os.path.join(GOLD, "rbs.npz"))
+    r3 = np.random.default_rng(3)
+    qv = np.concatenate([gi["q"], gr["qa"][:200], gr["qa"][:200] + r3.normal(size=(200, 12)) * 0.01, gr["qb"][:200] + r3.normal(size=(200, 12)) * 0.04])
+    vfull = refshim.isvalid_full(qv)
+    idv = refshim.identify_ik(qv)
+    np.savez_compressed(os.path.join(GOLD, "isvalid_full.npz"), q=qv, valid=vfull, ik=idv)
+    print("isValid(state): %d configs, %d identified, %d valid" % (len(qv), (idv >= 0).all(1).sum(), vfull.sum()))
+
     # 6b. env 2 (cones, D = 1200, L = 500, "T7z > 800" rule): masks of 60000 S-PCS samples from the genuine binary
     O2 = lib.Oracle(2)
     q2, ik2 = O2.sample_pcs(4, 0, 60000)
