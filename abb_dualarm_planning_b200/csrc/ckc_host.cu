@@ -39,7 +39,8 @@ struct dev_buf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-#define CKC_NUM_LANES 4
+#define CKC_NUM_LANES 16          /* lanes that exist */
+#define CKC_FAN_LANES 4           /* lanes the device-resident entry points fan out over */
 struct ckc_lane {
     cudaStream_t st = nullptr;
     cudaStream_t st_hi = nullptr;       /* high-priority stream for the collision stage of this lane's chunk */
@@ -70,7 +71,10 @@ struct ckc_ctx {
     /* per-chunk work buffers: CKC_NUM_LANES independent sets, each with its own stream, so that the host entry points
      * can overlap the H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 */
     ckc_lane lanes[CKC_NUM_LANES];
-    int64_t pipe_chunk = 1 << 17;       /* samples per pipelined chunk of the host entry points */
+    int64_t pipe_chunk = 1 << 18;       /* largest pipelined chunk of the host entry points (samples); a call is cut into ~4 chunks
+                                           of 2^16 .. pipe_chunk samples (measured: 2^18 beats 2^17 by 10 % on S-GD, 2^16 loses 20 %) */
+    int host_lanes = 4;                 /* lanes the host pipeline cycles through: a 1e6-sample call is 4 chunks, one per lane, so all
+                                           H2D copies are in flight from the start; 8 lanes measured equal or slower (CKC_HOST_LANES) */
     bool overlap = true;                /* device-resident entry points fan out over the lanes */
     cudaEvent_t ev_fork = nullptr;
     int64_t launches = 0;
@@ -454,6 +458,8 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
     if (ch) ctx->overlap = atoi(ch) != 0;
     ch = getenv("CKC_PIPE_CHUNK");
     if (ch && atoll(ch) >= 1024) ctx->pipe_chunk = atoll(ch);
+    const char* hl = getenv("CKC_HOST_LANES");
+    if (hl && atoi(hl) >= 1 && atoi(hl) <= CKC_NUM_LANES) ctx->host_lanes = atoi(hl);
     *out = ctx;
     return CKC_OK;
 }
@@ -570,7 +576,7 @@ static int run_gd_chunk(ckc_ctx* ctx, ckc_lane& L, int64_t n, const double* d_q,
 
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* host entry points of the projection flavours: software pipeline over the lanes                                     */
-/*   chunk k runs entirely on lane k % CKC_NUM_LANES (H2D -> kernels -> D2H in stream order); the lanes' streams overlap */
+/*   chunk k runs entirely on lane k % host_lanes (H2D -> kernels -> D2H in stream order); the lanes' streams overlap */
 /*   each other, so copies in both directions and kernels of neighbouring chunks run concurrently (pinned host memory). */
 /* ---------------------------------------------------------------------------------------------------------------- */
 struct compact_out { int64_t* n_valid; int32_t* idx; double* q_valid; int64_t cap; };
@@ -579,7 +585,7 @@ static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, co
                         uint8_t* ok, uint8_t* conv, int32_t* iters, uint8_t* valid, bool collide, const compact_out* co = nullptr) {
     if (!ctx || n < 0 || n > 0x7fffffff || (n > 0 && (!q || (flavour == 0 && !ik)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    const int64_t C = n <= ctx->pipe_chunk ? std::max<int64_t>(n, 1) : ctx->pipe_chunk;
+    const int64_t C = std::max<int64_t>(1, std::min<int64_t>(ctx->pipe_chunk, std::max<int64_t>(std::min<int64_t>(n, 1 << 16), (n + 3) / 4)));
     /* compact mode: each chunk appends its valid (index, configuration) pairs to its own device region; a fixed-size prefix
      * (5 % of the chunk + 1024 entries) of every region is copied back inside the pipeline, the rare overflow afterwards */
     const int64_t nchunks = n > 0 ? (n + C - 1) / C : 0;
@@ -603,7 +609,7 @@ static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, co
     int k = 0;
     for (int64_t off = 0; off < n; off += C, k++) {
         const int64_t c = std::min(C, n - off);
-        ckc_lane& L = ctx->lanes[k % CKC_NUM_LANES];
+        ckc_lane& L = ctx->lanes[k % ctx->host_lanes];
         cudaStream_t st = L.st;
         CU(L.qin.reserve((size_t)C * 96)); CU(L.qout.reserve((size_t)C * 96)); CU(L.ok.reserve((size_t)C)); CU(L.valid.reserve((size_t)C));
         CU(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
@@ -693,7 +699,7 @@ extern "C" int ckc_gd_validate(ckc_ctx* ctx, int64_t n, const double* q, double*
 
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* device-resident entry points: fork / join over the lanes                                                           */
-/*   the batch is cut into up to CKC_NUM_LANES chunks that run on the lanes' own streams (forked from / joined to the   */
+/*   the batch is cut into up to CKC_FAN_LANES chunks that run on the lanes' own streams (forked from / joined to the   */
 /*   caller's stream with events), so the latency-bound collision kernel of one chunk overlaps the FP64-bound projection */
 /*   kernel of the next.  CKC_OVERLAP=0 (ckc_set_overlap) runs everything in order on the caller's stream instead.       */
 /* ---------------------------------------------------------------------------------------------------------------- */
@@ -707,15 +713,15 @@ static int dev_fanout(ckc_ctx* ctx, cudaStream_t user, int64_t n, bool fan, F bo
         }
         return CKC_OK;
     }
-    int64_t c = (n + CKC_NUM_LANES - 1) / CKC_NUM_LANES;
+    int64_t c = (n + CKC_FAN_LANES - 1) / CKC_FAN_LANES;
     c = std::max<int64_t>(c, 1 << 16);
     c = std::min<int64_t>(c, ctx->chunk);
     CU(cudaEventRecord(ctx->ev_fork, user));
     int used = 0, k = 0;
     for (int64_t off = 0; off < n; off += c, k++) {
-        const int li = k % CKC_NUM_LANES;
+        const int li = k % CKC_FAN_LANES;
         ckc_lane& L = ctx->lanes[li];
-        if (k < CKC_NUM_LANES) { CU(cudaStreamWaitEvent(L.st, ctx->ev_fork, 0)); used = k + 1; }
+        if (k < CKC_FAN_LANES) { CU(cudaStreamWaitEvent(L.st, ctx->ev_fork, 0)); used = k + 1; }
         int rc = body(L, off, std::min(c, n - off), L.st);
         if (rc) return rc;
     }

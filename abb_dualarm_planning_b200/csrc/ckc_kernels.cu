@@ -14,6 +14,7 @@
  *   k_rx_check, k_limits, k_identify_ik, k_compact_valid, k_update_pair_order, k_fma_peak, k_transpose: helpers.
  */
 #include "ckc_device.cuh"
+#include <cstdlib>
 
 using namespace ckc;
 
@@ -663,8 +664,11 @@ void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gd_project<false>, CKC_GD_BLOCK, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 2;
     }
     int64_t blocks = (int64_t)num_sms * blocks_per_sm;
-    /* at least ~6 samples per lane so that the lane-level work stealing can balance the iteration counts */
-    const int64_t needed = (n + 6 * CKC_GD_BLOCK - 1) / (6 * CKC_GD_BLOCK);
+    /* at least ~2 samples per lane so that the lane-level work stealing can balance the iteration counts (measured on
+     * 2^16..2^18-sample chunks: 1-3 equal, 6 slower by 5 %; a 1e6-sample launch is capped by the resident grid anyway) */
+    static int spl = 0;
+    if (spl == 0) { const char* e = getenv("CKC_GD_SPL"); spl = e ? atoi(e) : 2; if (spl < 1) spl = 1; }
+    const int64_t needed = (n + spl * CKC_GD_BLOCK - 1) / (spl * CKC_GD_BLOCK);
     if (blocks > needed) blocks = needed;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
     if (seeded) k_gd_project<true><<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, q_out, lo, state_scratch, work_counter);
