@@ -321,15 +321,16 @@ def run_native(args):
             flop_launch = flop_cfg * cfgs
         dur = kms / max(kl, 1) * 1e-3
         achieved = flop_launch / dur / 1e12 if dur > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None
         try:        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture
             tr = json.load(open(os.path.join(REPO, "profiles", "r1_traffic.json")))[kern]
-            traffic = {"bytes_per_launch": tr["traffic"], "source": "profiles/" + tr["capture"].replace(".ncu-rep", "") + " (ncu --set full)", "note": tr["note"]}
+            traffic = tr["traffic"]         # bytes per launch
+            traffic_src = "dram bytes per launch from profiles/" + tr["capture"].replace(".ncu-rep", "") + " (ncu --set full); " + tr["note"]
         except Exception:
             pass
         share = {k: round(v["ms"] / max(ms_serial, 1e-9), 4) for k, v in stages.items()}
         out["roofline"] = {"bound": "fp64", "kernel": kern, "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
-                           "frac": achieved / peak64 if peak64 else None, "traffic": traffic,
+                           "frac": achieved / peak64 if peak64 else None, "traffic": traffic, "traffic_source": traffic_src,
                            "peak_source": "FP64 FMA-chain peak measured live by ckc_measure_fma_peak (MEASURED_PEAKS.json has HBM/bf16 only; FP32 FMA peak %.1f TFLOP/s)" % peak32,
                            "work_model": "algorithmic flop of the reference path (SURVEY 8d): GD 2600 flop x measured Newton iterations; collision 300 flop x (116 + n_bv) + 1000 flop x n_tri with PQP counters of tests/golden/work_model.json",
                            "kernel_ms_per_launch": kms / max(kl, 1), "stage_share_of_step": share,
