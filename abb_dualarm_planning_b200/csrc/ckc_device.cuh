@@ -534,10 +534,19 @@ __constant__ double c_sc[16] = {
     4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,         /* 9..14: C1..C6 */
     -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11, 0.0 };
 
-__device__ __noinline__ void sincos_lib(double x, double* sn, double* cs) { sincos(x, sn, cs); }     /* cold: |x| >= 1e4 */
+/* the same chain packed for the two rolled walks: joint j = segment j + 1; its tip is (x, 0, z) in every segment (no y
+ * component anywhere in kdl_class.cpp:32-45), so the position update needs two FMAs per coordinate */
+struct gd_joint { double tx, tz; int axis, pad; };
+__constant__ gd_joint c_gd_joint[2][12] = {
+    { { 0, 124, 2, 0 }, { 0, 270, 1, 0 }, { 149.6, 70, 1, 0 }, { 152.4, 0, 0, 0 }, { 66, 0, 1, 0 }, { 2 * 66 + 300.0, 0, 0, 0 },
+      { 66, 0, 0, 0 }, { 152.4, 0, 1, 0 }, { 149.6, -70, 0, 0 }, { 0, -270, 1, 0 }, { 0, -124, 1, 0 }, { 0, -166, 2, 0 } },
+    { { 0, 124, 2, 0 }, { 0, 270, 1, 0 }, { 149.6, 70, 1, 0 }, { 152.4, 0, 0, 0 }, { 66, 0, 1, 0 }, { 2 * 66 + 500.0, 0, 0, 0 },
+      { 66, 0, 0, 0 }, { 152.4, 0, 1, 0 }, { 149.6, -70, 0, 0 }, { 0, -270, 1, 0 }, { 0, -124, 1, 0 }, { 0, -166, 2, 0 } } };
+
+__device__ __noinline__ double2 sincos_lib(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }     /* cold: |x| >= 1e4 */
 
 __device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
-    if (!(fabs(x) < 1.0e4)) { sincos_lib(x, sn, cs); return; }
+    if (!(fabs(x) < 1.0e4)) { const double2 r = sincos_lib(x); *sn = r.x; *cs = r.y; return; }
     const double kd = rint(x * c_sc[0]);
     const int k = (int)kd;
     double r = fma(-kd, c_sc[1], x);
@@ -586,6 +595,29 @@ __device__ __noinline__ void gd_singular_step(const ckc_kin_dev& k, const gd_ref
 __device__ __forceinline__ void rot_by_axis(int ax, double* R, double c, double s) {     /* ax is warp-uniform */
     if (ax == 0) post_rot_x(R, c, s); else if (ax == 1) post_rot_y(R, c, s); else post_rot_z(R, c, s);
 }
+template <int AX> __device__ __forceinline__ void post_rot(double* R, double c, double s) {
+    if (AX == 0) post_rot_x(R, c, s); else if (AX == 1) post_rot_y(R, c, s); else post_rot_z(R, c, s);
+}
+/* walk 1, joint about the compile-time axis AX: column of J0 (the axis is column AX of R, which the joint's own rotation
+ * leaves unchanged), rank-1 update of A0 = J0 J0^T, then the joint rotation */
+template <int AX> __device__ __forceinline__ void gd_walk1_joint(double* R, const double* p, double (*A)[6], double c, double s) {
+    double col[6];
+    col[3] = R[AX]; col[4] = R[3 + AX]; col[5] = R[6 + AX];
+    col[0] = p[1] * col[5] - p[2] * col[4];
+    col[1] = p[2] * col[3] - p[0] * col[5];
+    col[2] = p[0] * col[4] - p[1] * col[3];
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) A[a][b] += col[a] * col[b];
+    post_rot<AX>(R, c, s);
+}
+/* walk 2: dq = col0 . z = a . (z_w + z_v x o), w = z_w + z_v x o precomputed by the caller */
+template <int AX> __device__ __forceinline__ double gd_walk2_joint(double* R, const double* w, double c, double s, bool rotate) {
+    const double dq = R[AX] * w[0] + R[3 + AX] * w[1] + R[6 + AX] * w[2];
+    if (rotate) post_rot<AX>(R, c, s);
+    return dq;
+}
 
 /* one ChainIkSolverPos_NR iteration; returns Equal(delta_twist, 0, 1e-5) evaluated on the twist BEFORE the update */
 __device__ __forceinline__ bool gd_iterate(const ckc_kin_dev& k, const gd_ref& s) {
@@ -598,28 +630,20 @@ __device__ __forceinline__ bool gd_iterate(const ckc_kin_dev& k, const gd_ref& s
 #pragma unroll
         for (int j = 0; j <= i; j++) A[i][j] = 0;
     /* ---- walk 1 ---- */
+    const gd_joint* jt = c_gd_joint[e];
 #pragma unroll 1
     for (int j = 0; j < 12; j++) {
-        const int ax = c_kdl_axis[j + 1];
-        double col[6];
-        if (ax == 0) { col[3] = R[0]; col[4] = R[3]; col[5] = R[6]; }
-        else if (ax == 1) { col[3] = R[1]; col[4] = R[4]; col[5] = R[7]; }
-        else { col[3] = R[2]; col[4] = R[5]; col[5] = R[8]; }
-        col[0] = p[1] * col[5] - p[2] * col[4];
-        col[1] = p[2] * col[3] - p[0] * col[5];
-        col[2] = p[0] * col[4] - p[1] * col[3];
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int b = 0; b <= a; b++) A[a][b] += col[a] * col[b];
         double sj, cj;
         sincos_fast(s.qc(j), &sj, &cj);
         s.cs(j) = cj; s.sn(j) = sj;
-        rot_by_axis(ax, R, cj, sj);
-        const double tx = c_kdl_tip[e][j + 1][0], ty = c_kdl_tip[e][j + 1][1], tz = c_kdl_tip[e][j + 1][2];
-        p[0] += R[0] * tx + R[1] * ty + R[2] * tz;
-        p[1] += R[3] * tx + R[4] * ty + R[5] * tz;
-        p[2] += R[6] * tx + R[7] * ty + R[8] * tz;
+        const int ax = jt[j].axis;                     /* warp-uniform: one three-way branch per joint */
+        if (ax == 0) gd_walk1_joint<0>(R, p, A, cj, sj);
+        else if (ax == 1) gd_walk1_joint<1>(R, p, A, cj, sj);
+        else gd_walk1_joint<2>(R, p, A, cj, sj);
+        const double tx = jt[j].tx, tz = jt[j].tz;
+        p[0] = fma(R[0], tx, fma(R[2], tz, p[0]));
+        p[1] = fma(R[3], tx, fma(R[5], tz, p[1]));
+        p[2] = fma(R[6], tx, fma(R[8], tz, p[2]));
     }
     /* ---- delta_twist = diff(f, target): vel = (D,0,0) - p ; rot = R * GetRot(R^T) ---- */
     double tw[6];
@@ -695,21 +719,21 @@ __device__ __forceinline__ bool gd_iterate(const ckc_kin_dev& k, const gd_ref& s
     p[0] = c_kdl_tip[e][0][0]; p[1] = c_kdl_tip[e][0][1]; p[2] = c_kdl_tip[e][0][2];
 #pragma unroll 1
     for (int j = 0; j < 12; j++) {
-        const int ax = c_kdl_axis[j + 1];
-        double a0, a1, a2;
-        if (ax == 0) { a0 = R[0]; a1 = R[3]; a2 = R[6]; }
-        else if (ax == 1) { a0 = R[1]; a1 = R[4]; a2 = R[7]; }
-        else { a0 = R[2]; a1 = R[5]; a2 = R[8]; }
-        const double dq = (p[1] * a2 - p[2] * a1) * z[0] + (p[2] * a0 - p[0] * a2) * z[1] + (p[0] * a1 - p[1] * a0) * z[2] +
-                          a0 * z[3] + a1 * z[4] + a2 * z[5];
+        double w[3];
+        w[0] = fma(z[1], p[2], fma(-z[2], p[1], z[3]));
+        w[1] = fma(z[2], p[0], fma(-z[0], p[2], z[4]));
+        w[2] = fma(z[0], p[1], fma(-z[1], p[0], z[5]));
+        const int ax = jt[j].axis;
+        const double cj = s.cs(j), sj = s.sn(j);
+        double dq;
+        if (ax == 0) dq = gd_walk2_joint<0>(R, w, cj, sj, j < 11);
+        else if (ax == 1) dq = gd_walk2_joint<1>(R, w, cj, sj, j < 11);
+        else dq = gd_walk2_joint<2>(R, w, cj, sj, j < 11);
         s.qc(j) += dq;
-        if (j < 11) {
-            rot_by_axis(ax, R, s.cs(j), s.sn(j));
-            const double tx = c_kdl_tip[e][j + 1][0], ty = c_kdl_tip[e][j + 1][1], tz = c_kdl_tip[e][j + 1][2];
-            p[0] += R[0] * tx + R[1] * ty + R[2] * tz;
-            p[1] += R[3] * tx + R[4] * ty + R[5] * tz;
-            p[2] += R[6] * tx + R[7] * ty + R[8] * tz;
-        }
+        const double tx = jt[j].tx, tz = jt[j].tz;
+        p[0] = fma(R[0], tx, fma(R[2], tz, p[0]));
+        p[1] = fma(R[3], tx, fma(R[5], tz, p[1]));
+        p[2] = fma(R[6], tx, fma(R[8], tz, p[2]));
     }
     return eq;
 }

@@ -149,6 +149,8 @@ struct collide_args {
     int32_t* ovf_count;
     uint32_t* big_stack;         /* overflow path: per-warp global stacks */
     ckc_counters_dev* ctr;
+    int count_rounds;            /* debug: the bv / tri counters count ROUNDS (warp steps) instead of tests */
+    int wide_cnt;                /* rounds with at most this many tasks split BOTH boxes of a task (4 children) */
 };
 
 __device__ __forceinline__ const double* frame64(const ckc_world_dev& w, const double* cfg_frames, int f) {
@@ -250,7 +252,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                 }
                 const double d = tri_dist_coop(act, lane, S0, S1, S2, T0, T1, T2);
                 const bool h = act && (lane - 9 * g) == 0 && d <= w.tol;      /* PQP: closer_than_tolerance iff d <= tolerance */
-                n_tri += take;
+                n_tri += a.count_rounds ? 1 : take;
                 ntri -= take;
                 if (per_pair) {
                     if (h) a.pair_flags[sample * CKC_MAX_PAIRS + (t >> 20)] = 1;
@@ -268,7 +270,8 @@ k_collide(const ckc_world_dev w, const collide_args a) {
             /* ---- box tests, one task per lane ---- */
             const int cnt = top < 32 ? top : 32;
             const bool active = lane < cnt;
-            bool expand = false, leafpair = false, likely = false;
+            bool expand = false, expand4 = false, leafpair = false, likely = false;
+            const bool wide = cnt <= a.wide_cnt;       /* few tasks in flight: idle lanes are free, halve the number of descent rounds */
             uint32_t c0 = 0, c1 = 0, tt = 0;
             if (active) {
                 const uint32_t t = stack[top - 1 - lane];
@@ -286,6 +289,10 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                             leafpair = true; tt = ((uint32_t)p << 20) | ((uint32_t)(~A.child) << 10) | (uint32_t)(~B.child);
                             likely = gap6 < 0.25f * w.cull_tol;       /* the two triangles' boxes are within ~2 mm along every face axis */
                         }
+                        else if (wide && A.child >= 0 && B.child >= 0) {
+                            expand4 = true;
+                            c0 = ((uint32_t)p << 22) | ((uint32_t)A.child << 11) | (uint32_t)B.child;
+                        }
                         else {
                             expand = true;
                             if (B.child < 0 || (A.child >= 0 && A.size2 > B.size2)) {       /* descend the larger box */
@@ -299,17 +306,20 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                     }
                 }
             }
-            n_bv += cnt;
+            n_bv += a.count_rounds ? 1 : cnt;
             top -= cnt;
             __syncwarp();
             if (!per_pair && __any_sync(0xffffffffu, likely)) hot = true;
             const unsigned mt = __ballot_sync(0xffffffffu, leafpair);
             const unsigned me = __ballot_sync(0xffffffffu, expand);
+            const unsigned m4 = __ballot_sync(0xffffffffu, expand4);
             if (leafpair) triq[ntri + __popc(mt & lt_mask)] = tt;
             ntri += __popc(mt);
-            const int npush = 2 * __popc(me);
+            const int npush = 2 * __popc(me) + 4 * __popc(m4);
             if (top + npush > cap) { overflow = true; break; }
-            if (expand) { const int pos = top + 2 * __popc(me & lt_mask); stack[pos] = c1; stack[pos + 1] = c0; }
+            const int pos = top + 2 * __popc(me & lt_mask) + 4 * __popc(m4 & lt_mask);
+            if (expand) { stack[pos] = c1; stack[pos + 1] = c0; }
+            if (expand4) { stack[pos] = c0 + (1u << 11) + 1u; stack[pos + 1] = c0 + (1u << 11); stack[pos + 2] = c0 + 1u; stack[pos + 3] = c0; }
             top += npush;
             __syncwarp();
         }
@@ -370,6 +380,12 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     collide_args a;
     a.frames = frames; a.list = list; a.d_m = d_m; a.m_max = m_max; a.hit_out = hit_out; a.valid_out = valid_out; a.pair_flags = pair_flags;
     a.work_counter = work_counter; a.ovf_list = ovf_list; a.ovf_count = ovf_count; a.big_stack = big_stack; a.ctr = ctr;
+    static int wide_cnt = -1;
+    if (wide_cnt < 0) { const char* e = getenv("CKC_WIDE_CNT"); wide_cnt = e ? atoi(e) : 16; }
+    a.wide_cnt = wide_cnt;
+    static int count_rounds = -1;
+    if (count_rounds < 0) { const char* e = getenv("CKC_COUNT_ROUNDS"); count_rounds = e ? atoi(e) : 0; }
+    a.count_rounds = count_rounds;
     /* work_counter[0] main pass, [1] overflow pass; the overflow count sits right behind them in the lanes' scratch block */
     if (ovf_count == work_counter + 2) cudaMemsetAsync(work_counter, 0, 3 * sizeof(int32_t), st);
     else { cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st); cudaMemsetAsync(ovf_count, 0, sizeof(int32_t), st); }
