@@ -73,6 +73,7 @@ struct ckc_ctx {
     ckc_lane lanes[CKC_NUM_LANES];
     int64_t pipe_chunk = 1 << 18;       /* largest pipelined chunk of the host entry points (samples); a call is cut into ~4 chunks
                                            of 2^16 .. pipe_chunk samples (measured: 2^18 beats 2^17 by 10 % on S-GD, 2^16 loses 20 %) */
+    bool gd_fan = false;                /* fan GD batches out over the lanes on the _dev paths (CKC_GD_FAN) */
     int host_lanes = 4;                 /* lanes the host pipeline cycles through: a 1e6-sample call is 4 chunks, one per lane, so all
                                            H2D copies are in flight from the start; 8 lanes measured equal or slower (CKC_HOST_LANES) */
     bool overlap = true;                /* device-resident entry points fan out over the lanes */
@@ -458,6 +459,8 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
     if (ch) ctx->overlap = atoi(ch) != 0;
     ch = getenv("CKC_PIPE_CHUNK");
     if (ch && atoll(ch) >= 1024) ctx->pipe_chunk = atoll(ch);
+    const char* gf = getenv("CKC_GD_FAN");
+    if (gf) ctx->gd_fan = atoi(gf) != 0;
     const char* hl = getenv("CKC_HOST_LANES");
     if (hl && atoi(hl) >= 1 && atoi(hl) <= CKC_NUM_LANES) ctx->host_lanes = atoi(hl);
     *out = ctx;
@@ -766,7 +769,7 @@ extern "C" int ckc_spcs_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_
 extern "C" int ckc_gd_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, double* d_q_out, uint8_t* d_valid, void* stream) {
     if (!ctx || n < 0 || !d_q || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    return dev_fanout(ctx, (cudaStream_t)stream, n, false /* the persistent Newton kernel fills the GPU; chunk tails cost more than the overlap gains (measured) */, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
+    return dev_fanout(ctx, (cudaStream_t)stream, n, ctx->gd_fan /* off by default: the persistent Newton kernel fills the GPU; chunk tails cost more than the overlap gains (measured) */, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
         double* qo; ckc_layout lo;
         if (d_q_out) { qo = d_q_out + off; lo = soa(n); }
         else { CU(L.qout.reserve((size_t)c * 96)); qo = L.qout.as<double>(); lo = soa(c); }
@@ -777,7 +780,7 @@ extern "C" int ckc_gd_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, d
 extern "C" int ckc_sgd_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out, uint8_t* d_ok, uint8_t* d_valid, void* stream) {
     if (!ctx || n < 0 || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    return dev_fanout(ctx, (cudaStream_t)stream, n, false /* the persistent Newton kernel fills the GPU; chunk tails cost more than the overlap gains (measured) */, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
+    return dev_fanout(ctx, (cudaStream_t)stream, n, ctx->gd_fan /* off by default: the persistent Newton kernel fills the GPU; chunk tails cost more than the overlap gains (measured) */, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
         double* qo; ckc_layout l;
         if (d_q_out) { qo = d_q_out + off; l = soa(n); }
         else { CU(L.qout.reserve((size_t)c * 96)); qo = L.qout.as<double>(); l = soa(c); }

@@ -789,7 +789,24 @@ k_rbs_push(const ckc_rbs_dev r, const int32_t* __restrict__ d_ncand, const uint8
         s = r.cand_seg[c]; node = r.cand_node[c];
         const int e = r.seg_edge[s];
         if (hit[node]) r.edge_ok[e] = 0;
-        else push = true;      /* edge_ok may still be cleared by a sibling; stale segments are dropped at the next expand */
+        else {
+            push = true;       /* edge_ok may still be cleared by a sibling; stale segments are dropped at the next expand */
+            /* stationary recursion: once the active joints of a and b coincide to the last bit (a projection discontinuity
+             * between them, ~53 halvings in), the projected midpoint IS one of the end points, so one child is the segment
+             * itself and the other has length 0 -- the reference keeps recursing on the identical segment until
+             * recursion_depth > RBS_max_depth and returns false (PCS.cpp:495).  Same answer, without the remaining levels. */
+            const long long* pm = reinterpret_cast<const long long*>(r.nodes + 12 * (int64_t)node);
+            const long long* pa = reinterpret_cast<const long long*>(r.nodes + 12 * (int64_t)r.seg_a[s]);
+            const long long* pb = reinterpret_cast<const long long*>(r.nodes + 12 * (int64_t)r.seg_b[s]);
+            bool eqa = true, eqb = true;
+#pragma unroll
+            for (int j = 0; j < 12; j++) { const long long v = pm[j]; eqa = eqa && (v == pa[j]); eqb = eqb && (v == pb[j]); }
+            if (eqa || eqb) {
+                push = false;
+                r.edge_ok[e] = 0;
+                if (r.nchecks) atomicAdd(&r.nchecks[e], r.max_depth - r.seg_depth[s]);      /* the checks of the skipped levels */
+            }
+        }
     }
     const unsigned mk = __ballot_sync(0xffffffffu, push);
     if (mk) {

@@ -1,0 +1,375 @@
+/*
+ * cbirrt_pcs_batch.cpp -- the caller side of the hot path (BASELINE configs[3]): an ensemble of
+ * independent CBiRRT-PCS planning queries stepped in lock-step, so that every validity question the planners ask in one
+ * step becomes ONE batched call of include/ckc.h.
+ *
+ * The planner is the reference's planners/CBiRRT_PCS.cpp (a constrained RRT-Connect) restated without OMPL: per query
+ * two trees, growTree(mode 1 = extend toward a uniform sample, 100 steps; mode 2 = connect the other tree to the new node,
+ * 500 steps) (:160-305), the solve loop that alternates the trees (:371-486), the projection of every step onto the
+ * closure constraint with the neighbour's IK branch and fall-back to the other active chain (:191-246), identify_state_ik
+ * on the projected state (:251), the RBS local connection with either active chain (:275-279), the duplicate-free path
+ * assembly (:424-460).  Reproduced quirk: activeDistance with active chain 1 measures |q2(target)| (:127-139).
+ * What differs from the reference is only WHEN the questions are asked: the reference asks them one at a time, this
+ * driver collects the pending question of every live query and asks them together:
+ *     step A  ckc_pcs_validate            project with (active chain, neighbour's branch) + joint limits + collision
+ *     step A' ckc_pcs_validate            the fall-back projection with the other chain for the samples A could not close
+ *     step B  ckc_identify_ik             both IK branches of the projected states
+ *     step C  ckc_pcs_check_motion_rbs    local connection with active chain 0 where the branches agree
+ *     step C' ckc_pcs_check_motion_rbs    ... with active chain 1 for the edges C rejected / could not try
+ * One query (n = 1) therefore behaves like the reference's serial planner; n = 500 runs the reference's benchmark
+ * protocol (500 repetitions of the same query, run/plan_PCS.cpp:300-330) in the time of a few.
+ *
+ * usage: cbirrt_pcs_batch <env> <n_queries> <max_step> <seed> <out.txt> [workers] [max_rounds]
+ * out.txt: per solved query "query k nodes m rounds r" followed by m rows
+ *          q[12] a_chain ik0 ik1 e_ac e_ik e_dir     (edge to the NEXT row: RBS arguments that validated it; e_dir 1 = checked
+ *          from the next row toward this one; -1 -1 -1 on the last row), then one summary line starting with "summary".
+ */
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <thread>
+#include <vector>
+#include "../../include/ckc.h"
+
+static const double kPI_ = 3.1416;
+/* run/plan_PCS.cpp:91-114: bounds of the sampled state space */
+static const double kLo[12] = { -2.88, -1.919, -1.919, -2.79, -2.09, -kPI_, -2.88, -1.919, -1.919, -2.79, -2.09, -kPI_ };
+static const double kHi[12] = { 2.88, 1.919, 1.22, 2.79, 2.09, kPI_, 2.88, 1.919, 1.22, 2.79, 2.09, kPI_ };
+/* run/plan_PCS.cpp:268-276: the published start / goal pairs */
+static const double kStart1[12] = { 0.5236, 1.7453, -1.8326, -1.4835, 1.5708, 0, 1.004278, 0.2729, 0.9486, -1.15011, 1.81001, -1.97739 };
+static const double kGoal1[12] = { 0.5236, 0.34907, 0.69813, -1.3963, 1.5708, 0, 0.7096, 1.8032, -1.7061, -1.6286, 1.9143, -2.0155 };
+static const double kStart2[12] = { 1.1, 1.1, 0, 1.24, -1.5708, 0, -0.79567, 0.60136, 0.43858, -0.74986, -1.0074, -0.092294 };
+static const double kGoal2[12] = { -1.1, 1.35, -0.2, -1, -1.9, 0, 0.80875, 0.72363, -0.47891, -1.0484, 0.73278, 1.7491 };
+
+struct Node {
+    double q[12];
+    int ik[2];
+    int parent;
+    int a_chain;
+    int e_ac, e_ik;          /* RBS arguments that validated the edge parent -> this node */
+};
+struct Tree {
+    std::vector<Node> n;
+    int nearest(const double* q) const {            /* si_->distance: 12-D Euclid, linear scan */
+        int best = 0; double bd = 1e300;
+        for (size_t i = 0; i < n.size(); i++) {
+            double s = 0;
+            for (int j = 0; j < 12; j++) { const double d = n[i].q[j] - q[j]; s += d * d; }
+            if (s < bd) { bd = s; best = (int)i; }
+        }
+        return best;
+    }
+};
+
+enum Wait { W_NONE, W_PROJECT, W_PROJECT_FALLBACK, W_IDENTIFY, W_RBS0, W_RBS1 };
+
+struct Query {
+    Tree t[2];                       /* 0 = start tree, 1 = goal tree */
+    std::mt19937_64 rng;
+    bool start_turn = true, solved = false, failed = false;
+    int rounds = 0;
+    /* solve-loop state */
+    int stage = 0;                   /* 0: begin an iteration, 1: growTree(extend) running, 2: growTree(connect) running */
+    int tree = 0, other = 1, added = -1;
+    /* growTree activation record */
+    int g_tree = 0, mode = 1, count = 0, nm = 0, active_chain = 0, xmotion = -1;
+    double target[12]; int target_ik[2];
+    bool reach = false, reached = false;
+    /* the step in flight */
+    Wait wait = W_NONE;
+    double dstate[12]; int ik[2];
+    std::vector<int> path_tree, path_node;
+    Node junction; bool junction_in_start_tree = false;      /* the copy of the connection state that :430-433 drops */
+};
+
+static double uni(std::mt19937_64& g) { return (double)(g() >> 11) * (1.0 / 9007199254740992.0); }
+
+/* CBiRRT_PCS.cpp:122-140 including its active-chain-1 quirk (qa stays zero, qb = q2 of the target) */
+static double active_distance(int active_chain, const double* a, const double* b) {
+    double s = 0;
+    if (!active_chain) for (int i = 0; i < 6; i++) s += (a[i] - b[i]) * (a[i] - b[i]);
+    else for (int i = 0; i < 6; i++) s += b[6 + i] * b[6 + i];
+    return std::sqrt(s);
+}
+
+struct Ensemble {
+    ckc_ctx* ctx = nullptr;
+    double max_step = 1.0;
+    std::vector<Query> qs;
+    long calls = 0, items = 0;
+    double t_kind[3] = { 0, 0, 0 }; long n_kind[3] = { 0, 0, 0 }; long i_kind[3] = { 0, 0, 0 };      /* validate / identify / rbs */
+    std::chrono::steady_clock::time_point t_mark;
+    void mark() { t_mark = std::chrono::steady_clock::now(); }
+
+    void begin_grow(Query& Q, int tree, int nm, const double* target, const int* tik, int mode, int count) {
+        Q.g_tree = tree; Q.nm = nm; Q.mode = mode; Q.count = count; Q.reached = false;
+        memcpy(Q.target, target, sizeof(Q.target)); Q.target_ik[0] = tik[0]; Q.target_ik[1] = tik[1];
+        Q.active_chain = (int)(Q.rng() & 1);                                   /* :168 */
+    }
+
+    /* growTree returned (:206,:221,:238,:265,:298-303): advance the solve loop; leaves wait == W_NONE */
+    void end_grow(Query& Q) {
+        Q.wait = W_NONE;
+        if (Q.stage == 1) {
+            Q.added = Q.nm;                                                    /* :411 reached_motion of the extend step */
+            Q.xmotion = -1;
+            const Node tn = Q.t[Q.tree].n[Q.added];
+            const int nm2 = Q.t[Q.other].nearest(tn.q);                        /* :416 */
+            Q.stage = 2;
+            begin_grow(Q, Q.other, nm2, tn.q, tn.ik, 2, 500);                  /* :417 */
+        } else {
+            if (Q.reached) finish(Q);
+            Q.stage = 0;
+        }
+    }
+
+    /* :424-460: one step back on one side (the connection state exists in both trees), then the two root paths */
+    void finish(Query& Q) {
+        int sm = Q.other == 0 ? Q.xmotion : Q.added, gm = Q.other == 0 ? Q.added : Q.xmotion;
+        /* the dropped copy's own edge record (parent -> copy) is the check that validated the junction edge of the path */
+        if (Q.t[0].n[sm].parent >= 0) { Q.junction = Q.t[0].n[sm]; Q.junction_in_start_tree = true; sm = Q.t[0].n[sm].parent; }
+        else { Q.junction = Q.t[1].n[gm]; Q.junction_in_start_tree = false; gm = Q.t[1].n[gm].parent; }
+        std::vector<int> p1, p2;
+        for (int k = sm; k >= 0; k = Q.t[0].n[k].parent) p1.push_back(k);
+        for (int k = gm; k >= 0; k = Q.t[1].n[k].parent) p2.push_back(k);
+        Q.path_tree.clear(); Q.path_node.clear();
+        for (int i = (int)p1.size() - 1; i >= 0; i--) { Q.path_tree.push_back(0); Q.path_node.push_back(p1[i]); }
+        for (size_t i = 0; i < p2.size(); i++) { Q.path_tree.push_back(1); Q.path_node.push_back(p2[i]); }
+        Q.solved = true;
+    }
+
+    /* one growTree loop head (:173-190, :253-262): either posts the step's first question or ends the growTree call */
+    void grow_head(Query& Q) {
+        if (Q.count == 0) { end_grow(Q); return; }
+        Q.count--;
+        const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
+        const double d = active_distance(Q.active_chain, nmn.q, Q.target);
+        if (d > max_step) {
+            const double f = max_step / d;
+            for (int j = 0; j < 12; j++) Q.dstate[j] = nmn.q[j] + (Q.target[j] - nmn.q[j]) * f;      /* RealVectorStateSpace::interpolate */
+            Q.reach = false;
+        } else { memcpy(Q.dstate, Q.target, sizeof(Q.dstate)); Q.reach = true; }
+        if (Q.mode == 1 || !Q.reach) { Q.ik[0] = Q.ik[1] = -1; Q.wait = W_PROJECT; return; }
+        /* the state belongs to the opposite tree and already satisfies the constraint */
+        Q.ik[0] = Q.target_ik[0]; Q.ik[1] = Q.target_ik[1];
+        if (nmn.ik[0] == Q.ik[0]) Q.active_chain = 0;
+        else if (nmn.ik[1] == Q.ik[1]) Q.active_chain = 1;
+        else { end_grow(Q); return; }
+        Q.wait = W_RBS0;
+    }
+
+    /* host logic of one query until it has a question for the device (or is solved) */
+    void advance(Query& Q) {
+        while (!Q.solved && Q.wait == W_NONE) {
+            if (Q.stage == 0) begin_iteration(Q);
+            grow_head(Q);
+        }
+    }
+
+    /* start an iteration of the solve loop (:371-413) */
+    void begin_iteration(Query& Q) {
+        Q.tree = Q.start_turn ? 0 : 1; Q.start_turn = !Q.start_turn; Q.other = 1 - Q.tree;
+        double r[12];
+        for (int j = 0; j < 12; j++) r[j] = kLo[j] + uni(Q.rng) * (kHi[j] - kLo[j]);       /* sampler_->sampleUniform */
+        const int tik[2] = { -1, -1 };
+        Q.stage = 1;
+        begin_grow(Q, Q.tree, Q.t[Q.tree].nearest(r), r, tik, 1, 100);                        /* :409-410 */
+    }
+
+    void run(int max_rounds) {
+        std::vector<int> idx; std::vector<double> q, qo, qa, qb; std::vector<int8_t> ac, ik, id; std::vector<uint8_t> ok, valid, res; std::vector<int32_t> nchk;
+        for (int round = 0; round < max_rounds; round++) {
+            /* host part: every live query advances to its next question */
+            int live = 0;
+            for (auto& Q : qs) {
+                if (Q.solved || Q.failed) continue;
+                live++;
+                advance(Q);
+                if (Q.solved) continue;
+                Q.rounds++;
+            }
+            if (!live) break;
+            /* ---- step A / A': projection + collision ---- */
+            for (int pass = 0; pass < 2; pass++) {
+                const Wait want = pass == 0 ? W_PROJECT : W_PROJECT_FALLBACK;
+                idx.clear();
+                for (size_t k = 0; k < qs.size(); k++) if (!qs[k].solved && qs[k].wait == want) idx.push_back((int)k);
+                if (idx.empty()) continue;
+                const size_t m = idx.size();
+                q.resize(m * 12); qo.resize(m * 12); ac.resize(m); ik.resize(m); ok.resize(m); valid.resize(m);
+                for (size_t i = 0; i < m; i++) {
+                    Query& Q = qs[idx[i]];
+                    memcpy(&q[12 * i], Q.dstate, 96);
+                    ac[i] = (int8_t)Q.active_chain; ik[i] = (int8_t)Q.t[Q.g_tree].n[Q.nm].ik[Q.active_chain];
+                }
+                mark();
+                check(ckc_pcs_validate(ctx, (int64_t)m, q.data(), ac.data(), ik.data(), qo.data(), ok.data(), valid.data()), m, 0);
+                for (size_t i = 0; i < m; i++) {
+                    Query& Q = qs[idx[i]];
+                    if (!ok[i]) {
+                        if (pass == 0) { Q.active_chain = 1 - Q.active_chain; Q.wait = W_PROJECT_FALLBACK; }      /* :196-203 / :214-221 */
+                        else end_grow(Q);
+                        continue;
+                    }
+                    if (!valid[i]) { end_grow(Q); continue; }                 /* :236-240 collision */
+                    memcpy(Q.dstate, &qo[12 * i], 96);
+                    Q.ik[Q.active_chain] = Q.t[Q.g_tree].n[Q.nm].ik[Q.active_chain];
+                    Q.wait = W_IDENTIFY;
+                }
+            }
+            /* ---- step B: identify_state_ik(dstate, ik) (:251) ---- */
+            idx.clear();
+            for (size_t k = 0; k < qs.size(); k++) if (!qs[k].solved && qs[k].wait == W_IDENTIFY) idx.push_back((int)k);
+            if (!idx.empty()) {
+                const size_t m = idx.size();
+                q.resize(m * 12); id.resize(m * 2);
+                for (size_t i = 0; i < m; i++) memcpy(&q[12 * i], qs[idx[i]].dstate, 96);
+                mark();
+                check(ckc_identify_ik(ctx, (int64_t)m, q.data(), id.data()), m, 1);
+                for (size_t i = 0; i < m; i++) {
+                    Query& Q = qs[idx[i]];
+                    for (int c = 0; c < 2; c++) if (Q.ik[c] == -1) Q.ik[c] = id[2 * i + c];
+                    Q.wait = W_RBS0;
+                }
+            }
+            /* ---- step C / C': RBS local connection (:275-279) ---- */
+            for (int pass = 0; pass < 2; pass++) {
+                idx.clear();
+                for (size_t k = 0; k < qs.size(); k++) {
+                    Query& Q = qs[k];
+                    if (Q.solved || Q.wait != (pass == 0 ? W_RBS0 : W_RBS1)) continue;
+                    const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
+                    if (nmn.ik[pass] == Q.ik[pass]) idx.push_back((int)k);
+                    else if (pass == 0) Q.wait = W_RBS1;
+                    else { Q.xmotion = Q.nm; end_grow(Q); }                                   /* :300-303 */
+                }
+                if (idx.empty()) continue;
+                const size_t m = idx.size();
+                qa.resize(m * 12); qb.resize(m * 12); ac.resize(m); ik.resize(m); res.resize(m); nchk.resize(m);
+                for (size_t i = 0; i < m; i++) {
+                    Query& Q = qs[idx[i]];
+                    const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
+                    memcpy(&qa[12 * i], nmn.q, 96); memcpy(&qb[12 * i], Q.dstate, 96);
+                    ac[i] = (int8_t)pass; ik[i] = (int8_t)nmn.ik[pass];
+                }
+                mark();
+                check(ckc_pcs_check_motion_rbs(ctx, (int64_t)m, qa.data(), qb.data(), ac.data(), ik.data(), res.data(), nchk.data()), m, 2);
+                for (size_t i = 0; i < m; i++) {
+                    Query& Q = qs[idx[i]];
+                    if (!res[i]) {
+                        if (pass == 0) Q.wait = W_RBS1;
+                        else { Q.xmotion = Q.nm; end_grow(Q); }
+                        continue;
+                    }
+                    Node nn;                                                                  /* :283-293 */
+                    memcpy(nn.q, Q.dstate, 96); nn.ik[0] = Q.ik[0]; nn.ik[1] = Q.ik[1];
+                    nn.parent = Q.nm; nn.a_chain = Q.active_chain; nn.e_ac = pass; nn.e_ik = Q.t[Q.g_tree].n[Q.nm].ik[pass];
+                    Q.t[Q.g_tree].n.push_back(nn);
+                    Q.nm = (int)Q.t[Q.g_tree].n.size() - 1; Q.xmotion = Q.nm;
+                    Q.wait = W_NONE;
+                    if (Q.reach) { Q.reached = true; end_grow(Q); }                           /* :295-298 */
+                }
+            }
+        }
+    }
+    void check(int rc, size_t m, int kind) {
+        if (rc != CKC_OK) { fprintf(stderr, "ckc: %s\n", ckc_last_error(ctx)); exit(-1); }
+        t_kind[kind] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_mark).count();
+        n_kind[kind]++; i_kind[kind] += (long)m;
+        calls++; items += (long)m;
+    }
+};
+
+int main(int argc, char** argv) {
+    if (argc < 6) { fprintf(stderr, "usage: %s <env> <n_queries> <max_step> <seed> <out.txt> [workers] [max_rounds]\n", argv[0]); return 2; }
+    const int env = atoi(argv[1]), nq = atoi(argv[2]); const double max_step = atof(argv[3]); const uint64_t seed = strtoull(argv[4], nullptr, 10);
+    const int workers = std::max(1, std::min(argc > 6 ? atoi(argv[6]) : 1, std::max(nq, 1)));
+    const int max_rounds = argc > 7 ? atoi(argv[7]) : 20000;
+    const char* mesh = getenv("CKC_MESH_PATH"); const char* dev = getenv("CKC_DEVICE");
+    const double* start = env == 2 ? kStart2 : kStart1; const double* goal = env == 2 ? kGoal2 : kGoal1;
+    /* one libckc context per worker thread (a context serves one host thread at a time, include/ckc.h); the workers'
+     * batched calls overlap on the device, which hides the per-call latency of the thin RBS levels */
+    std::vector<Ensemble> E(workers);
+    int8_t id[4]; uint8_t hit[2];
+    for (int w = 0; w < workers; w++) {
+        E[w].max_step = max_step;
+        if (ckc_create(&E[w].ctx, env, mesh ? mesh : "./simulator", dev ? atoi(dev) : 0) != CKC_OK) { fprintf(stderr, "ckc_create failed\n"); return 1; }
+    }
+    /* :325-343, :380-396: start and goal must be identifiable on both chains and collision free */
+    double sg[24]; memcpy(sg, start, 96); memcpy(sg + 12, goal, 96);
+    if (ckc_identify_ik(E[0].ctx, 2, sg, id) != CKC_OK || ckc_collide(E[0].ctx, 2, sg, hit) != CKC_OK) { fprintf(stderr, "ckc: %s\n", ckc_last_error(E[0].ctx)); return 1; }
+    if (id[0] < 0 || id[1] < 0 || id[2] < 0 || id[3] < 0 || hit[0] || hit[1]) { fprintf(stderr, "start / goal state not feasible\n"); return 1; }
+    std::vector<std::vector<int> > qid(workers);
+    for (int k = 0; k < nq; k++) {
+        const int w = k % workers;
+        E[w].qs.emplace_back(); qid[w].push_back(k);
+        Query& Q = E[w].qs.back();
+        Q.rng.seed(seed * 1000003ull + (uint64_t)k);                    /* a query's random stream does not depend on the ensemble */
+        for (int t = 0; t < 2; t++) {
+            Node r; memcpy(r.q, t == 0 ? start : goal, 96); r.ik[0] = id[2 * t]; r.ik[1] = id[2 * t + 1]; r.parent = -1; r.a_chain = 0; r.e_ac = r.e_ik = -1;
+            Q.t[t].n.push_back(r);
+        }
+    }
+    /* one untimed warm-up call of each entry point (buffer allocation) */
+    for (int w = 0; w < workers; w++) {
+        double wq[12]; memcpy(wq, start, 96); int8_t a = 0, b = id[0]; double o[12]; uint8_t k1, k2; int32_t nc;
+        ckc_pcs_validate(E[w].ctx, 1, wq, &a, &b, o, &k1, &k2); ckc_pcs_check_motion_rbs(E[w].ctx, 1, start, start, &a, &b, &k1, &nc);
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    if (workers == 1) E[0].run(max_rounds);
+    else {
+        std::vector<std::thread> th;
+        for (int w = 0; w < workers; w++) th.emplace_back([&E, w, max_rounds]() { E[w].run(max_rounds); });
+        for (auto& t : th) t.join();
+    }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+    std::vector<const Query*> all(nq);
+    for (int w = 0; w < workers; w++) for (size_t i = 0; i < qid[w].size(); i++) all[qid[w][i]] = &E[w].qs[i];
+    FILE* fp = fopen(argv[5], "w");
+    if (!fp) { fprintf(stderr, "cannot write %s\n", argv[5]); return 1; }
+    int solved = 0; long nodes_trees = 0, rounds = 0, path_nodes = 0, calls = 0, items = 0;
+    for (int k = 0; k < nq; k++) {
+        const Query& Q = *all[k];
+        nodes_trees += (long)(Q.t[0].n.size() + Q.t[1].n.size());
+        if (!Q.solved) continue;
+        solved++; rounds += Q.rounds; path_nodes += (long)Q.path_node.size();
+        fprintf(fp, "query %d nodes %zu rounds %d\n", k, Q.path_node.size(), Q.rounds);
+        for (size_t i = 0; i < Q.path_node.size(); i++) {
+            const Node& n = Q.t[Q.path_tree[i]].n[Q.path_node[i]];
+            for (int j = 0; j < 12; j++) fprintf(fp, "%.17g ", n.q[j]);
+            int e_ac = -1, e_ik = -1, e_dir = -1;
+            if (i + 1 < Q.path_node.size()) {
+                const int tn = Q.path_tree[i + 1];
+                const Node& nx = Q.t[tn].n[Q.path_node[i + 1]];
+                if (Q.path_tree[i] == 0 && tn == 0) { e_ac = nx.e_ac; e_ik = nx.e_ik; e_dir = 0; }            /* parent -> child in the start tree */
+                else if (Q.path_tree[i] == 1 && tn == 1) { e_ac = n.e_ac; e_ik = n.e_ik; e_dir = 1; }        /* child -> parent in the goal tree */
+                else {                                                                                       /* the junction */
+                    e_ac = Q.junction.e_ac; e_ik = Q.junction.e_ik;
+                    e_dir = Q.junction_in_start_tree ? 0 : 1;
+                }
+            }
+            fprintf(fp, "%d %d %d %d %d %d\n", n.a_chain, n.ik[0], n.ik[1], e_ac, e_ik, e_dir);
+        }
+    }
+    static const char* kn[3] = { "validate", "identify", "rbs" };
+    for (int k = 0; k < 3; k++) {
+        long n = 0, it = 0; double t = 0;
+        for (int w = 0; w < workers; w++) { n += E[w].n_kind[k]; it += E[w].i_kind[k]; t += E[w].t_kind[k]; }
+        calls += n; items += it;
+        printf("  %-8s %6ld calls %8ld items  %.3f s summed over workers (%.1f us per call)\n", kn[k], n, it, t, n ? 1e6 * t / n : 0.0);
+    }
+    fprintf(fp, "summary queries %d solved %d seconds %.6f ms_per_query %.4f workers %d gpu_calls %ld items %ld mean_rounds %.1f mean_path_nodes %.1f mean_tree_nodes %.1f max_step %.3f env %d\n",
+            nq, solved, secs, 1e3 * secs / std::max(nq, 1), workers, calls, items, solved ? (double)rounds / solved : 0.0, solved ? (double)path_nodes / solved : 0.0,
+            (double)nodes_trees / std::max(nq, 1), max_step, env);
+    fclose(fp);
+    printf("queries %d solved %d in %.3f s (%.3f ms per query), %d workers, %ld batched calls, %.1f items per call\n", nq, solved, secs, 1e3 * secs / std::max(nq, 1),
+           workers, calls, calls ? (double)items / calls : 0.0);
+    for (int w = 0; w < workers; w++) ckc_destroy(E[w].ctx);
+    return 0;
+}

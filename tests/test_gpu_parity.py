@@ -123,6 +123,32 @@ def test_rbs_vs_reference_binary_golden(ck, gold):
     assert (nc[~good] >= 1).all()                           # failed edges: the level-synchronous order may evaluate more nodes
 
 
+def test_rbs_discontinuity_edges(ck, oracle):
+    """edges between valid configurations of one IK branch whose passive arm jumps in between: the reference recurses to
+    depth 150 on them and fails (PCS.cpp:495); the device stops at the first stationary segment -- same answers"""
+    from abb_dualarm_planning_b200 import sampling
+    q, ik = sampling.sample_pcs(21, 0, 200000)
+    _, valid, qo = ck.pcs_validate(q, 0, ik)
+    v, vik = qo[valid == 1], ik[valid == 1]
+    rng = np.random.default_rng(1)
+    A, B, K = [], [], []
+    for k in range(8):
+        idx = np.where(vik == k)[0]
+        for _ in range(150):
+            i, j = rng.choice(idx, 2, replace=False)
+            t = min(1.0, 1.0 / np.linalg.norm(v[i][:6] - v[j][:6]))          # active-arm distance <= 1 rad, as a planner step
+            A.append(v[i]); B.append(v[i] + (v[j] - v[i]) * t); K.append(k)
+    A, B, K = np.array(A), np.array(B), np.array(K, np.int8)
+    _, vb, qb = ck.pcs_validate(B, 0, K)
+    A, B, K = A[vb == 1], qb[vb == 1], K[vb == 1]
+    r_o, nc_o = oracle.pcs_check_motion_rbs(A, B, 0, K)
+    r, nc = ck.pcs_check_motion_rbs(A, B, 0, K)
+    assert (r == r_o).all()
+    assert (nc[r_o == 1] == nc_o[r_o == 1]).all()
+    deep = (r_o == 0) & (nc_o >= 140)
+    assert deep.sum() >= 10 and (nc[deep] >= 140).all()                    # the depth-cap failures are in the set
+
+
 def test_rbs_degenerate_edges(ck, gold):
     g = gold("rbs.npz")
     ok, nc = ck.pcs_check_motion_rbs(g["qa"][:8], g["qa"][:8], 0, g["ik"][:8])     # zero-length edges: d < tol at once

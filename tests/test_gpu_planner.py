@@ -1,0 +1,57 @@
+"""GPU: the lock-step CBiRRT-PCS ensemble (abb_dualarm_planning_b200/host/cbirrt_pcs_batch.cpp) -- every
+returned path is re-validated with the CPU oracle: end points, closure + IK branches of every milestone, no collision,
+and every edge accepted by the oracle's checkMotionRBS with the arguments the planner recorded."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(REPO, "abb_dualarm_planning_b200", "host")
+PACK = os.path.join(REPO, "abb_dualarm_planning_b200", "data", "meshes.ckcmesh")
+START = np.array([0.5236, 1.7453, -1.8326, -1.4835, 1.5708, 0, 1.004278, 0.2729, 0.9486, -1.15011, 1.81001, -1.97739])   # run/plan_PCS.cpp:269
+GOAL = np.array([0.5236, 0.34907, 0.69813, -1.3963, 1.5708, 0, 0.7096, 1.8032, -1.7061, -1.6286, 1.9143, -2.0155])      # :271
+
+
+def _plan(tmp_path, n, step, seed):
+    out = str(tmp_path / ("paths_%d.txt" % n))
+    env = dict(os.environ, CKC_MESH_PATH=PACK)
+    r = subprocess.run([os.path.join(HOST, "cbirrt_pcs_batch"), "1", str(n), str(step), str(seed), out], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    paths, summary = [], None
+    lines = open(out).read().strip().split("\n")
+    i = 0
+    while i < len(lines):
+        t = lines[i].split()
+        if t[0] == "summary":
+            summary = dict(zip(t[1::2], t[2::2])); i += 1
+        else:
+            m = int(t[3])
+            paths.append(np.array([[float(x) for x in ln.split()] for ln in lines[i + 1:i + 1 + m]])); i += 1 + m
+    return paths, summary, r.stdout
+
+
+def test_cbirrt_pcs_ensemble_paths_are_valid(tmp_path, oracle):
+    paths, summary, _ = _plan(tmp_path, 24, 1.0, 5)
+    assert int(summary["solved"]) == 24 == len(paths)
+    n_edges = 0
+    for P in paths:
+        q = P[:, :12]; ikn = P[:, 13:15].astype(int); e = P[:, 15:18].astype(int)
+        assert np.abs(q[0] - START).max() == 0 and np.abs(q[-1] - GOAL).max() == 0
+        assert (oracle.collision_state(q) == 0).all()
+        assert (oracle.identify_state_ik(q) == ikn).all() and (ikn >= 0).all()      # closed on both chains, branches as recorded
+        a = np.where(e[:-1, 2:3] == 0, q[:-1], q[1:]); b = np.where(e[:-1, 2:3] == 0, q[1:], q[:-1])
+        ok, _ = oracle.pcs_check_motion_rbs(a, b, e[:-1, 0].astype(np.int8), e[:-1, 1].astype(np.int8))
+        assert (ok == 1).all() and (e[-1] == -1).all()
+        n_edges += len(a)
+    assert n_edges >= 24
+
+
+def test_cbirrt_single_query_matches_its_ensemble_run(tmp_path):
+    """a query's random stream is its own: query 0 of an ensemble of 8 returns the path it returns when run alone"""
+    p1, _, _ = _plan(tmp_path, 1, 1.0, 9)
+    p8, _, _ = _plan(tmp_path, 8, 1.0, 9)
+    assert p1[0].shape == p8[0].shape and np.abs(p1[0] - p8[0]).max() == 0
