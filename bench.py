@@ -429,6 +429,24 @@ def extra_measurements(ck, sampling, torch, dev, stream):
     t = time.perf_counter() - t0
     ex["rbs_edges_per_s"] = ne / t
     ex["rbs_note"] = "%d S-RBS edges, %.1f%% succeed, %.1f validity checks per edge" % (ne, 100.0 * ok.mean(), nc.mean())
+    # BASELINE configs[3]: the reference's benchmark protocol (500 repetitions of the env-1 CBiRRT-PCS query) as one lock-step ensemble
+    try:
+        import subprocess, tempfile
+        exe = os.path.join(REPO, "abb_dualarm_planning_b200", "host", "cbirrt_pcs_batch")
+        if os.path.exists(exe):
+            with tempfile.TemporaryDirectory() as td:
+                out = os.path.join(td, "paths.txt")
+                env = dict(os.environ, CKC_MESH_PATH=os.path.join(REPO, "abb_dualarm_planning_b200", "data", "meshes.ckcmesh"),
+                           CKC_DEVICE=str(torch.cuda.current_device()))
+                subprocess.run([exe, "1", "500", "1.0", "7", out, "4"], env=env, capture_output=True, timeout=300, check=True)
+                t = open(out).read().strip().split("\n")[-1].split()
+                sm = dict(zip(t[1::2], t[2::2]))
+            ex["cbirrt_pcs_ms_per_query"] = float(sm["ms_per_query"])
+            ex["cbirrt_pcs_note"] = ("%s of %s env-1 start-to-goal queries solved in %.2f s by the lock-step ensemble (host/cbirrt_pcs_batch.cpp, 4 workers, "
+                                     "max step 1.0, %s batched calls); the reference reports 218 ms per query on its author's CPU (BASELINE.md)"
+                                     % (sm["solved"], sm["queries"], float(sm["seconds"]), sm["gpu_calls"]))
+    except Exception as e:       # an extra, never the metric
+        ex["cbirrt_pcs_note"] = "not run: %r" % (e,)
     return ex
 
 
