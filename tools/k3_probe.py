@@ -17,7 +17,7 @@ ok, qo = ck.pcs_project(q, 0, ik)
 feas = qo[ok == 1]                                   # ~95k IK-feasible configurations, half of them colliding
 hit = ck.collide(feas)
 free = feas[hit == 0]
-for label, arr in (("feasible", feas), ("free", free)):
+for label, arr in (("feasible", feas), ("free", free), ("feas31k", feas[:31500]), ("feas8k", feas[:8000]), ("feas2k", feas[:2000])):
     for _ in range(2): ck.collide(arr)
     ck.reset_stats(); ck.set_stage_timing(True)
     for _ in range(5): h = ck.collide(arr)
