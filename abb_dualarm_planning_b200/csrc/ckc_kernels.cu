@@ -380,11 +380,10 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     collide_args a;
     a.frames = frames; a.list = list; a.d_m = d_m; a.m_max = m_max; a.hit_out = hit_out; a.valid_out = valid_out; a.pair_flags = pair_flags;
     a.work_counter = work_counter; a.ovf_list = ovf_list; a.ovf_count = ovf_count; a.big_stack = big_stack; a.ctr = ctr;
-    static int wide_cnt = -1;
-    if (wide_cnt < 0) { const char* e = getenv("CKC_WIDE_CNT"); wide_cnt = e ? atoi(e) : 16; }
+    /* tuning / debug knobs, read once (function-local statics: initialisation is thread safe, contexts may live on several threads) */
+    static const int wide_cnt = [] { const char* e = getenv("CKC_WIDE_CNT"); return e ? atoi(e) : 16; }();
+    static const int count_rounds = [] { const char* e = getenv("CKC_COUNT_ROUNDS"); return e ? atoi(e) : 0; }();
     a.wide_cnt = wide_cnt;
-    static int count_rounds = -1;
-    if (count_rounds < 0) { const char* e = getenv("CKC_COUNT_ROUNDS"); count_rounds = e ? atoi(e) : 0; }
     a.count_rounds = count_rounds;
     /* work_counter[0] main pass, [1] overflow pass; the overflow count sits right behind them in the lanes' scratch block */
     if (ovf_count == work_counter + 2) cudaMemsetAsync(work_counter, 0, 3 * sizeof(int32_t), st);
@@ -675,15 +674,15 @@ void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const
                            double* q_out, ckc_layout lo, uint8_t* ok, uint8_t* converged, int32_t* iters, uint8_t* valid,
                            int32_t* list, int32_t* list_count, int32_t* state_scratch, unsigned long long* work_counter, ckc_counters_dev* ctr, cudaStream_t st) {
     if (n <= 0) return;
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gd_project<false>, CKC_GD_BLOCK, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 2;
-    }
+    static const int blocks_per_sm = [] {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_gd_project<false>, CKC_GD_BLOCK, 0) != cudaSuccess || b < 1) b = 2;
+        return b;
+    }();
     int64_t blocks = (int64_t)num_sms * blocks_per_sm;
     /* at least ~2 samples per lane so that the lane-level work stealing can balance the iteration counts (measured on
      * 2^16..2^18-sample chunks: 1-3 equal, 6 slower by 5 %; a 1e6-sample launch is capped by the resident grid anyway) */
-    static int spl = 0;
-    if (spl == 0) { const char* e = getenv("CKC_GD_SPL"); spl = e ? atoi(e) : 2; if (spl < 1) spl = 1; }
+    static const int spl = [] { const char* e = getenv("CKC_GD_SPL"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
     const int64_t needed = (n + spl * CKC_GD_BLOCK - 1) / (spl * CKC_GD_BLOCK);
     if (blocks > needed) blocks = needed;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
