@@ -1,11 +1,14 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-nvidia-smi topo -m 2>&1 | head -14
 N=8
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 10 --warmup 3 --no-extra > gpurun_out/bench_gd_n$N.json 2> gpurun_out/bench_gd_n$N.err; echo "N=$N rc=$?"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 10 --warmup 3 --no-extra > gpurun_out/r1_bench_gd_n$N.json 2> gpurun_out/bench_gd_n$N.err; echo "gd N=$N rc=$?"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --workload pcs --steps 10 --warmup 3 --no-extra > gpurun_out/r1_bench_pcs_n$N.json 2> gpurun_out/bench_pcs_n$N.err; echo "pcs N=$N rc=$?"
+N=2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus $N --steps 10 --warmup 3 --no-extra > gpurun_out/r1_bench_gd_n$N.json 2> gpurun_out/bench_gd_n$N.err; echo "gd N=$N rc=$?"
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/bench_gd_n8.json').read().strip().split('\n')[-1])
-print('gd 8 value %.3e e2e %.3e ms/step %.3f numa %s'%(d['value'],d['e2e']['value'],d['ms_per_step'],d['config'].get('numa_node_rank0')))
+for f in ('gd_n8','pcs_n8','gd_n2'):
+    d=json.loads(open('gpurun_out/r1_bench_%s.json'%f).read().strip().split('\n')[-1])
+    print(f,'value %.3e e2e %.3e ms/step %.3f n_gpus %d'%(d['value'],d['e2e']['value'],d['ms_per_step'],d['n_gpus']))
 PY
