@@ -110,6 +110,15 @@ def test_reference_path_fixture(oracle, gold):
         assert np.abs(T[:3, :3] - np.eye(3)).max() < 2e-3
 
 
+def test_gd_golden_mask_prefix(oracle, gold):
+    """the committed S-GD mask is what the restatement computes (first 3000 samples re-done here)"""
+    from abb_dualarm_planning_b200 import sampling
+    g = gold("sgd_seed1_1e6_mask.npz")
+    want = np.unpackbits(g["valid_bits"])[:3000]
+    v, _ = oracle.gd_validate(sampling.sample_gd(int(g["seed"]), 0, 3000))
+    assert (v == want).all() and want.sum() > 20
+
+
 def test_is_valid_full_vs_binary(oracle, gold):
     """isValid(const ob::State*) PCS.cpp:323-357 run through the genuine binary; unidentified branches (-1) are UB there"""
     g = gold("isvalid_full.npz")
