@@ -19,7 +19,9 @@
  * One query (n = 1) therefore behaves like the reference's serial planner; n = 500 runs the reference's benchmark
  * protocol (500 repetitions of the same query, run/plan_PCS.cpp:300-330) in the time of a few.
  *
- * usage: cbirrt_pcs_batch <env> <n_queries> <max_step> <seed> <out.txt> [workers] [max_rounds]
+ * usage: cbirrt_pcs_batch <env> <n_queries> <max_step> <seed> <out.txt> [workers] [pcs|gd] [max_rounds]
+ * flavour gd = planners/CBiRRT_GD.cpp: 12-D distance, IKproject(dstate) = kdl::GD + limits + collision (ckc_gd_validate),
+ * checkMotionRBS(s1, s2) (ckc_gd_check_motion_rbs); rows then carry -1 for the branch / edge columns.
  * out.txt: per solved query "query k nodes m rounds r" followed by m rows
  *          q[12] a_chain ik0 ik1 e_ac e_ik e_dir     (edge to the NEXT row: RBS arguments that validated it; e_dir 1 = checked
  *          from the next row toward this one; -1 -1 -1 on the last row), then one summary line starting with "summary".
@@ -100,6 +102,7 @@ static double active_distance(int active_chain, const double* a, const double* b
 struct Ensemble {
     ckc_ctx* ctx = nullptr;
     double max_step = 1.0;
+    bool gd = false;                 /* CBiRRT-GD (planners/CBiRRT_GD.cpp) instead of CBiRRT-PCS */
     std::vector<Query> qs;
     long calls = 0, items = 0;
     double t_kind[3] = { 0, 0, 0 }; long n_kind[3] = { 0, 0, 0 }; long i_kind[3] = { 0, 0, 0 };      /* validate / identify / rbs */
@@ -107,7 +110,7 @@ struct Ensemble {
     void mark() { t_mark = std::chrono::steady_clock::now(); }
 
     void begin_grow(Query& Q, int tree, int nm, const double* target, const int* tik, int mode, int count) {
-        Q.g_tree = tree; Q.nm = nm; Q.mode = mode; Q.count = count; Q.reached = false;
+        Q.g_tree = tree; Q.nm = nm; Q.mode = mode; Q.count = gd ? count + 1 : count; Q.reached = false;      /* GD: while (count >= 0), CBiRRT_GD.cpp:166 */
         memcpy(Q.target, target, sizeof(Q.target)); Q.target_ik[0] = tik[0]; Q.target_ik[1] = tik[1];
         Q.active_chain = (int)(Q.rng() & 1);                                   /* :168 */
     }
@@ -148,13 +151,19 @@ struct Ensemble {
         if (Q.count == 0) { end_grow(Q); return; }
         Q.count--;
         const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
-        const double d = active_distance(Q.active_chain, nmn.q, Q.target);
+        double d;
+        if (gd) {                                   /* CBiRRT_GD.cpp:171: distanceFunction = 12-D Euclid */
+            d = 0;
+            for (int j = 0; j < 12; j++) d += (nmn.q[j] - Q.target[j]) * (nmn.q[j] - Q.target[j]);
+            d = std::sqrt(d);
+        } else d = active_distance(Q.active_chain, nmn.q, Q.target);
         if (d > max_step) {
             const double f = max_step / d;
             for (int j = 0; j < 12; j++) Q.dstate[j] = nmn.q[j] + (Q.target[j] - nmn.q[j]) * f;      /* RealVectorStateSpace::interpolate */
             Q.reach = false;
         } else { memcpy(Q.dstate, Q.target, sizeof(Q.dstate)); Q.reach = true; }
         if (Q.mode == 1 || !Q.reach) { Q.ik[0] = Q.ik[1] = -1; Q.wait = W_PROJECT; return; }
+        if (gd) { Q.wait = W_RBS0; return; }       /* CBiRRT_GD.cpp:183-206: no branch bookkeeping */
         /* the state belongs to the opposite tree and already satisfies the constraint */
         Q.ik[0] = Q.target_ik[0]; Q.ik[1] = Q.target_ik[1];
         if (nmn.ik[0] == Q.ik[0]) Q.active_chain = 0;
@@ -194,6 +203,7 @@ struct Ensemble {
                 Q.rounds++;
             }
             if (!live) break;
+            if (gd) { run_gd_steps(idx, q, qo, qa, qb, valid, res, nchk); continue; }
             /* ---- step A / A': projection + collision ---- */
             for (int pass = 0; pass < 2; pass++) {
                 const Wait want = pass == 0 ? W_PROJECT : W_PROJECT_FALLBACK;
@@ -277,6 +287,48 @@ struct Ensemble {
             }
         }
     }
+    /* CBiRRT-GD: IKproject(dstate) = kdl::GD + joint limits + collision (StateValidityCheckerGD.cpp:96-110) in one batched
+     * ckc_gd_validate, then checkMotionRBS(nmotion, dstate) (:214-241) in one batched ckc_gd_check_motion_rbs */
+    void run_gd_steps(std::vector<int>& idx, std::vector<double>& q, std::vector<double>& qo, std::vector<double>& qa, std::vector<double>& qb,
+                      std::vector<uint8_t>& valid, std::vector<uint8_t>& res, std::vector<int32_t>& nchk) {
+        idx.clear();
+        for (size_t k = 0; k < qs.size(); k++) if (!qs[k].solved && qs[k].wait == W_PROJECT) idx.push_back((int)k);
+        if (!idx.empty()) {
+            const size_t m = idx.size();
+            q.resize(m * 12); qo.resize(m * 12); valid.resize(m);
+            for (size_t i = 0; i < m; i++) memcpy(&q[12 * i], qs[idx[i]].dstate, 96);
+            mark();
+            check(ckc_gd_validate(ctx, (int64_t)m, q.data(), qo.data(), valid.data()), m, 0);
+            for (size_t i = 0; i < m; i++) {
+                Query& Q = qs[idx[i]];
+                if (!valid[i]) { end_grow(Q); continue; }                                     /* CBiRRT_GD.cpp:187-191 */
+                memcpy(Q.dstate, &qo[12 * i], 96);
+                Q.wait = W_RBS0;
+            }
+        }
+        idx.clear();
+        for (size_t k = 0; k < qs.size(); k++) if (!qs[k].solved && qs[k].wait == W_RBS0) idx.push_back((int)k);
+        if (idx.empty()) return;
+        const size_t m = idx.size();
+        qa.resize(m * 12); qb.resize(m * 12); res.resize(m); nchk.resize(m);
+        for (size_t i = 0; i < m; i++) {
+            Query& Q = qs[idx[i]];
+            memcpy(&qa[12 * i], Q.t[Q.g_tree].n[Q.nm].q, 96); memcpy(&qb[12 * i], Q.dstate, 96);
+        }
+        mark();
+        check(ckc_gd_check_motion_rbs(ctx, (int64_t)m, qa.data(), qb.data(), res.data(), nchk.data()), m, 2);
+        for (size_t i = 0; i < m; i++) {
+            Query& Q = qs[idx[i]];
+            if (!res[i]) { Q.xmotion = Q.nm; end_grow(Q); continue; }                         /* :229-232 */
+            Node nn;
+            memcpy(nn.q, Q.dstate, 96); nn.ik[0] = nn.ik[1] = -1; nn.parent = Q.nm; nn.a_chain = 0; nn.e_ac = nn.e_ik = -1;
+            Q.t[Q.g_tree].n.push_back(nn);
+            Q.nm = (int)Q.t[Q.g_tree].n.size() - 1; Q.xmotion = Q.nm;
+            Q.wait = W_NONE;
+            if (Q.reach) { Q.reached = true; end_grow(Q); }
+        }
+    }
+
     void check(int rc, size_t m, int kind) {
         if (rc != CKC_OK) { fprintf(stderr, "ckc: %s\n", ckc_last_error(ctx)); exit(-1); }
         t_kind[kind] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_mark).count();
@@ -286,10 +338,11 @@ struct Ensemble {
 };
 
 int main(int argc, char** argv) {
-    if (argc < 6) { fprintf(stderr, "usage: %s <env> <n_queries> <max_step> <seed> <out.txt> [workers] [max_rounds]\n", argv[0]); return 2; }
+    if (argc < 6) { fprintf(stderr, "usage: %s <env> <n_queries> <max_step> <seed> <out.txt> [workers] [pcs|gd] [max_rounds]\n", argv[0]); return 2; }
     const int env = atoi(argv[1]), nq = atoi(argv[2]); const double max_step = atof(argv[3]); const uint64_t seed = strtoull(argv[4], nullptr, 10);
     const int workers = std::max(1, std::min(argc > 6 ? atoi(argv[6]) : 1, std::max(nq, 1)));
-    const int max_rounds = argc > 7 ? atoi(argv[7]) : 20000;
+    const bool gd = argc > 7 && strcmp(argv[7], "gd") == 0;
+    const int max_rounds = argc > 8 ? atoi(argv[8]) : 20000;
     const char* mesh = getenv("CKC_MESH_PATH"); const char* dev = getenv("CKC_DEVICE");
     const double* start = env == 2 ? kStart2 : kStart1; const double* goal = env == 2 ? kGoal2 : kGoal1;
     /* one libckc context per worker thread (a context serves one host thread at a time, include/ckc.h); the workers'
@@ -297,13 +350,14 @@ int main(int argc, char** argv) {
     std::vector<Ensemble> E(workers);
     int8_t id[4]; uint8_t hit[2];
     for (int w = 0; w < workers; w++) {
-        E[w].max_step = max_step;
+        E[w].max_step = max_step; E[w].gd = gd;
         if (ckc_create(&E[w].ctx, env, mesh ? mesh : "./simulator", dev ? atoi(dev) : 0) != CKC_OK) { fprintf(stderr, "ckc_create failed\n"); return 1; }
     }
     /* :325-343, :380-396: start and goal must be identifiable on both chains and collision free */
     double sg[24]; memcpy(sg, start, 96); memcpy(sg + 12, goal, 96);
     if (ckc_identify_ik(E[0].ctx, 2, sg, id) != CKC_OK || ckc_collide(E[0].ctx, 2, sg, hit) != CKC_OK) { fprintf(stderr, "ckc: %s\n", ckc_last_error(E[0].ctx)); return 1; }
-    if (id[0] < 0 || id[1] < 0 || id[2] < 0 || id[3] < 0 || hit[0] || hit[1]) { fprintf(stderr, "start / goal state not feasible\n"); return 1; }
+    if (!gd && (id[0] < 0 || id[1] < 0 || id[2] < 0 || id[3] < 0 || hit[0] || hit[1])) { fprintf(stderr, "start / goal state not feasible\n"); return 1; }
+    if (gd) id[0] = id[1] = id[2] = id[3] = -1;                          /* CBiRRT_GD.cpp:252-256: no feasibility test, no branches */
     std::vector<std::vector<int> > qid(workers);
     for (int k = 0; k < nq; k++) {
         const int w = k % workers;
@@ -318,7 +372,8 @@ int main(int argc, char** argv) {
     /* one untimed warm-up call of each entry point (buffer allocation) */
     for (int w = 0; w < workers; w++) {
         double wq[12]; memcpy(wq, start, 96); int8_t a = 0, b = id[0]; double o[12]; uint8_t k1, k2; int32_t nc;
-        ckc_pcs_validate(E[w].ctx, 1, wq, &a, &b, o, &k1, &k2); ckc_pcs_check_motion_rbs(E[w].ctx, 1, start, start, &a, &b, &k1, &nc);
+        if (gd) { ckc_gd_validate(E[w].ctx, 1, wq, o, &k1); ckc_gd_check_motion_rbs(E[w].ctx, 1, start, start, &k1, &nc); }
+        else { b = b < 0 ? 0 : b; ckc_pcs_validate(E[w].ctx, 1, wq, &a, &b, o, &k1, &k2); ckc_pcs_check_motion_rbs(E[w].ctx, 1, start, start, &a, &b, &k1, &nc); }
     }
     const auto t0 = std::chrono::steady_clock::now();
     if (workers == 1) E[0].run(max_rounds);
@@ -364,9 +419,9 @@ int main(int argc, char** argv) {
         calls += n; items += it;
         printf("  %-8s %6ld calls %8ld items  %.3f s summed over workers (%.1f us per call)\n", kn[k], n, it, t, n ? 1e6 * t / n : 0.0);
     }
-    fprintf(fp, "summary queries %d solved %d seconds %.6f ms_per_query %.4f workers %d gpu_calls %ld items %ld mean_rounds %.1f mean_path_nodes %.1f mean_tree_nodes %.1f max_step %.3f env %d\n",
+    fprintf(fp, "summary queries %d solved %d seconds %.6f ms_per_query %.4f workers %d gpu_calls %ld items %ld mean_rounds %.1f mean_path_nodes %.1f mean_tree_nodes %.1f max_step %.3f env %d flavour %s\n",
             nq, solved, secs, 1e3 * secs / std::max(nq, 1), workers, calls, items, solved ? (double)rounds / solved : 0.0, solved ? (double)path_nodes / solved : 0.0,
-            (double)nodes_trees / std::max(nq, 1), max_step, env);
+            (double)nodes_trees / std::max(nq, 1), max_step, env, gd ? "gd" : "pcs");
     fclose(fp);
     printf("queries %d solved %d in %.3f s (%.3f ms per query), %d workers, %ld batched calls, %.1f items per call\n", nq, solved, secs, 1e3 * secs / std::max(nq, 1),
            workers, calls, calls ? (double)items / calls : 0.0);

@@ -438,13 +438,14 @@ def extra_measurements(ck, sampling, torch, dev, stream):
                 out = os.path.join(td, "paths.txt")
                 env = dict(os.environ, CKC_MESH_PATH=os.path.join(REPO, "abb_dualarm_planning_b200", "data", "meshes.ckcmesh"),
                            CKC_DEVICE=str(torch.cuda.current_device()))
-                subprocess.run([exe, "1", "500", "1.0", "7", out, "4"], env=env, capture_output=True, timeout=300, check=True)
-                t = open(out).read().strip().split("\n")[-1].split()
-                sm = dict(zip(t[1::2], t[2::2]))
-            ex["cbirrt_pcs_ms_per_query"] = float(sm["ms_per_query"])
-            ex["cbirrt_pcs_note"] = ("%s of %s env-1 start-to-goal queries solved in %.2f s by the lock-step ensemble (host/cbirrt_pcs_batch.cpp, 4 workers, "
-                                     "max step 1.0, %s batched calls); the reference reports 218 ms per query on its author's CPU (BASELINE.md)"
-                                     % (sm["solved"], sm["queries"], float(sm["seconds"]), sm["gpu_calls"]))
+                for flav, step, ref_ms in (("pcs", "1.0", 218), ("gd", "2.6", 128)):
+                    subprocess.run([exe, "1", "500", step, "7", out, "4", flav], env=env, capture_output=True, timeout=300, check=True)
+                    t = open(out).read().strip().split("\n")[-1].split()
+                    sm = dict(zip(t[1::2], t[2::2]))
+                    ex["cbirrt_%s_ms_per_query" % flav] = float(sm["ms_per_query"])
+                    ex["cbirrt_%s_note" % flav] = ("%s of %s env-1 start-to-goal queries solved in %.2f s by the lock-step ensemble (host/cbirrt_pcs_batch.cpp, 4 workers, "
+                                                   "max step %s, %s batched calls); the reference reports %d ms per query on its author's CPU (BASELINE.md)"
+                                                   % (sm["solved"], sm["queries"], float(sm["seconds"]), step, sm["gpu_calls"], ref_ms))
     except Exception as e:       # an extra, never the metric
         ex["cbirrt_pcs_note"] = "not run: %r" % (e,)
     return ex

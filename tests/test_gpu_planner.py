@@ -16,10 +16,11 @@ START = np.array([0.5236, 1.7453, -1.8326, -1.4835, 1.5708, 0, 1.004278, 0.2729,
 GOAL = np.array([0.5236, 0.34907, 0.69813, -1.3963, 1.5708, 0, 0.7096, 1.8032, -1.7061, -1.6286, 1.9143, -2.0155])      # :271
 
 
-def _plan(tmp_path, n, step, seed):
-    out = str(tmp_path / ("paths_%d.txt" % n))
+def _plan(tmp_path, n, step, seed, flavour="pcs", workers=1):
+    out = str(tmp_path / ("paths_%s_%d.txt" % (flavour, n)))
     env = dict(os.environ, CKC_MESH_PATH=PACK)
-    r = subprocess.run([os.path.join(HOST, "cbirrt_pcs_batch"), "1", str(n), str(step), str(seed), out], env=env, capture_output=True, text=True, timeout=900)
+    r = subprocess.run([os.path.join(HOST, "cbirrt_pcs_batch"), "1", str(n), str(step), str(seed), out, str(workers), flavour], env=env, capture_output=True,
+                       text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     paths, summary = [], None
     lines = open(out).read().strip().split("\n")
@@ -55,3 +56,19 @@ def test_cbirrt_single_query_matches_its_ensemble_run(tmp_path):
     p1, _, _ = _plan(tmp_path, 1, 1.0, 9)
     p8, _, _ = _plan(tmp_path, 8, 1.0, 9)
     assert p1[0].shape == p8[0].shape and np.abs(p1[0] - p8[0]).max() == 0
+
+
+def test_cbirrt_gd_ensemble_paths_are_valid(tmp_path, oracle):
+    """the GD flavour (planners/CBiRRT_GD.cpp): kdl::GD projection + RBS through ckc_gd_validate / ckc_gd_check_motion_rbs"""
+    paths, summary, _ = _plan(tmp_path, 12, 2.0, 3, "gd", workers=2)
+    assert int(summary["solved"]) == 12 == len(paths)
+    for P in paths:
+        q = P[:, :12]; e = P[:, 15:18].astype(int)
+        assert np.abs(q[0] - START).max() == 0 and np.abs(q[-1] - GOAL).max() == 0
+        assert (oracle.collision_state(q) == 0).all()
+        for row in q[1:-1]:                                   # projected milestones close the KDL chain (reference tolerance 0.1 mm)
+            T = oracle.kdl_fk(row)
+            assert np.abs(T[:3, 3] - [900, 0, 0]).max() < 0.1 and np.abs(T[:3, :3] - np.eye(3)).max() < 2e-4
+        a = np.where(e[:-1, 2:3] == 0, q[:-1], q[1:]); b = np.where(e[:-1, 2:3] == 0, q[1:], q[:-1])
+        ok, _ = oracle.gd_check_motion_rbs(a, b)
+        assert (ok == 1).all()
