@@ -72,3 +72,23 @@ def test_cbirrt_gd_ensemble_paths_are_valid(tmp_path, oracle):
         a = np.where(e[:-1, 2:3] == 0, q[:-1], q[1:]); b = np.where(e[:-1, 2:3] == 0, q[1:], q[:-1])
         ok, _ = oracle.gd_check_motion_rbs(a, b)
         assert (ok == 1).all()
+
+
+def test_prm_pcs_roadmap_path_is_valid(tmp_path, oracle):
+    """the roadmap flavour (planners/PRM_PCS.cpp): batched sample_q + batched addMilestone connections"""
+    out = str(tmp_path / "prm.txt")
+    env = dict(os.environ, CKC_MESH_PATH=PACK)
+    r = subprocess.run([os.path.join(HOST, "prm_pcs_batch"), "1", "400", "11", out], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-1500:]
+    lines = open(out).read().strip().split("\n")
+    m = int(lines[0].split()[3])
+    P = np.array([[float(x) for x in ln.split()] for ln in lines[1:1 + m]])
+    summary = dict(zip(lines[-1].split()[1::2], lines[-1].split()[2::2]))
+    assert int(summary["solved"]) == 1 and int(summary["edges_valid"]) > 50
+    q = P[:, :12]; ikn = P[:, 13:15].astype(int); e = P[:, 15:18].astype(int)
+    assert np.abs(q[0] - START).max() == 0 and np.abs(q[-1] - GOAL).max() == 0
+    assert (oracle.collision_state(q) == 0).all()
+    assert (oracle.identify_state_ik(q) == ikn).all()
+    a = np.where(e[:-1, 2:3] == 0, q[:-1], q[1:]); b = np.where(e[:-1, 2:3] == 0, q[1:], q[:-1])
+    ok, _ = oracle.pcs_check_motion_rbs(a, b, e[:-1, 0].astype(np.int8), e[:-1, 1].astype(np.int8))
+    assert (ok == 1).all()
