@@ -67,6 +67,33 @@ def test_pcs_ten_million_seeded_checksum(ck):
     assert 0.0230 < f_ok < 0.0245 and 0.0110 < f_valid < 0.0120
 
 
+def test_full_size_1e8_seeded_sweeps(ck):
+    """BASELINE configs[4] at its full size on one GPU: 1e8 S-PCS and 1e8 S-GD samples generated on the device.  The first 1e6
+    flags reproduce the golden masks, one 1e8 call equals ten 1e7 calls flag for flag (sample i depends on (seed, i) only, so this
+    is also what sharding the index range over ranks returns), and the feasibility statistics stay in the reference's band."""
+    import os
+    import torch
+    from conftest import GOLD
+    n, part = 100_000_000, 10_000_000
+    st = torch.cuda.current_stream().cuda_stream
+    for name, call, gold_file, band in (
+            ("pcs", lambda i0, m, v: ck.spcs_validate_seeded_dev(1, i0, m, None, None, v, st), "spcs_seed1_1e6_mask.npz", (0.0110, 0.0120)),
+            ("gd", lambda i0, m, v: ck.sgd_validate_seeded_dev(1, i0, m, None, None, v, st), "sgd_seed1_1e6_mask.npz", (0.0135, 0.0147))):
+        whole = torch.empty(n, dtype=torch.uint8, device="cuda"); parts = torch.empty(n, dtype=torch.uint8, device="cuda")
+        call(0, n, whole.data_ptr())
+        for i0 in range(0, n, part):
+            call(i0, part, parts[i0:].data_ptr())
+        torch.cuda.synchronize()
+        g = np.load(os.path.join(GOLD, gold_file))
+        want = np.unpackbits(g["valid_bits"])[:1_000_000]
+        got = whole[:1_000_000].cpu().numpy()
+        assert (got != want).sum() <= (2 if name == "gd" else 0), name
+        assert torch.equal(whole, parts), name
+        f = whole.float().mean().item()
+        assert band[0] < f < band[1], (name, f)
+        del whole, parts
+
+
 def test_rbs_is_symmetric_and_monotone(ck, gold):
     """checkMotionRBS(a, b) == checkMotionRBS(b, a) (the bisection tree is mirrored), and an edge that succeeds keeps
     succeeding when cut in half at its (projected) midpoint."""
