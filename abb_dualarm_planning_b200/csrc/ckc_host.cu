@@ -45,13 +45,19 @@ struct ckc_lane {
     cudaStream_t st = nullptr;
     cudaStream_t st_hi = nullptr;       /* high-priority stream for the collision stage of this lane's chunk */
     cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_c = nullptr;
-    dev_buf qin, qout, ac, ik, ok, valid, list, frames, ovf, bigstack, flags, aux, aux2, small, gdstate;
+    dev_buf qin, qout, ac, ik, ok, valid, list, frames, ovf, bigstack, flags, aux, aux2, small, gdstate, pairstat;
+    int64_t collide_launches = 0;
+    /* this lane's own first-hit statistics and processing order of the pair table: [0, MAX_PAIRS) hits, [MAX_PAIRS, 2 MAX_PAIRS)
+     * order.  They are read and rewritten only by kernels on this lane's stream -- a table shared by the lanes would be
+     * re-sorted on one stream while another lane's k_collide seeds its stacks from it (a torn permutation = a missed pair) */
+    unsigned int* pair_hits() const { return pairstat.as<unsigned int>(); }
+    int* pair_order() const { return pairstat.as<int>() + CKC_MAX_PAIRS; }
     int32_t* list_count() const { return small.as<int32_t>(); }
     int32_t* work_counter() const { return small.as<int32_t>() + 2; }      /* 2 ints */
     int32_t* ovf_count() const { return small.as<int32_t>() + 4; }
     int32_t* rbs_counts() const { return small.as<int32_t>() + 8; }        /* 2 ints */
     unsigned long long* gd_counter() const { return (unsigned long long*)(small.as<int32_t>() + 12); }
-    void release() { dev_buf* b[] = { &qin, &qout, &ac, &ik, &ok, &valid, &list, &frames, &ovf, &bigstack, &flags, &aux, &aux2, &small, &gdstate }; for (dev_buf* x : b) x->release(); }
+    void release() { dev_buf* b[] = { &qin, &qout, &ac, &ik, &ok, &valid, &list, &frames, &ovf, &bigstack, &flags, &aux, &aux2, &small, &gdstate, &pairstat }; for (dev_buf* x : b) x->release(); }
 };
 
 struct ckc_ctx {
@@ -67,7 +73,6 @@ struct ckc_ctx {
     dev_buf d_cidx, d_cq, d_ccount;                     /* compact outputs of the *_compact entry points (per chunk regions) */
     void* h_stage = nullptr; size_t h_stage_cap = 0;    /* pinned staging of the compact outputs */
     dev_buf rbs_seg[2], rbs_cand, rbs_pool, rbs_eok, rbs_nck, rbs_hit, rbs_eac, rbs_eik;      /* RBS frontier storage, kept between calls */
-    int64_t collide_launches = 0;           /* d_small: list_count, work counters, overflow count */
     /* per-chunk work buffers: CKC_NUM_LANES independent sets, each with its own stream, so that the host entry points
      * can overlap the H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 */
     ckc_lane lanes[CKC_NUM_LANES];
@@ -452,6 +457,13 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
         if (!okt) { std::string msg = std::string("device upload: ") + cudaGetErrorString(cudaGetLastError()); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA; }
         ctx->world.pair_hits = ctx->d_pairhits.as<unsigned int>();
         ctx->world.pair_order = ctx->d_pairorder.as<int>();
+        for (int l = 0; l < CKC_NUM_LANES && okt; l++) {
+            ckc_lane& L = ctx->lanes[l];
+            okt = L.pairstat.reserve(2 * CKC_MAX_PAIRS * 4) == cudaSuccess &&
+                  cudaMemcpy(L.pair_hits(), prior.data(), CKC_MAX_PAIRS * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(L.pair_order(), ord.data(), CKC_MAX_PAIRS * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+        if (!okt) { std::string msg = std::string("device upload: ") + cudaGetErrorString(cudaGetLastError()); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA; }
     }
     const char* ch = getenv("CKC_CHUNK");
     if (ch && atoll(ch) >= 1024) ctx->chunk = atoll(ch);
@@ -533,13 +545,15 @@ static int run_collision_stage(ckc_ctx* ctx, ckc_lane& L, int64_t m_max, const d
     const bool hop = ctx->overlap && st == L.st && L.st_hi;
     cudaStream_t lane_st = st;
     if (hop) { CU(cudaEventRecord(L.ev_p, st)); CU(cudaStreamWaitEvent(L.st_hi, L.ev_p, 0)); st = L.st_hi; }
+    ckc_world_dev w = ctx->world;                 /* by-value launch argument: this lane's pair statistics */
+    w.pair_hits = L.pair_hits(); w.pair_order = L.pair_order();
     { stage_scope ts(ctx, st, 1);
-      ckc_launch_link_frames(ctx->world, d_q, l, d_list, d_m, m_max, L.frames.as<double>(), st); }
+      ckc_launch_link_frames(w, d_q, l, d_list, d_m, m_max, L.frames.as<double>(), st); }
     ckc_launch_cfg cfg = { ctx->num_sms };
     /* refresh the processing order from the hit statistics now and then (a 1-block kernel on the same stream) */
-    if ((ctx->collide_launches++ & 7) == 7) { ckc_launch_update_pair_order(ctx->world, ctx->d_pairorder.as<int>(), st); ctx->launches++; }
+    if ((L.collide_launches++ & 7) == 7) { ckc_launch_update_pair_order(w, L.pair_order(), st); ctx->launches++; }
     { stage_scope ts(ctx, st, 2);
-      ckc_launch_collide(ctx->world, cfg, L.frames.as<double>(), d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, L.work_counter(),
+      ckc_launch_collide(w, cfg, L.frames.as<double>(), d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, L.work_counter(),
                          L.ovf.as<int32_t>(), L.ovf_count(), L.bigstack.as<uint32_t>(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
     ctx->launches += 3;
     CU(cudaGetLastError());
