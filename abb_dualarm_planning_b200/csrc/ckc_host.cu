@@ -535,14 +535,14 @@ static ckc_layout soa(int64_t n) { ckc_layout l = { 1, n }; return l; }
 
 /* K2 + K3 on the configurations listed in d_list (count on the device), scratch of lane L, stream st */
 static int run_collision_stage(ckc_ctx* ctx, ckc_lane& L, int64_t m_max, const double* d_q, ckc_layout l, const int32_t* d_list, const int32_t* d_m,
-                               uint8_t* d_hit, uint8_t* d_valid, uint8_t* d_pair_flags, cudaStream_t st) {
+                               uint8_t* d_hit, uint8_t* d_valid, uint8_t* d_pair_flags, cudaStream_t st, bool allow_hop = true) {
     if (m_max <= 0) return CKC_OK;
     CU(L.frames.reserve((size_t)m_max * CKC_FRAME_DOUBLES * 8));
     CU(L.ovf.reserve((size_t)m_max * 4));
     CU(L.bigstack.reserve((size_t)16 * 8 * 65536 * 4));
     /* on the lane's own stream the collision stage moves to the lane's HIGH-PRIORITY stream: its blocks then win the SM slots
      * that free up while the persistent projection kernels of the other lanes are still queued */
-    const bool hop = ctx->overlap && st == L.st && L.st_hi;
+    const bool hop = allow_hop && ctx->overlap && st == L.st && L.st_hi;      /* RBS levels run alone: no hop, four stream operations less per level */
     cudaStream_t lane_st = st;
     if (hop) { CU(cudaEventRecord(L.ev_p, st)); CU(cudaStreamWaitEvent(L.st_hi, L.ev_p, 0)); st = L.st_hi; }
     ckc_world_dev w = ctx->world;                 /* by-value launch argument: this lane's pair statistics */
@@ -1017,7 +1017,7 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
          * (one host synchronisation per level); large levels read it back and run bounded sub-batches */
         int32_t h[2];
         if (nseg <= (1 << 20)) {
-            int rc = run_collision_stage(ctx, L, nseg, pool.as<double>(), AOS, r.cand_node, d_cnt, hit.as<uint8_t>(), nullptr, nullptr, st);
+            int rc = run_collision_stage(ctx, L, nseg, pool.as<double>(), AOS, r.cand_node, d_cnt, hit.as<uint8_t>(), nullptr, nullptr, st, false);
             if (rc) return rc;
             { stage_scope ts(ctx, st, 3);
               ckc_launch_rbs_push(r, (int)nseg, d_cnt, hit.as<uint8_t>(), st); }
@@ -1026,7 +1026,7 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
             CU(cudaStreamSynchronize(st));
             const int64_t sub = 1 << 20;
             for (int64_t off = 0; off < h[0]; off += sub) {
-                int rc = run_collision_stage(ctx, L, std::min<int64_t>(sub, h[0] - off), pool.as<double>(), AOS, r.cand_node + off, nullptr, hit.as<uint8_t>(), nullptr, nullptr, st);
+                int rc = run_collision_stage(ctx, L, std::min<int64_t>(sub, h[0] - off), pool.as<double>(), AOS, r.cand_node + off, nullptr, hit.as<uint8_t>(), nullptr, nullptr, st, false);
                 if (rc) return rc;
             }
             { stage_scope ts(ctx, st, 3);
