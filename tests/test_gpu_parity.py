@@ -114,6 +114,25 @@ def test_empty_and_tiny_batches(ck, oracle):
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
 
 
+def test_nan_configurations(ck, oracle, gold):
+    """NaN joints (the reference's sqrt(1 - s^2) hair): they pass every joint-limit test, and PQP's TriDist
+    falls through to its "triangles overlap -> 0" return, so the reference binary reports them IN COLLISION (checked through
+    the binary: oracle/refshim.py collide -> 1).  The device must agree and must not get lost in the traversal."""
+    g = gold("rbs.npz")
+    q = g["qa"][:6].copy()
+    q[0, 3] = np.nan; q[1, 9] = np.nan; q[2, 0] = np.nan; q[3, 6] = np.nan; q[4, :] = np.nan
+    want = oracle.collision_state(q)
+    assert want.tolist() == [1, 1, 1, 1, 1, 0]
+    assert (ck.collide(q) == want).all()
+    assert (ck.check_angle_limits(q) == oracle.check_angle_limits(q)).all()
+    ik = g["ik"][:6]
+    ok, valid, _ = ck.pcs_validate(q, 0, ik)
+    ok_o, valid_o, _ = oracle.pcs_validate(q, 0, ik)
+    assert (ok == ok_o).all() and (valid == valid_o).all()
+    v = ck.pcs_is_valid(q)
+    assert (v == oracle.pcs_is_valid_full(q)).all()
+
+
 def test_rbs_vs_reference_binary_golden(ck, gold):
     g = gold("rbs.npz")
     ok, nc = ck.pcs_check_motion_rbs(g["qa"], g["qb"], 0, g["ik"])
