@@ -171,7 +171,14 @@ static void sym_eig3(double A[3][3], double V[3][3]) {
 
 struct builder {
     host_mesh& m;
-    explicit builder(host_mesh& mm) : m(mm) {}
+    bool fit_refine, split_best, size_area, split_sah, fit_edges; int nfrac;
+    explicit builder(host_mesh& mm) : m(mm) {
+        /* bit 0: in-plane refit, 1: best-of-three split axis, 2: descend by surface area, 3: binned split positions, 4: edge-aligned candidates */
+        const char* e = getenv("CKC_BVH");
+        const int f = e ? atoi(e) : 31;
+        fit_refine = (f & 1) != 0; split_best = (f & 2) != 0; size_area = (f & 4) != 0; split_sah = (f & 8) != 0; fit_edges = (f & 16) != 0; nfrac = (f & 32) ? 5 : 3;
+    }
+    static double area(const ckc_node& n) { return (double)n.h[0] * n.h[1] + (double)n.h[2] * ((double)n.h[0] + n.h[1]); }
     const double* vert(int t, int v) const { return &m.tris[9 * (size_t)t + 3 * v]; }
 
     void fit(const std::vector<int>& idx, ckc_node& n, double axes[3][3]) {
@@ -196,6 +203,35 @@ struct builder {
             double e[3] = { fabs(a0[0]) < 0.9 ? 1.0 : 0.0, fabs(a0[0]) < 0.9 ? 0.0 : 1.0, 0 };
             a1[0] = a0[1] * e[2] - a0[2] * e[1]; a1[1] = a0[2] * e[0] - a0[0] * e[2]; a1[2] = a0[0] * e[1] - a0[1] * e[0];
             nrm(a1);
+        }
+        /* PCA fixes the plane of least spread well but not the rotation inside it: scan the in-plane angle for the smallest
+         * rectangle (for a single triangle that is the one standing on its longest edge, half the area a skewed box can have) */
+        if (fit_refine) {
+            double a2p[3] = { a0[1] * a1[2] - a0[2] * a1[1], a0[2] * a1[0] - a0[0] * a1[2], a0[0] * a1[1] - a0[1] * a1[0] };
+            const double* pca[3] = { a0, a1, a2p };
+            double best = 1e300, bu[3] = { a0[0], a0[1], a0[2] }, bv[3] = { a1[0], a1[1], a1[2] };
+            const int steps = 48;
+            /* fixed axis = the PCA axis of least spread; fit_edges: each of the three PCA axes in turn */
+            for (int fix = 2; fix >= (fit_edges ? 0 : 2); fix--) {
+                const double* e0 = pca[(fix + 1) % 3]; const double* e1 = pca[(fix + 2) % 3]; const double* n2 = pca[fix];
+                for (int k = 0; k < steps; k++) {
+                    const double th = (M_PI / 2) * k / steps, c = cos(th), sn = sin(th);
+                    double u[3], v[3];
+                    for (int i = 0; i < 3; i++) { u[i] = c * e0[i] + sn * e1[i]; v[i] = -sn * e0[i] + c * e1[i]; }
+                    double lu = 1e300, hu = -1e300, lv = 1e300, hv = -1e300, ln = 1e300, hn = -1e300;
+                    for (int t : idx) for (int vv = 0; vv < 3; vv++) {
+                        const double* pt = vert(t, vv);
+                        const double pu = pt[0] * u[0] + pt[1] * u[1] + pt[2] * u[2], pv = pt[0] * v[0] + pt[1] * v[1] + pt[2] * v[2];
+                        const double pn = pt[0] * n2[0] + pt[1] * n2[1] + pt[2] * n2[2];
+                        lu = std::min(lu, pu); hu = std::max(hu, pu); lv = std::min(lv, pv); hv = std::max(hv, pv); ln = std::min(ln, pn); hn = std::max(hn, pn);
+                    }
+                    /* surface area of the box (the traversal cost of a bounding volume scales with its area, not its volume) */
+                    const double du = hu - lu, dv = hv - lv, dn = hn - ln;
+                    const double cost = du * dv + dn * (du + dv);
+                    if (cost < best * (1 - 1e-9)) { best = cost; for (int i = 0; i < 3; i++) { bu[i] = u[i]; bv[i] = v[i]; } }
+                }
+            }
+            for (int i = 0; i < 3; i++) { a0[i] = bu[i]; a1[i] = bv[i]; }
         }
         /* the kernel rebuilds a2 = a0 x a1 from the FP32 copies: round first so that host extents match what it sees */
         float f0[3], f1[3];
@@ -222,7 +258,7 @@ struct builder {
         const double slack = 1e-3 + 4e-6 * (ext + cmag);
         for (int i = 0; i < 3; i++) { n.h[i] = (float)(0.5 * (hi[i] - lo[i]) + slack); n.c[i] = (float)cworld[i]; }
         for (int k = 0; k < 3; k++) { n.a0[k] = f0[k]; n.a1[k] = f1[k]; }
-        n.size2 = n.h[0] * n.h[0] + n.h[1] * n.h[1] + n.h[2] * n.h[2];
+        n.size2 = size_area ? (float)area(n) : n.h[0] * n.h[0] + n.h[1] * n.h[1] + n.h[2] * n.h[2];
         n.pad0 = n.pad1 = 0;
         for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) axes[i][k] = ax[i][k];
     }
@@ -232,18 +268,36 @@ struct builder {
         ckc_node n; memset(&n, 0, sizeof(n));
         fit(idx, n, axes);
         if (idx.size() == 1) { n.child = ~idx[0]; m.nodes[self] = n; return; }
+        /* median split by triangle centroid along a box axis: the longest one, or (split_best) the one of the three whose two
+         * child boxes have the smallest total surface area */
         int axis = 0; if (n.h[1] > n.h[axis]) axis = 1; if (n.h[2] > n.h[axis]) axis = 2;
-        const double* a = axes[axis];
-        std::vector<std::pair<double, int>> key(idx.size());
-        for (size_t i = 0; i < idx.size(); i++) {
-            double c = 0;
-            for (int v = 0; v < 3; v++) { const double* p = vert(idx[i], v); c += p[0] * a[0] + p[1] * a[1] + p[2] * a[2]; }
-            key[i] = { c, idx[i] };
-        }
-        std::sort(key.begin(), key.end());
-        const size_t half = idx.size() / 2;
         std::vector<int> L, R;
-        for (size_t i = 0; i < key.size(); i++) (i < half ? L : R).push_back(key[i].second);
+        auto split = [&](int ax, std::vector<int>& l, std::vector<int>& r, double frac = 0.5) {
+            const double* a = axes[ax];
+            std::vector<std::pair<double, int>> key(idx.size());
+            for (size_t i = 0; i < idx.size(); i++) {
+                double c = 0;
+                for (int v = 0; v < 3; v++) { const double* p = vert(idx[i], v); c += p[0] * a[0] + p[1] * a[1] + p[2] * a[2]; }
+                key[i] = { c, idx[i] };
+            }
+            std::sort(key.begin(), key.end());
+            const size_t half = std::max<size_t>(1, std::min<size_t>(idx.size() - 1, (size_t)(idx.size() * frac)));
+            l.clear(); r.clear();
+            for (size_t i = 0; i < key.size(); i++) (i < half ? l : r).push_back(key[i].second);
+        };
+        if (split_best && idx.size() > 2) {
+            double best = 1e300;
+            const double fr[5] = { 0.5, 0.375, 0.625, 0.25, 0.75 };
+            for (int ax = 0; ax < 3; ax++)
+                for (int f = 0; f < (split_sah && idx.size() >= 8 ? nfrac : 1); f++) {
+                    std::vector<int> l, r; split(ax, l, r, fr[f]);
+                    ckc_node nl, nr; double tmp[3][3];
+                    memset(&nl, 0, sizeof(nl)); memset(&nr, 0, sizeof(nr));
+                    fit(l, nl, tmp); fit(r, nr, tmp);
+                    const double cost = split_sah ? area(nl) * l.size() + area(nr) * r.size() : area(nl) + area(nr);
+                    if (cost < best) { best = cost; L.swap(l); R.swap(r); }
+                }
+        } else split(axis, L, R);
         const int child = (int)m.nodes.size();
         m.nodes.resize(m.nodes.size() + 2);          /* siblings are adjacent: right = left + 1 */
         n.child = child;
@@ -436,7 +490,11 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
             const ckc_pair& pr = ctx->world.pairs[p];
             pt[p].node_a = ctx->world.node_off[pr.mesh_a]; pt[p].node_b = ctx->world.node_off[pr.mesh_b];
             pt[p].tri_a = ctx->world.tri_off[pr.mesh_a]; pt[p].tri_b = ctx->world.tri_off[pr.mesh_b];
-            pt[p].frame_a = pr.frame_a; pt[p].frame_b = pr.frame_b; pt[p].pad0 = pt[p].pad1 = 0;
+            pt[p].frame_a = pr.frame_a; pt[p].frame_b = pr.frame_b; pt[p].pad1 = 0;
+            /* root pre-test of k_collide: two spheres around the root boxes; radius sum + tolerance + FP32 slack, as float bits */
+            auto radius = [&](int mesh) { const ckc_node& r = ctx->meshes[mesh].nodes[0]; return sqrt((double)r.h[0] * r.h[0] + (double)r.h[1] * r.h[1] + (double)r.h[2] * r.h[2]); };
+            const float rsum = (float)((radius(pr.mesh_a) + radius(pr.mesh_b) + ctx->world.cull_tol) * (1 + 1e-5) + 2e-3);
+            memcpy(&pt[p].pad0, &rsum, 4);
         }
         bool okt = ctx->d_pairtab.reserve(pt.size() * sizeof(ckc_pair_dev)) == cudaSuccess && ctx->d_static.reserve(sizeof(ctx->world.static_frames)) == cudaSuccess &&
                    cudaMemcpy(ctx->d_pairtab.p, pt.data(), pt.size() * sizeof(ckc_pair_dev), cudaMemcpyHostToDevice) == cudaSuccess &&

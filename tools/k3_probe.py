@@ -11,13 +11,14 @@ name, v = sys.argv[1], sys.argv[2]
 os.environ[name] = v
 import numpy as np
 from abb_dualarm_planning_b200 import Checker, sampling
-ck = Checker(1)
+import time
+_t0 = time.time(); ck = Checker(1); print('%s=%s create %.2f s' % (name, v, time.time() - _t0))
 q, ik = sampling.sample_pcs(1, 0, 4_000_000)
 ok, qo = ck.pcs_project(q, 0, ik)
 feas = qo[ok == 1]                                   # ~95k IK-feasible configurations, half of them colliding
 hit = ck.collide(feas)
 free = feas[hit == 0]
-for label, arr in (("feasible", feas), ("free", free), ("feas31k", feas[:31500]), ("feas8k", feas[:8000]), ("feas2k", feas[:2000])):
+for label, arr in (("feasible", feas), ("free", free), ("feas31k", feas[:31500])):
     for _ in range(2): ck.collide(arr)
     ck.reset_stats(); ck.set_stage_timing(True)
     for _ in range(5): h = ck.collide(arr)
