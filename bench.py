@@ -321,6 +321,11 @@ def run_native(args):
             flop_launch = flop_cfg * cfgs
         dur = kms / max(kl, 1) * 1e-3
         achieved = flop_launch / dur / 1e12 if dur > 0 else 0.0
+        # the same kernel by the work it actually executed (own counters): K3 prunes far harder than PQP's 116 full queries, so the
+        # contract figure above (PQP's work per configuration) can exceed the peak; this one cannot
+        executed = None
+        if wl != "gd" and dur > 0:
+            executed = (300.0 * stats["bv_tests"] + 1000.0 * stats["tri_tests"]) / max(kl, 1) / dur / 1e12
         traffic, traffic_src = None, None
         try:        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture
             tr = json.load(open(os.path.join(REPO, "profiles", "r1_traffic.json")))[kern]
@@ -331,6 +336,7 @@ def run_native(args):
         share = {k: round(v["ms"] / max(ms_serial, 1e-9), 4) for k, v in stages.items()}
         out["roofline"] = {"bound": "fp64", "kernel": kern, "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
                            "frac": achieved / peak64 if peak64 else None, "traffic": traffic, "traffic_source": traffic_src,
+                           "achieved_executed_work": executed, "frac_executed_work": (executed / peak64 if executed is not None and peak64 else None),
                            "peak_source": "FP64 FMA-chain peak measured live by ckc_measure_fma_peak (MEASURED_PEAKS.json has HBM/bf16 only; FP32 FMA peak %.1f TFLOP/s)" % peak32,
                            "work_model": "algorithmic flop of the reference path (SURVEY 8d): GD 2600 flop x measured Newton iterations; collision 300 flop x (116 + n_bv) + 1000 flop x n_tri with PQP counters of tests/golden/work_model.json",
                            "kernel_ms_per_launch": kms / max(kl, 1), "stage_share_of_step": share,
@@ -371,6 +377,9 @@ def run_native(args):
         dur = stages["collide"]["ms"] * 1e-3
         out["roofline"] = {"bound": "fp64", "kernel": "k_collide", "achieved": flop / dur / 1e12 if dur else 0.0, "peak": peak64, "unit": "TFLOP/s",
                            "frac": (flop / dur / 1e12) / peak64 if dur and peak64 else None, "traffic": None,
+                           "achieved_executed_work": ((300.0 * stats["bv_tests"] + 1000.0 * stats["tri_tests"]) / dur / 1e12) if dur else None,
+                           "frac_executed_work": ((300.0 * stats["bv_tests"] + 1000.0 * stats["tri_tests"]) / dur / 1e12 / peak64) if dur and peak64 else None,
+                           "work_model": "contract figure: PQP's work per configuration (300 flop x (116 + n_bv) + 1000 flop x n_tri, counters of tests/golden/work_model.json) -- it can exceed the peak because k_collide prunes far harder than PQP's 116 full queries; *_executed_work uses the kernel's own test counters",
                            "stage_share_of_step": {k: round(v["ms"] / (1e3 * t), 4) for k, v in stages.items()}}
         out["path_stats"] = {"edges_ok_fraction": okc / n, "checks_per_edge": stats["collision_calls"] / (K * n)}
 
