@@ -149,6 +149,8 @@ struct collide_args {
     int32_t* ovf_count;
     uint32_t* big_stack;         /* overflow path: per-warp global stacks */
     ckc_counters_dev* ctr;
+    int deep4;                   /* interpenetrating box pairs split both boxes at once (4 children) */
+    float deep_gap;              /* face-axis gap below which a box pair counts as interpenetrating (children pushed on top) */
     int count_rounds;            /* debug: the bv / tri counters count ROUNDS (warp steps) instead of tests */
     int wide_cnt;                /* rounds with at most this many tasks split BOTH boxes of a task (4 children) */
 };
@@ -304,7 +306,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
             /* ---- box tests, one task per lane ---- */
             const int cnt = top < 32 ? top : 32;
             const bool active = lane < cnt;
-            bool expand = false, expand4 = false, leafpair = false, likely = false;
+            bool expand = false, expand4 = false, leafpair = false, likely = false, deep = false;
             const bool wide = cnt <= a.wide_cnt;       /* few tasks in flight: idle lanes are free, halve the number of descent rounds */
             uint32_t c0 = 0, c1 = 0, tt = 0;
             if (active) {
@@ -323,12 +325,13 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                             leafpair = true; tt = ((uint32_t)p << 20) | ((uint32_t)(~A.child) << 10) | (uint32_t)(~B.child);
                             likely = gap6 < 0.25f * w.cull_tol;       /* the two triangles' boxes are within ~2 mm along every face axis */
                         }
-                        else if (wide && A.child >= 0 && B.child >= 0) {
+                        else if ((wide || (a.deep4 && gap6 < a.deep_gap)) && A.child >= 0 && B.child >= 0) {
                             expand4 = true;
                             c0 = ((uint32_t)p << 22) | ((uint32_t)A.child << 11) | (uint32_t)B.child;
                         }
                         else {
                             expand = true;
+                            deep = gap6 < a.deep_gap;                 /* the boxes interpenetrate along every face axis */
                             if (B.child < 0 || (A.child >= 0 && A.size2 > B.size2)) {       /* descend the larger box */
                                 c0 = ((uint32_t)p << 22) | ((uint32_t)A.child << 11) | (uint32_t)nb;
                                 c1 = c0 + (1u << 11);
@@ -349,9 +352,14 @@ k_collide(const ckc_world_dev w, const collide_args a) {
             const unsigned m4 = __ballot_sync(0xffffffffu, expand4);
             if (leafpair) triq[ntri + __popc(mt & lt_mask)] = tt;
             ntri += __popc(mt);
+            /* children of interpenetrating boxes go on top of the others: they are popped first, which takes a colliding
+             * configuration to its hit in fewer rounds (any order gives the same boolean) */
+            const unsigned md = __ballot_sync(0xffffffffu, expand && deep);
             const int npush = 2 * __popc(me) + 4 * __popc(m4);
             if (top + npush > cap) { overflow = true; break; }
-            const int pos = top + 2 * __popc(me & lt_mask) + 4 * __popc(m4 & lt_mask);
+            const unsigned mshallow = me & ~md;
+            int pos = top + 4 * __popc(m4 & lt_mask);
+            if (expand) pos = top + 4 * __popc(m4) + (deep ? 2 * __popc(mshallow) + 2 * __popc(md & lt_mask) : 2 * __popc(mshallow & lt_mask));
             if (expand) { stack[pos] = c1; stack[pos + 1] = c0; }
             if (expand4) { stack[pos] = c0 + (1u << 11) + 1u; stack[pos + 1] = c0 + (1u << 11); stack[pos + 2] = c0 + 1u; stack[pos + 3] = c0; }
             top += npush;
@@ -415,10 +423,14 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     a.frames = frames; a.list = list; a.d_m = d_m; a.m_max = m_max; a.hit_out = hit_out; a.valid_out = valid_out; a.pair_flags = pair_flags;
     a.work_counter = work_counter; a.ovf_list = ovf_list; a.ovf_count = ovf_count; a.big_stack = big_stack; a.ctr = ctr;
     /* tuning / debug knobs, read once (function-local statics: initialisation is thread safe, contexts may live on several threads) */
-    static const int wide_cnt = [] { const char* e = getenv("CKC_WIDE_CNT"); return e ? atoi(e) : 16; }();
+    static const int wide_cnt = [] { const char* e = getenv("CKC_WIDE_CNT"); return e ? atoi(e) : 8; }();
     static const int count_rounds = [] { const char* e = getenv("CKC_COUNT_ROUNDS"); return e ? atoi(e) : 0; }();
+    static const float deep_gap = [] { const char* e = getenv("CKC_DEEP_GAP"); return e ? (float)atof(e) : 0.0f; }();
     a.wide_cnt = wide_cnt;
     a.count_rounds = count_rounds;
+    a.deep_gap = deep_gap;
+    static const int deep4 = [] { const char* e = getenv("CKC_DEEP4"); return e ? atoi(e) : 1; }();
+    a.deep4 = deep4;
     /* work_counter[0] main pass, [1] overflow pass; the overflow count sits right behind them in the lanes' scratch block */
     if (ovf_count == work_counter + 2) cudaMemsetAsync(work_counter, 0, 3 * sizeof(int32_t), st);
     else { cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st); cudaMemsetAsync(ovf_count, 0, sizeof(int32_t), st); }
