@@ -492,7 +492,15 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
             pt[p].tri_a = ctx->world.tri_off[pr.mesh_a]; pt[p].tri_b = ctx->world.tri_off[pr.mesh_b];
             pt[p].frame_a = pr.frame_a; pt[p].frame_b = pr.frame_b; pt[p].pad1 = 0;
             /* root pre-test of k_collide: two spheres around the root boxes; radius sum + tolerance + FP32 slack, as float bits */
-            auto radius = [&](int mesh) { const ckc_node& r = ctx->meshes[mesh].nodes[0]; return sqrt((double)r.h[0] * r.h[0] + (double)r.h[1] * r.h[1] + (double)r.h[2] * r.h[2]); };
+            auto radius = [&](int mesh) {          /* smallest sphere about the root box centre that holds every vertex (<= |half extents|) */
+                const host_mesh& hm = ctx->meshes[mesh]; const ckc_node& r = hm.nodes[0];
+                double r2 = 0;
+                for (size_t v = 0; v + 2 < hm.tris.size(); v += 3) {
+                    const double dx = hm.tris[v] - r.c[0], dy = hm.tris[v + 1] - r.c[1], dz = hm.tris[v + 2] - r.c[2];
+                    r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+                }
+                return sqrt(r2);
+            };
             const float rsum = (float)((radius(pr.mesh_a) + radius(pr.mesh_b) + ctx->world.cull_tol) * (1 + 1e-5) + 2e-3);
             memcpy(&pt[p].pad0, &rsum, 4);
         }

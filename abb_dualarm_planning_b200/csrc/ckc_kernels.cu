@@ -149,6 +149,8 @@ struct collide_args {
     int32_t* ovf_count;
     uint32_t* big_stack;         /* overflow path: per-warp global stacks */
     ckc_counters_dev* ctr;
+    int flush_n;                 /* queued triangle pairs that trigger a drain of the queue */
+    float likely_gap;            /* face-axis gap below which a leaf pair is tested at once */
     int deep4;                   /* interpenetrating box pairs split both boxes at once (4 children) */
     float deep_gap;              /* face-axis gap below which a box pair counts as interpenetrating (children pushed on top) */
     int count_rounds;            /* debug: the bv / tri counters count ROUNDS (warp steps) instead of tests */
@@ -273,7 +275,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
         __syncwarp();
 
         while (!hit) {
-            if (ntri > 0 && (draining || ntri >= 6 || top == 0 || hot)) {
+            if (ntri > 0 && (draining || ntri >= a.flush_n || top == 0 || hot)) {
                 hot = false; draining = ntri > 3;
                 /* ---- exact triangle tests: three pairs per step, nine lanes (one per edge pair) each ---- */
                 const int g = lane / 9;
@@ -323,7 +325,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                     if (!far) {
                         if (A.child < 0 && B.child < 0) {
                             leafpair = true; tt = ((uint32_t)p << 20) | ((uint32_t)(~A.child) << 10) | (uint32_t)(~B.child);
-                            likely = gap6 < 0.25f * w.cull_tol;       /* the two triangles' boxes are within ~2 mm along every face axis */
+                            likely = gap6 < a.likely_gap;             /* the two triangles' boxes are within ~2 mm along every face axis */
                         }
                         else if ((wide || (a.deep4 && gap6 < a.deep_gap)) && A.child >= 0 && B.child >= 0) {
                             expand4 = true;
@@ -431,6 +433,9 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     a.deep_gap = deep_gap;
     static const int deep4 = [] { const char* e = getenv("CKC_DEEP4"); return e ? atoi(e) : 1; }();
     a.deep4 = deep4;
+    static const int flush_n = [] { const char* e = getenv("CKC_FLUSH_N"); return e ? atoi(e) : 6; }();
+    static const float likely_gap = [] { const char* e = getenv("CKC_LIKELY_GAP"); return e ? (float)atof(e) : 2.0125f; }();
+    a.flush_n = flush_n; a.likely_gap = likely_gap;
     /* work_counter[0] main pass, [1] overflow pass; the overflow count sits right behind them in the lanes' scratch block */
     if (ovf_count == work_counter + 2) cudaMemsetAsync(work_counter, 0, 3 * sizeof(int32_t), st);
     else { cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st); cudaMemsetAsync(ovf_count, 0, sizeof(int32_t), st); }
