@@ -299,7 +299,7 @@ def run_native(args):
         n_valid_host = int(nv.value)
         h2d = n * 96 + (n if wl == "pcs" else 0)
         out["e2e"] = {"value": world * K * n / e2e["compact"], "unit": "configs/s", "h2d_bytes_per_step": h2d,
-                      "d2h_bytes_per_step": n + 8 + (n // (1 << 17) + 1) * ((1 << 17) // 20 + 1024) * 100,
+                      "d2h_bytes_per_step": n + 8 + d2h_compact_bytes(n),
                       "api": "ckc_%s_validate_compact (mask + index and projected configuration of the valid samples), pinned host buffers" % wl,
                       "valid_last_step": n_valid_host, "checksum_valid_last_step": int(h_valid.sum().item()),
                       "full_output": {"value": world * K * n / e2e["full"], "d2h_bytes_per_step": n * 96 + n + (n if wl == "pcs" else 0),
@@ -458,6 +458,14 @@ def extra_measurements(ck, sampling, torch, dev, stream):
     except Exception as e:       # an extra, never the metric
         ex["cbirrt_pcs_note"] = "not run: %r" % (e,)
     return ex
+
+
+def d2h_compact_bytes(n):
+    """bytes the compact entry points copy back besides the mask: per pipeline chunk a count and a fixed-size prefix (5 % of the
+    chunk + 1024 entries of index + configuration), the chunking of project_host in csrc/ckc_host.cu"""
+    c = max(1, min(1 << 18, max(min(n, 1 << 16), (n + 3) // 4)))
+    nchunks = (n + c - 1) // c
+    return nchunks * (4 + (c // 20 + 1024) * 100)
 
 
 # ------------------------------------------------------------------------------------------------------------------
