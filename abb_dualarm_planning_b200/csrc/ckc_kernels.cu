@@ -4,13 +4,15 @@
  *   k_pcs_project   K1  one thread per sample: FK(active arm) -> closure target -> one analytic IK branch -> joint
  *                       limits; FP64 in registers; warp-aggregated append of the IK-feasible samples to a work list.
  *   k_link_frames   K2  one thread per feasible configuration: the 18 configuration-dependent link frames (FP64).
- *   k_collide       K3  one WARP per feasible configuration: warp-cooperative traversal of the OBB hierarchies of
- *                       the pair table with a shared-memory task stack; FP32 conservative box culling (guard band),
- *                       warp-cooperative FP64 PQP-exact triangle distance at the leaves (9 lanes per triangle pair),
- *                       __ballot_sync early-out on the first hit, adaptive pair order.
+ *   k_collide       K3  one WARP per feasible configuration: sphere pre-test of the 116 root pairs, then warp-cooperative
+ *                       traversal of the OBB hierarchies with a shared-memory task stack; FP32 conservative box culling
+ *                       (guard band), interpenetrating pairs first and split four ways, warp-cooperative FP64 PQP-exact
+ *                       triangle distance at the leaves (9 lanes per triangle pair), __ballot_sync early-out on the first
+ *                       hit, adaptive per-lane pair order.
  *   k_gd_project    K5  persistent grid with lane-level work stealing: Jacobian-free two-walk Newton iteration (kdl::GD);
  *   k_gd_finish         dense post-processing, joint limits, work-list append.
  *   k_rbs_expand / k_rbs_push  K4: one level of the recursive-bisection frontier.
+ *   k_isvalid_prepare / k_isvalid_combine: isValid(const ob::State*) around K2 / K3.
  *   k_rx_check, k_limits, k_identify_ik, k_compact_valid, k_update_pair_order, k_fma_peak, k_transpose: helpers.
  */
 #include "ckc_device.cuh"
