@@ -965,21 +965,25 @@ extern "C" int ckc_measure_fma_peak(ckc_ctx* ctx, int precision, double* tflops)
     CU(cudaSetDevice(ctx->device));
     ckc_lane& L = ctx->lanes[0];
     CU(L.aux.reserve(64));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t err = cudaEventCreate(&e0);
+    if (err == cudaSuccess) err = cudaEventCreate(&e1);
     const int iters = precision == 64 ? 1 << 15 : 1 << 16;
     double best = 0;
-    for (int rep = 0; rep < 4; rep++) {
-        CU(cudaEventRecord(e0, ctx->stream));
+    for (int rep = 0; rep < 4 && err == cudaSuccess; rep++) {
+        err = cudaEventRecord(e0, ctx->stream);
         ckc_launch_fma_peak(precision, ctx->num_sms, iters, L.aux.as<float>(), ctx->stream);
-        CU(cudaEventRecord(e1, ctx->stream));
-        CU(cudaEventSynchronize(e1));
-        float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (err == cudaSuccess) err = cudaEventRecord(e1, ctx->stream);
+        if (err == cudaSuccess) err = cudaEventSynchronize(e1);
+        float ms = 0;
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
         const double flop = 2.0 * 8.0 * iters * 1024.0 * 2.0 * ctx->num_sms;
-        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+        if (err == cudaSuccess && rep > 0 && ms > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
     }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (err != cudaSuccess) return fail(ctx, CKC_ERR_CUDA, std::string("fma peak probe: ") + cudaGetErrorString(err));
     ctx->launches += 4;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     *tflops = best;
     return CKC_OK;
 }
