@@ -123,3 +123,35 @@ def test_rss_dropin_class(tmp_path, oracle):
             assert rbs == int(_singular_rbs_oracle(oracle, a, b, 1, ida[1]))
             n_rbs += 1
     assert n_rbs >= 1
+
+
+def test_hb_dropin_class(tmp_path, oracle):
+    """hybrid flavour (StateValidityCheckerHB): GD projection + collision, then identify_state_ik and the APC local connection"""
+    from abb_dualarm_planning_b200 import sampling
+    qs = sampling.sample_gd(51, 0, 40000)
+    v, qp = oracle.gd_validate(qs)
+    seeds = qs[v == 1][:40]                                   # seeds whose projection is valid
+    rng = np.random.default_rng(7)
+    qa = seeds; qb = oracle.gd_validate(seeds)[1] + rng.normal(size=seeds.shape) * 0.05      # a second seed next to the projected point
+    inp, out = str(tmp_path / "in.txt"), str(tmp_path / "out.txt")
+    with open(inp, "w") as f:
+        f.write("%d\n" % len(qa))
+        for a, b in zip(qa, qb):
+            f.write(" ".join(repr(float(x)) for x in a) + " " + " ".join(repr(float(x)) for x in b) + "\n")
+    _run("test_dropin_hb", inp, out)
+    lines = open(out).read().strip().split("\n")
+    res = np.array([[float(x) for x in ln.split()] for ln in lines[:len(qa)]])
+    va_o, pa = oracle.gd_validate(qa); vb_o, pb = oracle.gd_validate(qb)
+    assert (res[:, 0] == va_o).all() and (res[:, 1] == vb_o).all() and va_o.sum() >= 30
+    both = (va_o == 1) & (vb_o == 1)
+    ida = oracle.identify_state_ik(pa[both]); idb = oracle.identify_state_ik(pb[both])
+    assert (res[both][:, 2:4] == ida).all() and (res[both][:, 4:6] == idb).all()
+    d = np.abs(res[both][:, 7:19] - pa[both]); d = np.minimum(d, np.abs(d - 2 * 3.1416))
+    assert (d.max(axis=1) < 2e-5).mean() >= 0.95
+    same = both.copy(); same[both] = (ida[:, 0] >= 0) & (ida[:, 0] == idb[:, 0])
+    ia = oracle.identify_state_ik(pa[same])[:, 0].astype(np.int8)
+    # the class ran the bisection on ITS projected points; the oracle's agree to ~1e-6, which does not move an RBS answer off a knife edge here
+    rbs_o, _ = oracle.pcs_check_motion_rbs(pa[same], pb[same], 0, ia)
+    assert (res[same][:, 6] == rbs_o).mean() >= 0.95 and same.sum() >= 10
+    s = np.array([float(x) for x in lines[len(qa)].split()[1:]])
+    assert oracle.gd_validate(s[None])[0][0] == 1             # the GD sampler returns a valid (closed, in limits, collision free) point
