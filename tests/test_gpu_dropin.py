@@ -155,3 +155,42 @@ def test_hb_dropin_class(tmp_path, oracle):
     assert (res[same][:, 6] == rbs_o).mean() >= 0.95 and same.sum() >= 10
     s = np.array([float(x) for x in lines[len(qa)].split()[1:]])
     assert oracle.gd_validate(s[None])[0][0] == 1             # the GD sampler returns a valid (closed, in limits, collision free) point
+
+
+def _rx_rbs_oracle(oracle, a, b, eps, depth=0):
+    """RX.cpp:216-243 restated with oracle primitives: the midpoint is NOT projected, only tested"""
+    if np.linalg.norm(a - b) < 0.05:
+        return True
+    if depth > 150:
+        return False
+    m = (a + b) / 2
+    ok, _ = oracle.rx_check(m[None], eps)
+    if not (ok[0] and oracle.check_angle_limits(m[None])[0] and not oracle.collision_state(m[None])[0]):
+        return False
+    return _rx_rbs_oracle(oracle, a, m, eps, depth + 1) and _rx_rbs_oracle(oracle, m, b, eps, depth + 1)
+
+
+def test_rx_dropin_class(tmp_path, oracle, gold):
+    """relaxed-constraint flavour (StateValidityCheckerRX): residual test, validity, bisection over unprojected midpoints"""
+    g = gold("rx_confs_eps0.7.npz")
+    eps = 0.7 * (1 + 1e-4)
+    qa = g["q"][:60]
+    rng = np.random.default_rng(11)
+    qb = qa + rng.normal(size=qa.shape) * np.where(np.arange(60)[:, None] % 2 == 0, 0.01, 0.1)      # short and longer edges
+    inp, out = str(tmp_path / "in.txt"), str(tmp_path / "out.txt")
+    with open(inp, "w") as f:
+        f.write("%d\n" % len(qa))
+        for a, b in zip(qa, qb):
+            f.write(" ".join(repr(float(x)) for x in a) + " " + " ".join(repr(float(x)) for x in b) + "\n")
+    env = dict(os.environ, CKC_MESH_PATH=PACK)
+    r = subprocess.run([os.path.join(HOST, "test_dropin_rx"), repr(eps), inp, out], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = np.array([[int(x) for x in ln.split()] for ln in open(out).read().strip().split("\n")])
+    def valid(q):
+        ok, _ = oracle.rx_check(q, eps)
+        return ok & oracle.check_angle_limits(q) & (1 - oracle.collision_state(q).astype(np.uint8))
+    ok_a, _ = oracle.rx_check(qa, eps)
+    va, vb = valid(qa), valid(qb)
+    assert (res[:, 0] == ok_a).all() and (res[:, 1] == va).all() and (res[:, 2] == vb).all()
+    want = np.array([int(va[i] and vb[i] and _rx_rbs_oracle(oracle, qa[i], qb[i], eps)) for i in range(len(qa))])
+    assert (res[:, 3] == want).all() and 5 <= want.sum() < len(want)
