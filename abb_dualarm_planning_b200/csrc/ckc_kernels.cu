@@ -630,7 +630,7 @@ void ckc_launch_transpose(const double* src, ckc_layout ls, double* dst, ckc_lay
  * result and takes the next sample (one warp-aggregated atomicAdd per refill), so the spread of the iteration count
  * (median 9, max > 25) does not idle the other 31 lanes of its warp. */
 #ifndef CKC_GD_MINBLOCKS
-#define CKC_GD_MINBLOCKS 4
+#define CKC_GD_MINBLOCKS 5
 #endif
 template <bool seeded>
 __global__ void __launch_bounds__(CKC_GD_BLOCK, CKC_GD_MINBLOCKS)
