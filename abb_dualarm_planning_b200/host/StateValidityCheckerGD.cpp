@@ -65,18 +65,47 @@ State StateValidityChecker::sample_q() {
         for (int i = 0; i < B; i++) { if (v[i]) { sampling_counter[0]++; return State(q.begin() + 12 * i, q.begin() + 12 * i + 12); } sampling_counter[1]++; }
     }
 }
-bool StateValidityChecker::checkMotionRBS(State s1, State s2, int recursion_depth, int ndc) {
-    /* RX keeps the midpoint as is (no projection): host recursion over single-sample device checks, reference order */
-    double d = normDistance(s1, s2);
-    if (d < RBS_tol) return true;
-    if (recursion_depth > RBS_max_depth) return false;
+/* RX keeps every midpoint as is (no projection, RX.cpp:216-243), so the whole bisection tree of an edge is known from its end
+ * points: it is generated on the host with the reference's own arithmetic ((s1 + s2) / 2 per component, the d < RBS_tol and
+ * depth tests per segment) and validated in ONE batched call; the edge is valid iff every node is (the reference's depth-first
+ * early return visits fewer nodes of a failing edge, the boolean is the same). */
+static bool rx_tree(const State& s1, const State& s2, int depth, double tol, int max_depth, std::vector<double>& nodes, double (*dist)(const State&, const State&)) {
+    if (dist(s1, s2) < tol) return true;
+    if (depth > max_depth) return false;                      /* RX.cpp:225-226: this branch alone already fails the edge */
     State mid(12); for (int i = 0; i < 12; i++) mid[i] = (s1[i] + s2[i]) / 2;
-    if (!isValidRBS(mid)) return false;
-    return checkMotionRBS(s1, mid, recursion_depth + 1, ndc) && checkMotionRBS(mid, s2, recursion_depth + 1, ndc);
+    nodes.insert(nodes.end(), mid.begin(), mid.end());
+    if (nodes.size() > 12u * (1u << 22)) return false;        /* 4 M nodes: an edge of > 2e5 rad, never a planner edge */
+    return rx_tree(s1, mid, depth + 1, tol, max_depth, nodes, dist) & rx_tree(mid, s2, depth + 1, tol, max_depth, nodes, dist);
+}
+static double rx_dist(const State& a, const State& b) { double s = 0; for (size_t i = 0; i < a.size(); i++) s += pow(a[i] - b[i], 2); return sqrt(s); }
+
+bool StateValidityChecker::checkMotionRBS(State s1, State s2, int recursion_depth, int) {
+    std::vector<double> nodes;
+    const bool shape_ok = rx_tree(s1, s2, recursion_depth, RBS_tol, RBS_max_depth, nodes, rx_dist);
+    if (nodes.empty()) return shape_ok;
+    const size_t m = nodes.size() / 12;
+    std::vector<unsigned char> valid(m, 0);
+    ckc_rx_validate(ckc_.ctx(), (int64_t)m, nodes.data(), epsilon, valid.data(), nullptr);
+    isValid_counter += (int)m; IK_counter += (int)m;
+    bool all = shape_ok;
+    for (size_t i = 0; i < m; i++) all = all && valid[i] != 0;
+    return all;
 }
 void StateValidityChecker::checkMotionRBSBatch(const std::vector<State>& a, const std::vector<State>& b, std::vector<unsigned char>& ok) {
+    /* all trees of all edges in one call */
+    std::vector<double> nodes; std::vector<size_t> first(a.size() + 1, 0); std::vector<char> shape(a.size(), 0);
+    for (size_t e = 0; e < a.size(); e++) { first[e] = nodes.size() / 12; shape[e] = rx_tree(a[e], b[e], 0, RBS_tol, RBS_max_depth, nodes, rx_dist); }
+    first[a.size()] = nodes.size() / 12;
+    const size_t m = nodes.size() / 12;
+    std::vector<unsigned char> valid(m, 0);
+    if (m) ckc_rx_validate(ckc_.ctx(), (int64_t)m, nodes.data(), epsilon, valid.data(), nullptr);
+    isValid_counter += (int)m; IK_counter += (int)m;
     ok.assign(a.size(), 0);
-    for (size_t i = 0; i < a.size(); i++) ok[i] = checkMotionRBS(a[i], b[i], 0, 0);
+    for (size_t e = 0; e < a.size(); e++) {
+        bool all = shape[e] != 0;
+        for (size_t i = first[e]; i < first[e + 1]; i++) all = all && valid[i] != 0;
+        ok[e] = all ? 1 : 0;
+    }
 }
 #else
 bool StateValidityChecker::IKproject(State& q, bool includeObs) {
