@@ -341,7 +341,7 @@ def run_native(args):
                            "work_model": "algorithmic flop of the reference path (SURVEY 8d): GD 2600 flop x measured Newton iterations; collision 300 flop x (116 + n_bv) + 1000 flop x n_tri with PQP counters of tests/golden/work_model.json",
                            "kernel_ms_per_launch": kms / max(kl, 1), "stage_share_of_step": share,
                            "timing_note": "kernel durations from a second pass of the same K steps with ckc_set_overlap(0) (every kernel alone on the stream, %.3f ms/step); the timed region overlaps chunks (%.3f ms/step)" % (ms_serial / K, ms / K),
-                           "hbm_gbs_algorithmic": (per_step * 200.0) / (ms * 1e-3) / 1e9, "hbm_peak_gbs_measured": 6545.9}
+                           "hbm_gbs_algorithmic": (per_step * 200.0) / (ms * 1e-3) / 1e9, "hbm_peak_gbs_measured": measured_hbm_peak()}
         out["path_stats"] = {"newton_iters_mean": stats["gd_iterations"] / per_step if wl == "gd" else None,
                              "fraction_passing_projection": stats["ik_feasible"] / per_step,
                              "collision_checks_per_step": stats["collision_calls"] / K, "bv_tests_per_check": stats["bv_tests"] / max(stats["collision_calls"], 1),
@@ -458,6 +458,14 @@ def extra_measurements(ck, sampling, torch, dev, stream):
     except Exception as e:       # an extra, never the metric
         ex["cbirrt_pcs_note"] = "not run: %r" % (e,)
     return ex
+
+
+def measured_hbm_peak():
+    """HBM copy bandwidth of this pool's B200 from the driver-written MEASURED_PEAKS.json (GB/s); the profiling recipe's figure if absent"""
+    try:
+        return float(json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6545.9
 
 
 def d2h_compact_bytes(n):
