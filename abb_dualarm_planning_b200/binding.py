@@ -14,7 +14,8 @@ class CkcError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "csrc", "libckc.so")
+    """csrc/libckc.so; CKC_LIB names another build of the same library (kernel experiments on the GPU box)"""
+    return os.environ.get("CKC_LIB") or os.path.join(_HERE, "csrc", "libckc.so")
 
 
 class Stats(C.Structure):

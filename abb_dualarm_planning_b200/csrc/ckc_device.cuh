@@ -6,7 +6,7 @@
  *   fk_arm            two_robots::FKsolve_rob          proj_classes/apc_class.cpp:51-76
  *   ik_arm            two_robots::IKsolve_rob          proj_classes/apc_class.cpp:114-245
  *   project_passive   calc_specific_IK_solution_R1/R2  proj_classes/apc_class.cpp:356-389
- *   robot_frames      collision_state link frames      validity_checkers/collisionDetection.cpp:72-260
+ *   warp_link_frames  collision_state link frames      validity_checkers/collisionDetection.cpp:72-260 (one warp per configuration)
  *   tri_dist_coop     PQP v1.3 TriDist / SegPoints (external library used by collision_state), warp-cooperative
  */
 #ifndef CKC_DEVICE_CUH_
@@ -163,39 +163,61 @@ __device__ __forceinline__ bool within_limits(const ckc_kin_dev& k, const double
 }
 
 /* ---------------------------------------------------------------------------------------------------------------- */
-/* link frames of one robot for the collision meshes (collisionDetection.cpp:72-166 / :177-260).                      */
-/* out: 8 frames x 12 doubles: (R row-major, T) for base, link1..link6 and the EE/rod pose (R6, T7)                   */
+/* link frames of both robots for the collision meshes (collisionDetection.cpp:72-166 / :177-260), computed by the     */
+/* WARP that collides the configuration, straight into its shared-memory frame table (no HBM round trip):              */
+/*   lanes 0..11   sin / cos of joint `lane` (FP64), one joint each;                                                     */
+/*   lanes 0..5    "row lanes": lane = 3 * robot + row carries row `row` of that robot's running rotation and component  */
+/*                 `row` of its running translation along the chain -- MRot{Z,Y,Y,X,Y,X} only mix entries of one row,    */
+/*                 and T += R * offset only needs that row, so the three rows of a robot are independent.               */
+/* F64: [CKC_NUM_FRAMES][12] doubles (R row-major 9 + T 3): 8 frames per robot (base, link1..link6, EE / rod pose        */
+/* (R6, T7)), frames 16 / 17 = the two poses the reference's pair table mixes up (collisionDetection.cpp:373, :397,     */
+/* :415: robot-2 rotation with robot-1 translation of link 2 and vice versa).  base: [2][12] robot base frames.         */
+/* ALL 32 lanes must call this (shuffles inside).                                                                       */
 /* ---------------------------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ void store_frame(double* dst, const double* R, const double* T) {
-#pragma unroll
-    for (int i = 0; i < 9; i++) dst[i] = R[i];
-    dst[9] = T[0]; dst[10] = T[1]; dst[11] = T[2];
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
 }
-__device__ __forceinline__ void robot_frames(const double* R0, const double* T0, const double* q, double* out) {
-    double R[9], T[3], s, c;
-#pragma unroll
-    for (int i = 0; i < 9; i++) R[i] = R0[i];
-    T[0] = T0[0]; T[1] = T0[1]; T[2] = T0[2];
-    store_frame(out, R, T);                                               /* base */
-    T[0] += R[2] * 290.0; T[1] += R[5] * 290.0; T[2] += R[8] * 290.0;     /* T1 = T0 + R0 (0,0,145*2) */
-    sincos(q[0], &s, &c); post_rot_z(R, c, s);
-    store_frame(out + 12, R, T);                                          /* link1 (R1,T1) */
-    sincos(q[1], &s, &c); post_rot_y(R, c, s);
-    store_frame(out + 24, R, T);                                          /* link2 (R2,T2_t), T2 = T1 */
-    T[0] += R[2] * 270.0; T[1] += R[5] * 270.0; T[2] += R[8] * 270.0;     /* T3 = T2 + R2 (0,0,270) */
-    sincos(q[2], &s, &c); post_rot_y(R, c, s);
-    store_frame(out + 36, R, T);                                          /* link3 (R3,T3) */
-    T[0] += R[0] * 134.0 + R[2] * 70.0; T[1] += R[3] * 134.0 + R[5] * 70.0; T[2] += R[6] * 134.0 + R[8] * 70.0;   /* T4 */
-    sincos(q[3], &s, &c); post_rot_x(R, c, s);
-    store_frame(out + 48, R, T);                                          /* link4 (R4,T4) */
-    T[0] += R[0] * 168.0; T[1] += R[3] * 168.0; T[2] += R[6] * 168.0;     /* T5 */
-    sincos(q[4], &s, &c); post_rot_y(R, c, s);
-    store_frame(out + 60, R, T);                                          /* link5 (R5,T5) */
-    T[0] += R[0] * 66.0; T[1] += R[3] * 66.0; T[2] += R[6] * 66.0;        /* T6: 72 - 13/2 = 66 (integer division) */
-    sincos(q[5], &s, &c); post_rot_x(R, c, s);
-    store_frame(out + 72, R, T);                                          /* link6 (R6,T6) */
-    T[0] += R[0] * 66.0; T[1] += R[3] * 66.0; T[2] += R[6] * 66.0;        /* T7: 13/2 + 60 = 66 */
-    store_frame(out + 84, R, T);                                          /* EE and rod pose (R6,T7) */
+__device__ __forceinline__ void warp_link_frames(const double* __restrict__ base, double qj, int lane, double* F64) {
+    double sj = 0.0, cj = 1.0;
+    if (lane < 12) sincos(qj, &sj, &cj);
+    const int rob = lane >= 3 ? 1 : 0, row = lane - 3 * rob;
+    const bool rl = lane < 6;
+    double R0 = 0, R1 = 0, R2 = 0, T = 0;
+    if (rl) { const double* b = base + 12 * rob; R0 = b[3 * row]; R1 = b[3 * row + 1]; R2 = b[3 * row + 2]; T = b[9 + row]; }
+    double* out = F64 + 96 * rob;
+    auto put = [&](int f) { if (rl) { double* d = out + 12 * f; d[3 * row] = R0; d[3 * row + 1] = R1; d[3 * row + 2] = R2; d[9 + row] = T; } };
+    const int src = 6 * rob;
+    double c, s, a, b;
+    put(0);                                                               /* base */
+    T += R2 * 290.0;                                                      /* T1 = T0 + R0 (0,0,145*2) */
+    c = shfl_f64(cj, src); s = shfl_f64(sj, src);
+    a = R0; b = R1; R0 = a * c + b * s; R1 = b * c - a * s;               /* R1 = R0 Rz(q1) */
+    put(1);
+    c = shfl_f64(cj, src + 1); s = shfl_f64(sj, src + 1);
+    a = R0; b = R2; R0 = a * c - b * s; R2 = a * s + b * c;               /* R2 = R1 Ry(q2), T2 = T1 */
+    put(2);
+    if (rl) {                                                             /* the pair table's mixed-up link-2 poses */
+        double* mixR = F64 + 12 * (rob == 0 ? 17 : 16); double* mixT = F64 + 12 * (rob == 0 ? 16 : 17);
+        mixR[3 * row] = R0; mixR[3 * row + 1] = R1; mixR[3 * row + 2] = R2; mixT[9 + row] = T;
+    }
+    T += R2 * 270.0;                                                      /* T3 = T2 + R2 (0,0,270) */
+    c = shfl_f64(cj, src + 2); s = shfl_f64(sj, src + 2);
+    a = R0; b = R2; R0 = a * c - b * s; R2 = a * s + b * c;               /* R3 = R2 Ry(q3) */
+    put(3);
+    T += R0 * 134.0 + R2 * 70.0;                                          /* T4 */
+    c = shfl_f64(cj, src + 3); s = shfl_f64(sj, src + 3);
+    a = R1; b = R2; R1 = a * c + b * s; R2 = b * c - a * s;               /* R4 = R3 Rx(q4) */
+    put(4);
+    T += R0 * 168.0;                                                      /* T5 */
+    c = shfl_f64(cj, src + 4); s = shfl_f64(sj, src + 4);
+    a = R0; b = R2; R0 = a * c - b * s; R2 = a * s + b * c;               /* R5 = R4 Ry(q5) */
+    put(5);
+    T += R0 * 66.0;                                                       /* T6: 72 - 13/2 = 66 (integer division) */
+    c = shfl_f64(cj, src + 5); s = shfl_f64(sj, src + 5);
+    a = R1; b = R2; R1 = a * c + b * s; R2 = b * c - a * s;               /* R6 = R5 Rx(q6) */
+    put(6);
+    T += R0 * 66.0;                                                       /* T7: 13/2 + 60 = 66 */
+    put(7);                                                               /* EE and rod pose (R6, T7) */
 }
 
 /* ---------------------------------------------------------------------------------------------------------------- */
@@ -341,10 +363,6 @@ __device__ __forceinline__ void seg_points_inl(v3& VEC, v3& X, v3& Y, const v3& 
             if (dot(VEC, T) < 0) { VEC.x = -VEC.x; VEC.y = -VEC.y; VEC.z = -VEC.z; }
         }
     }
-}
-
-__device__ __forceinline__ double shfl_f64(double v, int src) {
-    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
 }
 
 __device__ __noinline__ double face_and_final(const v3 S0, const v3 S1, const v3 S2, const v3 T0, const v3 T1, const v3 T2, bool shown_disjoint, double mindd) {
@@ -735,6 +753,196 @@ __device__ __forceinline__ bool gd_iterate(const ckc_kin_dev& k, const gd_ref& s
         p[0] = fma(R[0], tx, fma(R[2], tz, p[0]));
         p[1] = fma(R[3], tx, fma(R[5], tz, p[1]));
         p[2] = fma(R[6], tx, fma(R[8], tz, p[2]));
+    }
+    return eq;
+}
+
+/* ---- the same iteration with the chain unrolled -------------------------------------------------------------------
+ * The axis sequence Z,Y,Y,X,Y,X | X,Y,X,Y,Y,Z and the segment tips of kdl_class.cpp:32-45 are compile-time facts: with the two
+ * walks fully unrolled every joint's axis arm is selected statically (no three-way branch, no constant-table loads, no loop
+ * counters), tip components that are zero cost nothing (14 of the 24 are non-zero), and the |q| >= 1e4 library fallback of the
+ * sin / cos moves out of the walk (a flag; the rolled gd_iterate above is the cold path that redoes such an iteration).
+ * kMerge: joints 5 and 6 (chain order) are both about X with a pure X translation between them (the rod), i.e. COLLINEAR:
+ * Rx(q5) Tx Rx(q6) = Tx Rx(q5 + q6), their Jacobian columns coincide, and the minimum-norm step gives both the same dq.  The
+ * merged form evaluates one sin / cos of q5 + q6, one rotation and one column with weight 2 in J0 J0^T (rounding-level
+ * differences against the two-joint evaluation, 1e-16 relative). */
+struct gd_chain_u {
+    /* tip (x, z) after each joint; joint 5 carries the rod: x = 2 * 66 + L, passed at run time */
+    static constexpr double tx[12] = { 0, 0, 149.6, 152.4, 66, -1 /* rod */, 66, 152.4, 149.6, 0, 0, 0 };
+    static constexpr double tz[12] = { 124, 270, 70, 0, 0, 0, 0, 0, -70, -270, -124, -166 };
+};
+
+/* sin / cos without the large-argument branch: `bad` collects |x| >= 1e4 (or NaN), the caller redoes the iteration on the cold path */
+__device__ __forceinline__ void sincos_nobranch(double x, double* sn, double* cs, bool& bad) {
+    bad = bad || !(fabs(x) < 1.0e4);
+    const double kd = rint(x * c_sc[0]);
+    const int k = (int)kd;
+    double r = fma(-kd, c_sc[1], x);
+    r = fma(-kd, c_sc[2], r);
+    const double z = r * r;
+    double ps = fma(z, c_sc[8], c_sc[7]);
+    ps = fma(z, ps, c_sc[6]); ps = fma(z, ps, c_sc[5]); ps = fma(z, ps, c_sc[4]); ps = fma(z, ps, c_sc[3]);
+    const double s0 = fma(r * z, ps, r);
+    double pc = fma(z, c_sc[14], c_sc[13]);
+    pc = fma(z, pc, c_sc[12]); pc = fma(z, pc, c_sc[11]); pc = fma(z, pc, c_sc[10]); pc = fma(z, pc, c_sc[9]);
+    const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double ss = (k & 1) ? c0 : s0, cc = (k & 1) ? s0 : c0;
+    /* sign flips on the high word (one integer instruction each instead of an FP64 negation + two selects) */
+    *sn = __hiloint2double(__double2hiint(ss) ^ ((k & 2) << 30), __double2loint(ss));
+    *cs = __hiloint2double(__double2hiint(cc) ^ (((k + 1) & 2) << 30), __double2loint(cc));
+}
+
+template <int AX> __device__ __forceinline__ void gd_col(const double* R, const double* p, double* col) {
+    col[3] = R[AX]; col[4] = R[3 + AX]; col[5] = R[6 + AX];
+    col[0] = p[1] * col[5] - p[2] * col[4];
+    col[1] = p[2] * col[3] - p[0] * col[5];
+    col[2] = p[0] * col[4] - p[1] * col[3];
+}
+template <int J> __device__ __forceinline__ void gd_tip_u(const double* R, double* p, double rodx) {
+    constexpr double tz = gd_chain_u::tz[J];
+    const double tx = J == 5 ? rodx : gd_chain_u::tx[J];
+    if (J == 5 || gd_chain_u::tx[J] != 0.0) { p[0] = fma(R[0], tx, p[0]); p[1] = fma(R[3], tx, p[1]); p[2] = fma(R[6], tx, p[2]); }
+    if (tz != 0.0) { p[0] = fma(R[2], tz, p[0]); p[1] = fma(R[5], tz, p[1]); p[2] = fma(R[8], tz, p[2]); }
+}
+
+template <bool kMerge> __device__ __noinline__ bool gd_iterate_cold(const ckc_kin_dev& k, const gd_ref& s) { return gd_iterate(k, s); }
+
+template <bool kMerge>
+__device__ __forceinline__ bool gd_iterate_u(const ckc_kin_dev& k, const gd_ref& s) {
+    const double rodx = 2 * 66.0 + k.L;
+    double R[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    double p[3] = { 0, 0, 166.0 };                 /* segment 0: Joint::None, Tz(b) */
+    double A[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) A[i][j] = 0;
+    bool bad = false;
+    constexpr int kAx[12] = { 2, 1, 1, 0, 1, 0, 0, 1, 0, 1, 1, 2 };
+    /* ---- walk 1 ---- */
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        if (kMerge && j == 6) continue;            /* folded into joint 5 */
+        double sj, cj;
+        const double qj = (kMerge && j == 5) ? s.qc(5) + s.qc(6) : s.qc(j);
+        sincos_nobranch(qj, &sj, &cj, bad);
+        s.cs(j) = cj; s.sn(j) = sj;
+        double col[6];
+        const int ax = kAx[j];
+        if (ax == 0) gd_col<0>(R, p, col); else if (ax == 1) gd_col<1>(R, p, col); else gd_col<2>(R, p, col);
+        if (kMerge && j == 5) {
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                const double c2 = col[a] + col[a];
+#pragma unroll
+                for (int b = 0; b <= a; b++) A[a][b] = fma(c2, col[b], A[a][b]);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int b = 0; b <= a; b++) A[a][b] = fma(col[a], col[b], A[a][b]);
+        }
+        if (ax == 0) post_rot_x(R, cj, sj); else if (ax == 1) post_rot_y(R, cj, sj); else post_rot_z(R, cj, sj);
+        if (j == 0) gd_tip_u<0>(R, p, rodx); else if (j == 1) gd_tip_u<1>(R, p, rodx); else if (j == 2) gd_tip_u<2>(R, p, rodx);
+        else if (j == 3) gd_tip_u<3>(R, p, rodx); else if (j == 4) gd_tip_u<4>(R, p, rodx); else if (j == 5) gd_tip_u<5>(R, p, rodx);
+        else if (j == 6) gd_tip_u<6>(R, p, rodx); else if (j == 7) gd_tip_u<7>(R, p, rodx); else if (j == 8) gd_tip_u<8>(R, p, rodx);
+        else if (j == 9) gd_tip_u<9>(R, p, rodx); else if (j == 10) gd_tip_u<10>(R, p, rodx); else gd_tip_u<11>(R, p, rodx);
+        if (kMerge && j == 5) gd_tip_u<6>(R, p, rodx);      /* joint 6's tip follows at once: Tx commutes with Rx */
+    }
+    if (bad) return gd_iterate_cold<kMerge>(k, s);          /* |q| >= 1e4: library sin / cos (state untouched so far) */
+    /* ---- delta_twist = diff(f, target): vel = (D,0,0) - p ; rot = R * GetRot(R^T) ---- */
+    double tw[6];
+    tw[0] = k.D - p[0]; tw[1] = -p[1]; tw[2] = -p[2];
+    {
+        double Rt[9], rv[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) Rt[3 * a + b] = R[3 * b + a];
+        kdl_rotvec(Rt, rv);
+#pragma unroll
+        for (int a = 0; a < 3; a++) tw[3 + a] = R[3 * a] * rv[0] + R[3 * a + 1] * rv[1] + R[3 * a + 2] * rv[2];
+    }
+    bool eq = true;
+#pragma unroll
+    for (int i = 0; i < 6; i++) eq = eq && (fabs(tw[i]) < 1e-5);
+    /* ---- Cholesky of A0 (lower, in place; reciprocal pivots kept) ---- */
+    bool regular = true;
+    double inv[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double v = A[i][j];
+#pragma unroll
+            for (int kk = 0; kk < j; kk++) v -= A[i][kk] * A[j][kk];
+            if (i == j) { if (!(v > 1e-300)) { regular = false; v = 1; } const double r = rsqrt(v); inv[i] = r; A[i][i] = v * r; }
+            else A[i][j] = v * inv[j];
+        }
+    }
+    if (regular) {
+        double fro = 0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            double Lc[6];
+#pragma unroll
+            for (int r = c; r < 6; r++) {
+                double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int kk = c; kk < r; kk++) v -= A[r][kk] * Lc[kk];
+                Lc[r] = v * inv[r];
+                fro += Lc[r] * Lc[r];
+            }
+        }
+        const double reach = 1.0 + sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+        regular = fro * (1.5e-5 * 1.5e-5) * reach * reach < 1.0;
+    }
+    if (!regular) { gd_singular_step(k, s, tw); return eq; }
+    double z[6];
+    z[0] = tw[0] + (p[1] * tw[5] - p[2] * tw[4]);
+    z[1] = tw[1] + (p[2] * tw[3] - p[0] * tw[5]);
+    z[2] = tw[2] + (p[0] * tw[4] - p[1] * tw[3]);
+    z[3] = tw[3]; z[4] = tw[4]; z[5] = tw[5];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double v = z[i];
+#pragma unroll
+        for (int kk = 0; kk < i; kk++) v -= A[i][kk] * z[kk];
+        z[i] = v * inv[i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        double v = z[i];
+#pragma unroll
+        for (int kk = i + 1; kk < 6; kk++) v -= A[kk][i] * z[kk];
+        z[i] = v * inv[i];
+    }
+    /* ---- walk 2 ---- */
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+    p[0] = 0; p[1] = 0; p[2] = 166.0;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        if (kMerge && j == 6) continue;
+        double w[3];
+        w[0] = fma(z[1], p[2], fma(-z[2], p[1], z[3]));
+        w[1] = fma(z[2], p[0], fma(-z[0], p[2], z[4]));
+        w[2] = fma(z[0], p[1], fma(-z[1], p[0], z[5]));
+        const int ax = kAx[j];
+        const double dq = R[ax] * w[0] + R[3 + ax] * w[1] + R[6 + ax] * w[2];
+        /* volatile reads: with the walks unrolled the compiler would otherwise forward the 36 values stored in walk 1 through
+         * registers across the whole solve (and spill them) instead of re-reading the shared-memory column */
+        s.qc(j) = *(volatile double*)&s.qc(j) + dq;
+        if (kMerge && j == 5) s.qc(6) = *(volatile double*)&s.qc(6) + dq;
+        if (j < 11) {
+            const double cj = *(volatile double*)&s.cs(j), sj = *(volatile double*)&s.sn(j);
+            if (ax == 0) post_rot_x(R, cj, sj); else if (ax == 1) post_rot_y(R, cj, sj); else post_rot_z(R, cj, sj);
+            if (j == 0) gd_tip_u<0>(R, p, rodx); else if (j == 1) gd_tip_u<1>(R, p, rodx); else if (j == 2) gd_tip_u<2>(R, p, rodx);
+            else if (j == 3) gd_tip_u<3>(R, p, rodx); else if (j == 4) gd_tip_u<4>(R, p, rodx); else if (j == 5) gd_tip_u<5>(R, p, rodx);
+            else if (j == 6) gd_tip_u<6>(R, p, rodx); else if (j == 7) gd_tip_u<7>(R, p, rodx); else if (j == 8) gd_tip_u<8>(R, p, rodx);
+            else if (j == 9) gd_tip_u<9>(R, p, rodx); else gd_tip_u<10>(R, p, rodx);
+            if (kMerge && j == 5) gd_tip_u<6>(R, p, rodx);
+        }
     }
     return eq;
 }

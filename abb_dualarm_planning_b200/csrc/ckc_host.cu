@@ -45,7 +45,7 @@ struct ckc_lane {
     cudaStream_t st = nullptr;
     cudaStream_t st_hi = nullptr;       /* high-priority stream for the collision stage of this lane's chunk */
     cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_c = nullptr;
-    dev_buf qin, qout, ac, ik, ok, valid, list, frames, ovf, bigstack, flags, aux, aux2, small, gdstate, pairstat;
+    dev_buf qin, qout, ac, ik, ok, valid, list, ovf, bigstack, flags, aux, aux2, small, gdstate, pairstat;
     int64_t collide_launches = 0;
     /* this lane's own first-hit statistics and processing order of the pair table: [0, MAX_PAIRS) hits, [MAX_PAIRS, 2 MAX_PAIRS)
      * order.  They are read and rewritten only by kernels on this lane's stream -- a table shared by the lanes would be
@@ -57,7 +57,7 @@ struct ckc_lane {
     int32_t* ovf_count() const { return small.as<int32_t>() + 4; }
     int32_t* rbs_counts() const { return small.as<int32_t>() + 8; }        /* 2 ints */
     unsigned long long* gd_counter() const { return (unsigned long long*)(small.as<int32_t>() + 12); }
-    void release() { dev_buf* b[] = { &qin, &qout, &ac, &ik, &ok, &valid, &list, &frames, &ovf, &bigstack, &flags, &aux, &aux2, &small, &gdstate, &pairstat }; for (dev_buf* x : b) x->release(); }
+    void release() { dev_buf* b[] = { &qin, &qout, &ac, &ik, &ok, &valid, &list, &ovf, &bigstack, &flags, &aux, &aux2, &small, &gdstate, &pairstat }; for (dev_buf* x : b) x->release(); }
 };
 
 struct ckc_ctx {
@@ -122,7 +122,7 @@ static bool read_tris_file(const std::string& path, std::vector<double>& out) {
     FILE* fp = fopen(path.c_str(), "r");
     if (!fp) return false;
     int n = 0;
-    bool ok = fscanf(fp, "%d", &n) == 1 && n >= 0;
+    bool ok = fscanf(fp, "%d", &n) == 1 && n >= 0 && n <= (1 << 20);      /* header sanity: no unbounded resize */
     if (ok) {
         out.resize((size_t)n * 9);
         for (size_t i = 0; ok && i < out.size(); i++) ok = fscanf(fp, "%lf", &out[i]) == 1;
@@ -138,7 +138,7 @@ static bool read_pack(const std::string& path, host_mesh* meshes) {
     bool ok = fread(magic, 1, 8, fp) == 8 && memcmp(magic, "CKCMESH1", 8) == 0 && fread(&nm, 4, 1, fp) == 1;
     for (int m = 0; ok && m < nm; m++) {
         int32_t id = -1, nt = 0;
-        ok = fread(&id, 4, 1, fp) == 1 && fread(&nt, 4, 1, fp) == 1 && id >= 0 && id < CKC_NUM_MESHES && nt >= 0;
+        ok = fread(&id, 4, 1, fp) == 1 && fread(&nt, 4, 1, fp) == 1 && id >= 0 && id < CKC_NUM_MESHES && nt >= 0 && nt <= (1 << 20);
         if (!ok) break;
         meshes[id].tris.resize((size_t)nt * 9);
         ok = fread(meshes[id].tris.data(), 8, (size_t)nt * 9, fp) == (size_t)nt * 9;
@@ -444,6 +444,11 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
     init_constants(ctx);
     make_rod(ctx->meshes[CKC_M_ROD], ctx->kin.L);
     for (int m = 0; m < CKC_NUM_MESHES; m++) build_hierarchy(ctx->meshes[m]);
+    /* the kernels pack node and triangle indices into 11 / 10 bits of a task word */
+    static_assert(CKC_MAX_MESH_NODES == (1 << 11) && CKC_MAX_MESH_TRIS == (1 << 10) && CKC_MAX_PAIRS <= (1 << 10), "task word bit fields");
+    for (int m = 0; m < CKC_NUM_MESHES; m++)
+        if (ctx->meshes[m].ntris() > CKC_MAX_MESH_TRIS || (int)ctx->meshes[m].nodes.size() > CKC_MAX_MESH_NODES)
+            return bail(CKC_ERR_ARG, std::string("mesh ") + (k_mesh_file[m] ? k_mesh_file[m] : "rod") + " has more than 1024 triangles (task word bit fields)");
     for (int p = 0; p < ctx->world.npairs; p++)
         if (ctx->meshes[ctx->world.pairs[p].mesh_a].ntris() == 0 || ctx->meshes[ctx->world.pairs[p].mesh_b].ntris() == 0)
             return bail(CKC_ERR_IO, "a mesh used by the pair table is empty");
@@ -504,9 +509,16 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
             const float rsum = (float)((radius(pr.mesh_a) + radius(pr.mesh_b) + ctx->world.cull_tol) * (1 + 1e-5) + 2e-3);
             memcpy(&pt[p].pad0, &rsum, 4);
         }
-        bool okt = ctx->d_pairtab.reserve(pt.size() * sizeof(ckc_pair_dev)) == cudaSuccess && ctx->d_static.reserve(sizeof(ctx->world.static_frames)) == cudaSuccess &&
+        /* obstacle poses, then the base frames of the two robots: robot 1 R0 = Rz(0)^2 = I, robot 2 R02 = Rz(3.14159265/2)^2 */
+        double stat[5][12];
+        memcpy(stat, ctx->world.static_frames, sizeof(ctx->world.static_frames));
+        for (int r = 0; r < 2; r++) {
+            for (int e = 0; e < 9; e++) stat[3 + r][e] = r == 0 ? (e % 4 == 0 ? 1.0 : 0.0) : ctx->world.base2_rot[e];
+            for (int e = 0; e < 3; e++) stat[3 + r][9 + e] = ctx->world.base_t[r][e];
+        }
+        bool okt = ctx->d_pairtab.reserve(pt.size() * sizeof(ckc_pair_dev)) == cudaSuccess && ctx->d_static.reserve(sizeof(stat)) == cudaSuccess &&
                    cudaMemcpy(ctx->d_pairtab.p, pt.data(), pt.size() * sizeof(ckc_pair_dev), cudaMemcpyHostToDevice) == cudaSuccess &&
-                   cudaMemcpy(ctx->d_static.p, ctx->world.static_frames, sizeof(ctx->world.static_frames), cudaMemcpyHostToDevice) == cudaSuccess;
+                   cudaMemcpy(ctx->d_static.p, stat, sizeof(stat), cudaMemcpyHostToDevice) == cudaSuccess;
         if (!okt) { std::string msg = std::string("device upload: ") + cudaGetErrorString(cudaGetLastError()); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA; }
         ctx->world.pair_tab = ctx->d_pairtab.as<ckc_pair_dev>();
         ctx->world.static_frames_dev = ctx->d_static.as<double>();
@@ -599,11 +611,10 @@ extern "C" int ckc_reset_stats(ckc_ctx* ctx) {
 static const ckc_layout AOS = { 12, 1 };
 static ckc_layout soa(int64_t n) { ckc_layout l = { 1, n }; return l; }
 
-/* K2 + K3 on the configurations listed in d_list (count on the device), scratch of lane L, stream st */
+/* K3 (link frames + collision) on the configurations listed in d_list (count on the device), scratch of lane L, stream st */
 static int run_collision_stage(ckc_ctx* ctx, ckc_lane& L, int64_t m_max, const double* d_q, ckc_layout l, const int32_t* d_list, const int32_t* d_m,
                                uint8_t* d_hit, uint8_t* d_valid, uint8_t* d_pair_flags, cudaStream_t st, bool allow_hop = true) {
     if (m_max <= 0) return CKC_OK;
-    CU(L.frames.reserve((size_t)m_max * CKC_FRAME_DOUBLES * 8));
     CU(L.ovf.reserve((size_t)m_max * 4));
     CU(L.bigstack.reserve((size_t)16 * 8 * 65536 * 4));
     /* on the lane's own stream the collision stage moves to the lane's HIGH-PRIORITY stream: its blocks then win the SM slots
@@ -613,15 +624,13 @@ static int run_collision_stage(ckc_ctx* ctx, ckc_lane& L, int64_t m_max, const d
     if (hop) { CU(cudaEventRecord(L.ev_p, st)); CU(cudaStreamWaitEvent(L.st_hi, L.ev_p, 0)); st = L.st_hi; }
     ckc_world_dev w = ctx->world;                 /* by-value launch argument: this lane's pair statistics */
     w.pair_hits = L.pair_hits(); w.pair_order = L.pair_order();
-    { stage_scope ts(ctx, st, 1);
-      ckc_launch_link_frames(w, d_q, l, d_list, d_m, m_max, L.frames.as<double>(), st); }
     ckc_launch_cfg cfg = { ctx->num_sms };
     /* refresh the processing order from the hit statistics now and then (a 1-block kernel on the same stream) */
     if ((L.collide_launches++ & 7) == 7) { ckc_launch_update_pair_order(w, L.pair_order(), st); ctx->launches++; }
     { stage_scope ts(ctx, st, 2);
-      ckc_launch_collide(w, cfg, L.frames.as<double>(), d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, L.work_counter(),
+      ckc_launch_collide(w, cfg, d_q, l, d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, L.work_counter(),
                          L.ovf.as<int32_t>(), L.ovf_count(), L.bigstack.as<uint32_t>(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
-    ctx->launches += 3;
+    ctx->launches += 2;
     CU(cudaGetLastError());
     if (hop) { CU(cudaEventRecord(L.ev_c, st)); CU(cudaStreamWaitEvent(lane_st, L.ev_c, 0)); }
     return CKC_OK;

@@ -17,6 +17,10 @@
 enum { CKC_M_BASE = 0, CKC_M_LINK1, CKC_M_LINK2, CKC_M_LINK3, CKC_M_LINK4, CKC_M_LINK5, CKC_M_LINK6, CKC_M_EE,
        CKC_M_TABLE, CKC_M_OBS, CKC_M_CONE, CKC_M_ROD };
 
+/* k_collide packs a task as pair << 22 | nodeA << 11 | nodeB and a leaf pair as pair << 20 | triA << 10 | triB */
+#define CKC_MAX_MESH_NODES 2048
+#define CKC_MAX_MESH_TRIS 1024
+
 /* One node of a per-mesh oriented-bounding-box hierarchy, 64 bytes (two 32-byte sectors, four float4 loads).
  * Box = { c + sum_i s_i h_i a_i, |s_i| <= 1 }, a2 = a0 x a1, all in the mesh's own frame.
  * child >= 0: inner node, children are `child` and `child + 1` (indices relative to the mesh's first node);
@@ -36,7 +40,7 @@ struct __align__(16) ckc_pair_dev { int node_a, node_b, tri_a, tri_b, frame_a, f
 struct ckc_world_dev {
     const ckc_node* nodes;              /* all meshes, concatenated */
     const ckc_pair_dev* pair_tab;       /* [npairs] in global memory: indexed per lane (a kernel-parameter array would be copied to local memory) */
-    const double* static_frames_dev;    /* [3][12] obstacle poses in global memory (same values as static_frames) */
+    const double* static_frames_dev;    /* [5][12] in global memory: the 3 obstacle poses (same values as static_frames), then the two robot base frames */
     unsigned int* pair_hits;            /* [CKC_MAX_PAIRS] how often each table entry produced the first hit (decayed): adaptive processing order */
     const int* pair_order;              /* [CKC_MAX_PAIRS] table entries sorted by decreasing pair_hits; any order yields the same boolean */
     const double*   tris;               /* all meshes, concatenated, 9 doubles per triangle (FP64, as parsed) */
@@ -98,11 +102,9 @@ struct ckc_launch_cfg { int num_sms; };
 void ckc_launch_pcs_project(const ckc_kin_dev& kin, int64_t n, const double* q, ckc_layout li, const int8_t* ac, const int8_t* ik,
                             uint64_t seed, uint64_t i0, int seeded, double* q_out, ckc_layout lo, uint8_t* ok, uint8_t* valid,
                             int32_t* list, int32_t* list_count, ckc_counters_dev* ctr, cudaStream_t st);
-/* K2: link frames of the configurations named by list[0..m) (or 0..m-1 when list == NULL) */
-void ckc_launch_link_frames(const ckc_world_dev& w, const double* q, ckc_layout l, const int32_t* list, const int32_t* d_m, int64_t m_max,
-                            double* frames, cudaStream_t st);
-/* K3: collision. hit flags / valid flags are indexed by the sample index (list[k]) */
-void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const double* frames, const int32_t* list, const int32_t* d_m,
+/* K3: link frames + collision of the configurations named by list[0..m) (or 0..m-1 when list == NULL); configuration
+ * (sample, j) = q[sample * lq.stride_i + j * lq.stride_j]; hit flags / valid flags are indexed by the sample index (list[k]) */
+void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const double* q, ckc_layout lq, const int32_t* list, const int32_t* d_m,
                         int64_t m_max, uint8_t* hit_out, uint8_t* valid_out, uint8_t* pair_flags, int32_t* work_counter,
                         int32_t* ovf_list, int32_t* ovf_count, uint32_t* big_stack, ckc_counters_dev* ctr, cudaStream_t st);
 void ckc_launch_update_pair_order(const ckc_world_dev& w, int* order_out, cudaStream_t st);

@@ -3,8 +3,10 @@
  *
  *   k_pcs_project   K1  one thread per sample: FK(active arm) -> closure target -> one analytic IK branch -> joint
  *                       limits; FP64 in registers; warp-aggregated append of the IK-feasible samples to a work list.
- *   k_link_frames   K2  one thread per feasible configuration: the 18 configuration-dependent link frames (FP64).
- *   k_collide       K3  one WARP per feasible configuration: sphere pre-test of the 116 root pairs, then warp-cooperative
+ *   k_collide       K3  one WARP per feasible configuration: the 18 configuration-dependent link frames computed by the warp
+ *                       itself into shared memory (FP64 for the exact leaf test + an FP32 copy for the box tests; the former
+ *                       K2 kernel and its 1 728 B per configuration HBM round trip are gone), sphere pre-test of the 116 root
+ *                       pairs, then warp-cooperative
  *                       traversal of the OBB hierarchies with a shared-memory task stack; FP32 conservative box culling
  *                       (guard band), interpenetrating pairs first and split four ways, warp-cooperative FP64 PQP-exact
  *                       triangle distance at the leaves (9 lanes per triangle pair), __ballot_sync early-out on the first
@@ -102,44 +104,11 @@ void ckc_launch_pcs_project(const ckc_kin_dev& kin, int64_t n, const double* q, 
 }
 
 /* ================================================================================================================ */
-/* K2                                                                                                                 */
-/* ================================================================================================================ */
-__global__ void __launch_bounds__(128)
-k_link_frames(const ckc_world_dev w, const double* __restrict__ q, ckc_layout l, const int32_t* __restrict__ list,
-              const int32_t* __restrict__ d_m, int64_t m_max, double* __restrict__ frames) {
-    int64_t m = d_m ? (int64_t)*d_m : m_max;
-    if (m > m_max) m = m_max;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
-        const int64_t i = list ? (int64_t)list[k] : k;
-        double qq[12];
-#pragma unroll
-        for (int j = 0; j < 12; j++) qq[j] = q[i * l.stride_i + j * l.stride_j];
-        double* out = frames + k * CKC_FRAME_DOUBLES;
-        const double I3[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
-        robot_frames(I3, w.base_t[0], qq, out);                   /* robot 1: R0 = Rz(0)^2 = I */
-        robot_frames(w.base2_rot, w.base_t[1], qq + 6, out + 96); /* robot 2: R02 = Rz(3.14159265/2)^2 */
-        /* the two frames the reference's pair table mixes up (collisionDetection.cpp:373, :397, :415) */
-#pragma unroll
-        for (int e = 0; e < 9; e++) { out[16 * 12 + e] = out[10 * 12 + e]; out[17 * 12 + e] = out[2 * 12 + e]; }
-#pragma unroll
-        for (int e = 9; e < 12; e++) { out[16 * 12 + e] = out[2 * 12 + e]; out[17 * 12 + e] = out[10 * 12 + e]; }
-    }
-}
-
-void ckc_launch_link_frames(const ckc_world_dev& w, const double* q, ckc_layout l, const int32_t* list, const int32_t* d_m, int64_t m_max,
-                            double* frames, cudaStream_t st) {
-    if (m_max <= 0) return;
-    int64_t blocks = (m_max + 127) / 128;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    k_link_frames<<<(unsigned)blocks, 128, 0, st>>>(w, q, l, list, d_m, m_max, frames);
-}
-
-/* ================================================================================================================ */
 /* K3: warp-cooperative collision                                                                                     */
 /* ================================================================================================================ */
 struct collide_args {
-    const double* frames;        /* [m][18][12] */
+    const double* q;             /* configurations, element (sample, j) = q[sample * lq.stride_i + j * lq.stride_j] */
+    ckc_layout lq;
     const int32_t* list;         /* sample index of configuration k (NULL: k) */
     const int32_t* d_m;          /* number of configurations (device), or NULL */
     int64_t m_max;
@@ -159,9 +128,6 @@ struct collide_args {
     int wide_cnt;                /* rounds with at most this many tasks split BOTH boxes of a task (4 children) */
 };
 
-__device__ __forceinline__ const double* frame64(const ckc_world_dev& w, const double* cfg_frames, int f) {
-    return f < CKC_NUM_DYN_FRAMES ? cfg_frames + 12 * f : w.static_frames_dev + 12 * (f - CKC_NUM_DYN_FRAMES);
-}
 __device__ __forceinline__ ckc_pair_dev smem_pair(const int4* sp, int p) {
     const int4 a = sp[2 * p], b = sp[2 * p + 1];
     ckc_pair_dev r; r.node_a = a.x; r.node_b = a.y; r.tri_a = a.z; r.tri_b = a.w; r.frame_a = b.x; r.frame_b = b.y; r.pad0 = b.z; r.pad1 = 0;
@@ -169,10 +135,10 @@ __device__ __forceinline__ ckc_pair_dev smem_pair(const int4* sp, int p) {
 }
 /* leaf operands with PQP_Tolerance's conventions: R = Ra^T Rb, T = Ra^T (Tb - Ta); triangle ta of mesh A as stored, triangle tb
  * of mesh B transformed into A's frame */
-__device__ __forceinline__ void load_leaf_pair(const ckc_world_dev& w, const double* cfg_frames, const ckc_pair_dev pr, int ta, int tb,
+__device__ __forceinline__ void load_leaf_pair(const ckc_world_dev& w, const double* F64, const ckc_pair_dev pr, int ta, int tb,
                                                v3& S0, v3& S1, v3& S2, v3& T0, v3& T1, v3& T2) {
-    const double* Fa = frame64(w, cfg_frames, pr.frame_a);
-    const double* Fb = frame64(w, cfg_frames, pr.frame_b);
+    const double* Fa = F64 + 12 * pr.frame_a;        /* FP64 frame table of this warp (shared memory), static poses included */
+    const double* Fb = F64 + 12 * pr.frame_b;
     double R[9], T[3];
     const double tx = Fb[9] - Fa[9], ty = Fb[10] - Fa[10], tz = Fb[11] - Fa[11];
 #pragma unroll
@@ -195,22 +161,27 @@ __device__ __forceinline__ void load_leaf_pair(const ckc_world_dev& w, const dou
 #ifndef CKC_COLLIDE_MINBLOCKS
 #define CKC_COLLIDE_MINBLOCKS 2
 #endif
+/* dynamic shared memory of one block (8 warps): FP64 frames 8 x 2016 B, FP32 frames 8 x 1008 B, task stacks 8 x 2560 B,
+ * triangle queues 8 x 256 B, pair table 3712 B = 50.3 kB (2 blocks per SM) */
+#define CKC_COLLIDE_SMEM(big) ((size_t)CKC_COLLIDE_WARPS * (CKC_NUM_FRAMES * 12 * (8 + 4) + ((big) ? 0 : CKC_STACK_CAP * 4) + CKC_TRIQ_CAP * 4) + CKC_MAX_PAIRS * 32)
 template <bool kBigStack>
 __global__ void __launch_bounds__(CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_MINBLOCKS)
 k_collide(const ckc_world_dev w, const collide_args a) {
-    __shared__ float s_frames[CKC_COLLIDE_WARPS][CKC_NUM_FRAMES * 12];
-    __shared__ uint32_t s_stack[kBigStack ? 1 : CKC_COLLIDE_WARPS][kBigStack ? 1 : CKC_STACK_CAP];
-    __shared__ uint32_t s_triq[CKC_COLLIDE_WARPS][CKC_TRIQ_CAP];
-    __shared__ int4 s_pairs[CKC_MAX_PAIRS * 2];       /* the pair table, once per block (32 bytes per entry) */
-    for (int e = threadIdx.x; e < w.npairs * 2; e += blockDim.x) s_pairs[e] = __ldg(reinterpret_cast<const int4*>(w.pair_tab) + e);
-    __syncthreads();
-
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
+    int4* s_pairs = reinterpret_cast<int4*>(s_raw);                                   /* the pair table, once per block (32 bytes per entry) */
+    double* F64 = reinterpret_cast<double*>(s_raw + CKC_MAX_PAIRS * 32) + wib * (CKC_NUM_FRAMES * 12);
+    float* F = reinterpret_cast<float*>(s_raw + CKC_MAX_PAIRS * 32 + CKC_COLLIDE_WARPS * CKC_NUM_FRAMES * 12 * 8) + wib * (CKC_NUM_FRAMES * 12);
+    uint32_t* triq = reinterpret_cast<uint32_t*>(s_raw + CKC_MAX_PAIRS * 32 + CKC_COLLIDE_WARPS * CKC_NUM_FRAMES * 12 * 12) + wib * CKC_TRIQ_CAP;
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(s_raw + CKC_MAX_PAIRS * 32 + CKC_COLLIDE_WARPS * (CKC_NUM_FRAMES * 12 * 12 + CKC_TRIQ_CAP * 4));
+    for (int e = threadIdx.x; e < w.npairs * 2; e += blockDim.x) s_pairs[e] = __ldg(reinterpret_cast<const int4*>(w.pair_tab) + e);
+    /* the three static obstacle poses never change: once per warp, in both precisions */
+    for (int e = lane; e < 36; e += 32) { const double v = w.static_frames_dev[e]; F64[CKC_FRAME_DOUBLES + e] = v; F[CKC_FRAME_DOUBLES + e] = (float)v; }
+    __syncthreads();
+
     const unsigned lt_mask = (1u << lane) - 1;
-    float* F = s_frames[wib];
-    uint32_t* triq = s_triq[wib];
-    uint32_t* stack = kBigStack ? a.big_stack + (size_t)(blockIdx.x * CKC_COLLIDE_WARPS + wib) * CKC_BIG_STACK_CAP : s_stack[kBigStack ? 0 : wib];
+    uint32_t* stack = kBigStack ? a.big_stack + (size_t)(blockIdx.x * CKC_COLLIDE_WARPS + wib) * CKC_BIG_STACK_CAP : s_stack + wib * CKC_STACK_CAP;
     const int cap = kBigStack ? CKC_BIG_STACK_CAP : CKC_STACK_CAP;
 
     int64_t m = kBigStack ? (int64_t)*a.ovf_count : (a.d_m ? (int64_t)*a.d_m : a.m_max);
@@ -224,13 +195,15 @@ k_collide(const ckc_world_dev w, const collide_args a) {
         if (lane == 0) k = atomicAdd(a.work_counter, 1);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= m) break;
-        const int cfg = kBigStack ? a.ovf_list[k] : k;                 /* index into frames[] / list[] */
+        const int cfg = kBigStack ? a.ovf_list[k] : k;                 /* index into list[] */
         const int64_t sample = a.list ? (int64_t)a.list[cfg] : (int64_t)cfg;
-        const double* cfg_frames = a.frames + (int64_t)cfg * CKC_FRAME_DOUBLES;
 
-        /* stage this configuration's frames as FP32 in shared memory (static obstacle poses from the parameter bank) */
-        for (int e = lane; e < CKC_NUM_FRAMES * 12; e += 32)
-            F[e] = e < CKC_FRAME_DOUBLES ? (float)cfg_frames[e] : (float)w.static_frames_dev[e - CKC_FRAME_DOUBLES];
+        /* this configuration's 18 link frames, FP64, by the warp itself (lane j < 12 fetches joint j), then the FP32 copy the
+         * box tests read */
+        const double qj = lane < 12 ? a.q[sample * a.lq.stride_i + lane * a.lq.stride_j] : 0.0;
+        warp_link_frames(w.static_frames_dev + 36, qj, lane, F64);
+        __syncwarp();
+        for (int e = lane; e < CKC_FRAME_DOUBLES; e += 32) F[e] = (float)F64[e];
         /* seed the stack with the root task of every table entry, first entry on top */
         /* processing order = table entries by decreasing (decayed) first-hit frequency: a colliding configuration usually
          * reaches its hit inside the first 32 root tasks and leaves through the ballot early-out */
@@ -273,7 +246,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
         int ntri = 0;
         bool hit = false, overflow = false, hot = false, draining = false;      /* hot: a queued triangle pair looks like a hit -> test it now */
         /* env 2: "path not from above" rule, collisionDetection.cpp:427-428 */
-        if (w.env == 2 && (cfg_frames[7 * 12 + 11] > 800.0 || cfg_frames[15 * 12 + 11] > 800.0)) { hit = true; top = 0; }
+        if (w.env == 2 && (F64[7 * 12 + 11] > 800.0 || F64[15 * 12 + 11] > 800.0)) { hit = true; top = 0; }
         __syncwarp();
 
         while (!hit) {
@@ -288,7 +261,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                 if (act) {
                     t = triq[ntri - 1 - g];
                     const ckc_pair_dev pr = smem_pair(s_pairs, t >> 20);
-                    load_leaf_pair(w, cfg_frames, pr, (t >> 10) & 1023, t & 1023, S0, S1, S2, T0, T1, T2);
+                    load_leaf_pair(w, F64, pr, (t >> 10) & 1023, t & 1023, S0, S1, S2, T0, T1, T2);
                 }
                 const double d = tri_dist_coop(act, lane, S0, S1, S2, T0, T1, T2);
                 const bool h = act && (lane - 9 * g) == 0 && d <= w.tol;      /* PQP: closer_than_tolerance iff d <= tolerance */
@@ -419,12 +392,12 @@ void ckc_launch_update_pair_order(const ckc_world_dev& w, int* order_out, cudaSt
     k_update_pair_order<<<1, 128, 0, st>>>(w.pair_hits, order_out, w.npairs);
 }
 
-void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const double* frames, const int32_t* list, const int32_t* d_m,
+void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const double* q, ckc_layout lq, const int32_t* list, const int32_t* d_m,
                         int64_t m_max, uint8_t* hit_out, uint8_t* valid_out, uint8_t* pair_flags, int32_t* work_counter,
                         int32_t* ovf_list, int32_t* ovf_count, uint32_t* big_stack, ckc_counters_dev* ctr, cudaStream_t st) {
     if (m_max <= 0) return;
     collide_args a;
-    a.frames = frames; a.list = list; a.d_m = d_m; a.m_max = m_max; a.hit_out = hit_out; a.valid_out = valid_out; a.pair_flags = pair_flags;
+    a.q = q; a.lq = lq; a.list = list; a.d_m = d_m; a.m_max = m_max; a.hit_out = hit_out; a.valid_out = valid_out; a.pair_flags = pair_flags;
     a.work_counter = work_counter; a.ovf_list = ovf_list; a.ovf_count = ovf_count; a.big_stack = big_stack; a.ctr = ctr;
     /* tuning / debug knobs, read once (function-local statics: initialisation is thread safe, contexts may live on several threads) */
     static const int wide_cnt = [] { const char* e = getenv("CKC_WIDE_CNT"); return e ? atoi(e) : 8; }();
@@ -437,18 +410,24 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     a.deep4 = deep4;
     static const int flush_n = [] { const char* e = getenv("CKC_FLUSH_N"); return e ? atoi(e) : 6; }();
     static const float likely_gap = [] { const char* e = getenv("CKC_LIKELY_GAP"); return e ? (float)atof(e) : 2.0125f; }();
-    a.flush_n = flush_n; a.likely_gap = likely_gap;
+    a.flush_n = flush_n < 1 ? 1 : (flush_n > CKC_TRIQ_CAP - 32 ? CKC_TRIQ_CAP - 32 : flush_n);      /* a round queues up to 32 leaf pairs on top of flush_n - 1 */
+    a.likely_gap = likely_gap;
+    static const bool smem_ok = [] {
+        return cudaFuncSetAttribute(k_collide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CKC_COLLIDE_SMEM(false)) == cudaSuccess &&
+               cudaFuncSetAttribute(k_collide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CKC_COLLIDE_SMEM(true)) == cudaSuccess;
+    }();
+    (void)smem_ok;
     /* work_counter[0] main pass, [1] overflow pass; the overflow count sits right behind them in the lanes' scratch block */
     if (ovf_count == work_counter + 2) cudaMemsetAsync(work_counter, 0, 3 * sizeof(int32_t), st);
     else { cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st); cudaMemsetAsync(ovf_count, 0, sizeof(int32_t), st); }
     int64_t blocks = (m_max + CKC_COLLIDE_WARPS - 1) / CKC_COLLIDE_WARPS;
     const int64_t resident = (int64_t)cfg.num_sms * CKC_COLLIDE_MINBLOCKS * 3;
     if (blocks > resident) blocks = resident;
-    k_collide<false><<<(unsigned)blocks, CKC_COLLIDE_WARPS * 32, 0, st>>>(w, a);
+    k_collide<false><<<(unsigned)blocks, CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_SMEM(false), st>>>(w, a);
     /* overflow pass: tiny grid, global-memory stacks; exits immediately when nothing overflowed */
     collide_args b = a;
     b.work_counter = work_counter + 1;
-    k_collide<true><<<16, CKC_COLLIDE_WARPS * 32, 0, st>>>(w, b);
+    k_collide<true><<<16, CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_SMEM(true), st>>>(w, b);
 }
 
 /* ================================================================================================================ */
@@ -632,8 +611,15 @@ void ckc_launch_transpose(const double* src, ckc_layout ls, double* dst, ckc_lay
 #ifndef CKC_GD_MINBLOCKS
 #define CKC_GD_MINBLOCKS 5
 #endif
-template <bool seeded>
-__global__ void __launch_bounds__(CKC_GD_BLOCK, CKC_GD_MINBLOCKS)
+#ifndef CKC_GD_MINBLOCKS_U
+#define CKC_GD_MINBLOCKS_U 4        /* the unrolled walks keep more values live: 128 registers */
+#endif
+#ifndef CKC_GD_DEFAULT_VARIANT
+#define CKC_GD_DEFAULT_VARIANT 0
+#endif
+/* kVariant: 0 = rolled joint loops (gd_iterate), 1 = unrolled chain (gd_iterate_u), 2 = unrolled + collinear joints 5 / 6 merged */
+template <bool seeded, int kVariant>
+__global__ void __launch_bounds__(CKC_GD_BLOCK, kVariant == 0 ? CKC_GD_MINBLOCKS : CKC_GD_MINBLOCKS_U)
 k_gd_project(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, ckc_layout li, uint64_t key, uint64_t i0,
              double* __restrict__ q_raw, ckc_layout lo, int32_t* __restrict__ state_out, unsigned long long* work_counter) {
     __shared__ double sh_state[36 * CKC_GD_BLOCK];
@@ -669,7 +655,7 @@ k_gd_project(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q_in, 
         if (!__any_sync(0xffffffffu, active)) break;
         /* ---- one Newton iteration on every busy lane ---- */
         if (active) {
-            const bool conv = gd_iterate(kin, s);
+            const bool conv = kVariant == 0 ? gd_iterate(kin, s) : (kVariant == 1 ? gd_iterate_u<false>(kin, s) : gd_iterate_u<true>(kin, s));
             it++;
             if (conv || it >= 10000) {                                 /* ChainIkSolverPos_NR(..., 10000, 1e-5) */
                 /* retire: the raw chain-order joints + (iterations | converged << 31); k_gd_finish post-processes densely */
@@ -727,9 +713,13 @@ void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const
                            double* q_out, ckc_layout lo, uint8_t* ok, uint8_t* converged, int32_t* iters, uint8_t* valid,
                            int32_t* list, int32_t* list_count, int32_t* state_scratch, unsigned long long* work_counter, ckc_counters_dev* ctr, cudaStream_t st) {
     if (n <= 0) return;
+    static const int variant = [] { const char* e = getenv("CKC_GD_VARIANT"); const int v = e ? atoi(e) : CKC_GD_DEFAULT_VARIANT; return v < 0 || v > 2 ? CKC_GD_DEFAULT_VARIANT : v; }();
     static const int blocks_per_sm = [] {
         int b = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_gd_project<false>, CKC_GD_BLOCK, 0) != cudaSuccess || b < 1) b = 2;
+        const cudaError_t e = variant == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_gd_project<false, 0>, CKC_GD_BLOCK, 0)
+                            : variant == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_gd_project<false, 1>, CKC_GD_BLOCK, 0)
+                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_gd_project<false, 2>, CKC_GD_BLOCK, 0);
+        if (e != cudaSuccess || b < 1) b = 2;
         return b;
     }();
     int64_t blocks = (int64_t)num_sms * blocks_per_sm;
@@ -739,8 +729,10 @@ void ckc_launch_gd_project(const ckc_kin_dev& kin, int num_sms, int64_t n, const
     const int64_t needed = (n + spl * CKC_GD_BLOCK - 1) / (spl * CKC_GD_BLOCK);
     if (blocks > needed) blocks = needed;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
-    if (seeded) k_gd_project<true><<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, q_out, lo, state_scratch, work_counter);
-    else k_gd_project<false><<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, q_out, lo, state_scratch, work_counter);
+#define CKC_GD_LAUNCH(S, V) k_gd_project<S, V><<<(unsigned)blocks, CKC_GD_BLOCK, 0, st>>>(kin, n, q, li, mix64(seed), i0, q_out, lo, state_scratch, work_counter)
+    if (seeded) { if (variant == 0) CKC_GD_LAUNCH(true, 0); else if (variant == 1) CKC_GD_LAUNCH(true, 1); else CKC_GD_LAUNCH(true, 2); }
+    else { if (variant == 0) CKC_GD_LAUNCH(false, 0); else if (variant == 1) CKC_GD_LAUNCH(false, 1); else CKC_GD_LAUNCH(false, 2); }
+#undef CKC_GD_LAUNCH
     k_gd_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kin, n, q, li, seeded, q_out, lo, state_scratch, ok, converged, iters, valid, list, list_count, ctr);
 }
 

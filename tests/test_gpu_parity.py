@@ -222,6 +222,38 @@ def test_gd_million_sample_mask_vs_restatement(ck, gold):
     assert (valid != want).sum() <= 2          # measured 0; Newton from uniform seeds is chaotic on ~1e-4 of the samples (Oracle)
 
 
+def test_gd_pinned_by_reference_closure_check(ck, gold):
+    """The pin of the GD flavour that the REFERENCE holds: on the 1e6-sample S-GD seed set (env 1) and 3e5 samples of env 2 every
+    configuration the device projects passes the reference's own closure check (verification_class::Tsb_matrix / test_constraint,
+    compiled from the reference source into oracle/_ref/; tests/test_gd_kdl.cpp:61-75 applies exactly this to kdl::GD), convergence
+    is 100 % as in the reference's log, the mean projection distance sits on the log's 7.32, and the Newton iteration histogram
+    equals the committed fixture (tests/golden/gd_pin.json, tools/gen_golden_gd_pin.py) up to the chaotic samples."""
+    import json, os
+    from conftest import GOLD
+    from oracle import reflibs
+    from abb_dualarm_planning_b200 import Checker, sampling
+    assert reflibs.available(), "oracle/_ref/ is built by __graft_entry__.build() where /root/reference is mounted and travels with the snapshot"
+    pin = json.load(open(os.path.join(GOLD, "gd_pin.json")))
+    for env, key in ((1, "env1"), (2, "env2")):
+        c = ck if env == 1 else Checker(env=2)
+        P = pin[key]
+        n = P["n"]
+        q = sampling.sample_gd(P["seed"], 0, n)
+        ok, conv, it, qo = c.gd_project(q)
+        assert conv.all() and P["converged"] == n
+        _, passed = reflibs.tsb_check(qo, env)
+        assert passed.all()                                                    # every projected point, 0.1 / 0.5 mm rule of the reference
+        hist = np.bincount(it, minlength=64)[:64]
+        assert np.abs(hist - np.array(P["iteration_histogram"])).sum() <= 2e-4 * n      # measured: a handful of samples move by one iteration
+        assert abs(int(ok.sum()) - P["within_joint_limits"]) <= 3
+        d = np.linalg.norm(qo - q, axis=1).mean()
+        assert abs(d - P["projection_distance_mean"]) < 2e-3
+        if env == 1:
+            assert abs(d - pin["reference_log"]["kdl_distance_mean"]) < 0.05   # reference log: 7.32 over 10 000 runs
+        if env == 2:
+            c.close()
+
+
 def test_gd_rbs_vs_oracle(ck, oracle):
     q = oracle.sample_gd(3, 0, 6000)
     valid, qp = oracle.gd_validate(q)

@@ -179,3 +179,60 @@ def test_env2_mask_vs_binary(oracle_env2, gold):
     ok, valid, _ = oracle_env2.pcs_validate(q, 0, ik)
     assert (ok == np.unpackbits(g["ok_bits"])[:n]).all() and (valid == np.unpackbits(g["valid_bits"])[:n]).all()
     assert ok.sum() == 749 and valid.sum() == 314
+
+
+# ---- pins compiled from the reference's own sources (oracle/_ref/, built by oracle/Makefile where /root/reference is mounted) ----
+def _reflibs():
+    from oracle import reflibs
+    if not reflibs.available():
+        pytest.skip("oracle/_ref/ libraries not built (they are compiled from /root/reference, which is not mounted here)")
+    return reflibs
+
+
+def test_restatement_vs_apc_class_compiled_from_source(oracle, oracle_env2):
+    """FK, closure projection and joint limits of oracle/ckc_oracle_kin.cpp against the reference's own proj_classes/apc_class.cpp
+    (oracle/_ref/libapc_ref.so), both environments, both active chains"""
+    rl = _reflibs()
+    for env, orc in ((1, oracle), (2, oracle_env2)):
+        q, ik = orc.sample_pcs(11 + env, 0, 3000)
+        for robot in (0, 1):
+            T = rl.apc_fk(q[:200, 6 * robot:6 * robot + 6], robot + 1, env)          # the reference numbers its robots 1 and 2
+            To = np.array([orc.fk(r[6 * robot:6 * robot + 6], robot + 1) for r in q[:200]])
+            assert np.abs(T - To).max() < 1e-9                                        # mm; the reference evaluates 6 kB symbolic expressions
+        for ac in (0, 1):
+            ok_r, q_r = rl.apc_project(q, ac, ik, env)
+            ok_o, q_o = orc.pcs_project(q, ac, ik)
+            assert (ok_r == ok_o).all() and ok_o.sum() > 20
+            assert np.abs(q_r[ok_o == 1] - q_o[ok_o == 1]).max() < 1e-10
+        qq = np.concatenate([q_o, q * 1.2])
+        assert (rl.apc_limits(qq, env) == orc.check_angle_limits(qq)).all()
+
+
+def test_gd_restatement_pinned_by_reference_closure_check(oracle, oracle_env2, gold):
+    """The reference's own closure check (verification_class::Tsb_matrix / test_constraint compiled from source -- the test its
+    tests/test_gd_kdl.cpp applies to kdl::GD) accepts every point the restated Newton projection returns, rejects the raw
+    seeds, accepts the reference's solved path; the restatement's statistics sit on the reference's log (tests/results/kdl_gd.txt)"""
+    rl = _reflibs()
+    pin = json.load(open(os.path.join(GOLD, "gd_pin.json")))
+    path = gold("ref_path.npz")["path"]
+    _, ok = rl.tsb_check(path, 1)
+    assert ok.all()                                               # paths/path.txt: 321 closed configurations
+    assert rl.tsb_test_constraint(path[17], 1)                    # the member itself, not only the silent restatement of its rule
+    from abb_dualarm_planning_b200 import sampling
+    for env, orc, key in ((1, oracle, "env1"), (2, oracle_env2, "env2")):
+        q = sampling.sample_gd(1, 0, 4000)
+        okp, conv, it, qo = orc.gd_project(q)
+        assert conv.all()                                         # reference log: 100 % success from uniform seeds
+        _, passed = rl.tsb_check(qo, env)
+        assert passed.all()
+        _, raw = rl.tsb_check(q[:500], env)
+        assert raw.sum() == 0
+        hist = np.array(pin[key]["iteration_histogram"], float) / pin[key]["n"]
+        mine = np.bincount(it, minlength=64)[:64] / len(it)
+        assert np.abs(hist - mine).sum() < 0.08                   # 4000 samples of the fixture's 1e6-sample distribution
+        d = np.linalg.norm(qo - q, axis=1).mean()
+        assert abs(d - pin[key]["projection_distance_mean"]) < 0.15
+    ref = pin["reference_log"]
+    assert ref["kdl_success_rate"] == 1.0 and pin["env1"]["converged"] == pin["env1"]["n"]
+    assert abs(pin["env1"]["projection_distance_mean"] - ref["kdl_distance_mean"]) < 0.05      # 7.34 vs the reference's 7.32 (N = 10 000)
+    assert pin["env1"]["closure_check_passed"] == pin["env1"]["n"] and pin["env2"]["closure_check_passed"] == pin["env2"]["n"]
