@@ -41,6 +41,13 @@ def load_library():
     L = C.CDLL(p)
     vp, i64, dp = C.c_void_p, C.c_int64, C.c_void_p
     L.ckc_create.argtypes = [C.POINTER(vp), C.c_int, C.c_char_p, C.c_int]
+    L.ckc_create_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_char_p, C.POINTER(C.c_int), C.c_int]
+    L.ckc_num_devices.argtypes = [vp]
+    L.ckc_fk.argtypes = [vp, i64, dp, dp, dp]
+    L.ckc_ik.argtypes = [vp, i64, dp, dp, dp, dp, dp]
+    L.ckc_kdl_fk.argtypes = [vp, i64, dp, dp]
+    L.ckc_pcs_reconstruct_rbs.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, i64, C.POINTER(C.c_int64), dp]
+    L.ckc_gd_reconstruct_rbs.argtypes = [vp, dp, dp, dp, i64, C.POINTER(C.c_int64), dp]
     L.ckc_destroy.argtypes = [vp]; L.ckc_destroy.restype = None
     L.ckc_last_error.argtypes = [vp]; L.ckc_last_error.restype = C.c_char_p
     L.ckc_create_error.restype = C.c_char_p
@@ -99,10 +106,17 @@ def _i8(a, n):
 class Checker:
     """One libckc context (one CUDA device).  Mirrors the batch forms of the reference's StateValidityChecker API."""
 
-    def __init__(self, env=1, mesh_path=None, device=0):
+    def __init__(self, env=1, mesh_path=None, device=0, devices=None):
+        """device: one CUDA ordinal; devices = [d0, d1, ...]: a multi-device context (ckc_create_multi) whose host entry points
+        split every batch into contiguous ranges, one per device"""
         self.L = load_library()
         self.ctx = C.c_void_p()
-        rc = self.L.ckc_create(C.byref(self.ctx), int(env), (mesh_path or MESH_PACK).encode(), int(device))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.L.ckc_create_multi(C.byref(self.ctx), int(env), (mesh_path or MESH_PACK).encode(), arr, len(devices))
+            device = devices[0]
+        else:
+            rc = self.L.ckc_create(C.byref(self.ctx), int(env), (mesh_path or MESH_PACK).encode(), int(device))
         if rc != 0:
             msg = self.L.ckc_create_error().decode()
             self.ctx = None
@@ -201,6 +215,43 @@ class Checker:
         q, n = _q(q); valid = np.zeros(n, np.uint8); res = np.zeros(n)
         self._chk(self.L.ckc_rx_validate(self.ctx, n, _ptr(q), float(eps), _ptr(valid), _ptr(res)))
         return valid, res
+
+    # ---- single-arm kinematics, one to one with the reference's members ----
+    def fk(self, q6, robot):
+        """FKsolve_rob(q, robot_num): robot numbers are the reference's 1 and 2; returns [n, 4, 4]"""
+        q6 = np.ascontiguousarray(q6, np.float64).reshape(-1, 6); n = len(q6); rb = _i8(robot, n); T = np.empty((n, 4, 4))
+        self._chk(self.L.ckc_fk(self.ctx, n, _ptr(q6), _ptr(rb), _ptr(T)))
+        return T
+
+    def ik(self, T, robot, sol):
+        """IKsolve_rob(T, robot_num, solution_num) -> (ok [n], q6 [n, 6])"""
+        T = np.ascontiguousarray(T, np.float64).reshape(-1, 16); n = len(T); rb = _i8(robot, n); so = _i8(sol, n)
+        q6 = np.empty((n, 6)); ok = np.zeros(n, np.uint8)
+        self._chk(self.L.ckc_ik(self.ctx, n, _ptr(T), _ptr(rb), _ptr(so), _ptr(q6), _ptr(ok)))
+        return ok, q6
+
+    def kdl_fk(self, q):
+        """kdl::FK(q): tip frame of the 12-joint chain, [n, 4, 4]"""
+        q, n = _q(q); T = np.empty((n, 4, 4))
+        self._chk(self.L.ckc_kdl_fk(self.ctx, n, _ptr(q), _ptr(T)))
+        return T
+
+    def pcs_reconstruct_rbs(self, qa, qb, ac, ik, cap=4096):
+        """reconstructRBS of one edge: (ok, ordered configurations [m, 12] from qa to qb)"""
+        qa = np.ascontiguousarray(qa, np.float64).reshape(12); qb = np.ascontiguousarray(qb, np.float64).reshape(12)
+        out = np.empty((cap, 12)); m = C.c_int64(); ok = np.zeros(1, np.uint8)
+        self._chk(self.L.ckc_pcs_reconstruct_rbs(self.ctx, _ptr(qa), _ptr(qb), int(ac), int(ik), _ptr(out), cap, C.byref(m), _ptr(ok)))
+        return bool(ok[0]), out[:m.value].copy()
+
+    def gd_reconstruct_rbs(self, qa, qb, cap=4096):
+        qa = np.ascontiguousarray(qa, np.float64).reshape(12); qb = np.ascontiguousarray(qb, np.float64).reshape(12)
+        out = np.empty((cap, 12)); m = C.c_int64(); ok = np.zeros(1, np.uint8)
+        self._chk(self.L.ckc_gd_reconstruct_rbs(self.ctx, _ptr(qa), _ptr(qb), _ptr(out), cap, C.byref(m), _ptr(ok)))
+        return bool(ok[0]), out[:m.value].copy()
+
+    @property
+    def num_devices(self):
+        return self.L.ckc_num_devices(self.ctx)
 
     # ---- raw-pointer API (host or device addresses, e.g. torch .data_ptr()) ----
     def pcs_validate_ptr(self, n, q, ac, ik, q_out, ok, valid):

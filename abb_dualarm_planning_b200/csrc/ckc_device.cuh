@@ -177,9 +177,13 @@ __device__ __forceinline__ bool within_limits(const ckc_kin_dev& k, const double
 __device__ __forceinline__ double shfl_f64(double v, int src) {
     return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
 }
-__device__ __forceinline__ void warp_link_frames(const double* __restrict__ base, double qj, int lane, double* F64) {
+__device__ __forceinline__ void sincos_compact(double x, double* sn, double* cs);      /* defined with the GD kernel's tables below */
+__device__ __noinline__ void warp_link_frames(const double* __restrict__ base, double qj, int lane, double* F64) {
+    /* noinline + the compact sin / cos (no inlined Payne-Hanek path): k_collide's loop body must stay inside the 32 kB
+     * instruction cache level (measured: with libdevice's sincos inlined here the kernel grew by 17 kB and `no_instruction`
+     * became its second largest stall) */
     double sj = 0.0, cj = 1.0;
-    if (lane < 12) sincos(qj, &sj, &cj);
+    if (lane < 12) sincos_compact(qj, &sj, &cj);
     const int rob = lane >= 3 ? 1 : 0, row = lane - 3 * rob;
     const bool rl = lane < 6;
     double R0 = 0, R1 = 0, R2 = 0, T = 0;
@@ -416,6 +420,36 @@ __device__ __forceinline__ double tri_dist_coop(bool act, int lane, const v3& S0
     else if (act && e == 0) result = face_and_final(S0, S1, S2, T0, T1, T2, m_sd != 0, mall);
     result = shfl_f64(result, base > 31 ? 31 : base);         /* lane e = 0 of the group holds the value in both cases */
     return result;
+}
+
+/* Sequential TriDist, one THREAD per triangle pair (the heavy-configuration kernel): the loop of the scalar routine over the nine
+ * edge pairs with exactly the per-edge-pair arithmetic of the cooperative version above (same seg_points_inl, same a / b / p), so
+ * both return the same value. */
+__device__ __noinline__ double tri_dist_seq(const v3 S0, const v3 S1, const v3 S2, const v3 T0, const v3 T1, const v3 T2) {
+    double mindd;
+    { const v3 d0 = S0 - T0; mindd = dot(d0, d0) + 1; }
+    bool shown_disjoint = false;
+#pragma unroll 1
+    for (int e = 0; e < 9; e++) {
+        const int i = e / 3, j = e - 3 * i;
+        const v3 Sa = i == 0 ? S0 : (i == 1 ? S1 : S2), Sb = i == 0 ? S1 : (i == 1 ? S2 : S0), Sc = i == 0 ? S2 : (i == 1 ? S0 : S1);
+        const v3 Ta = j == 0 ? T0 : (j == 1 ? T1 : T2), Tb = j == 0 ? T1 : (j == 1 ? T2 : T0), Tc = j == 0 ? T2 : (j == 1 ? T0 : T1);
+        v3 VEC, P, Q;
+        seg_points_inl(VEC, P, Q, Sa, Sb - Sa, Ta, Tb - Ta);
+        const v3 V = Q - P;
+        const double dd = dot(V, V);
+        if (dd <= mindd) {
+            mindd = dd;
+            double a = dot(Sc - P, VEC);
+            double b = dot(Tc - Q, VEC);
+            if ((a <= 0) && (b >= 0)) return sqrt(dd);
+            const double pp = dot(V, VEC);
+            if (a < 0) a = 0;
+            if (b > 0) b = 0;
+            if ((pp - a + b) > 0) shown_disjoint = true;
+        }
+    }
+    return face_and_final(S0, S1, S2, T0, T1, T2, shown_disjoint, mindd);
 }
 
 }  // namespace ckc
@@ -771,6 +805,9 @@ struct gd_chain_u {
     static constexpr double tx[12] = { 0, 0, 149.6, 152.4, 66, -1 /* rod */, 66, 152.4, 149.6, 0, 0, 0 };
     static constexpr double tz[12] = { 124, 270, 70, 0, 0, 0, 0, 0, -70, -270, -124, -166 };
 };
+
+/* sin / cos for the link frames of k_collide: Cody-Waite + fdlibm kernels as above (< 1 ulp), library call only for |x| >= 1e4 */
+__device__ __forceinline__ void sincos_compact(double x, double* sn, double* cs) { sincos_fast(x, sn, cs); }
 
 /* sin / cos without the large-argument branch: `bad` collects |x| >= 1e4 (or NaN), the caller redoes the iteration on the cold path */
 __device__ __forceinline__ void sincos_nobranch(double x, double* sn, double* cs, bool& bad) {

@@ -13,7 +13,9 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <algorithm>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #define CKC_VERSION_STR "ckc-b200 0.1 (sm_100a)"
@@ -61,6 +63,9 @@ struct ckc_lane {
 };
 
 struct ckc_ctx {
+    /* multi-device context (ckc_create_multi): owns one ordinary context per device and nothing else; every host entry point
+     * splits its batch into contiguous ranges, one per child, each driven by its own host thread */
+    std::vector<ckc_ctx*> children;
     int env = 1, device = 0, num_sms = 148;
     std::string err;
     ckc_kin_dev kin;
@@ -72,7 +77,7 @@ struct ckc_ctx {
     dev_buf d_nodes, d_tris, d_ctr, d_pairtab, d_static, d_pairhits, d_pairorder;
     dev_buf d_cidx, d_cq, d_ccount;                     /* compact outputs of the *_compact entry points (per chunk regions) */
     void* h_stage = nullptr; size_t h_stage_cap = 0;    /* pinned staging of the compact outputs */
-    dev_buf rbs_seg[2], rbs_cand, rbs_pool, rbs_eok, rbs_nck, rbs_hit, rbs_eac, rbs_eik;      /* RBS frontier storage, kept between calls */
+    dev_buf rbs_seg[2], rbs_cand, rbs_pool, rbs_eok, rbs_nck, rbs_hit, rbs_eac, rbs_eik, rbs_nt;      /* RBS frontier storage, kept between calls */
     /* per-chunk work buffers: CKC_NUM_LANES independent sets, each with its own stream, so that the host entry points
      * can overlap the H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 */
     ckc_lane lanes[CKC_NUM_LANES];
@@ -110,6 +115,11 @@ struct stage_scope {
 
 static int fail(ckc_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, CKC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+/* A failure in the middle of a pipelined call must not return while earlier chunks still copy into the caller's buffers
+ * on other lanes: drain every lane first (errors of the drain itself are ignored, the first failure is what gets reported). */
+static void drain_lanes(ckc_ctx* ctx);
+#define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { drain_lanes(ctx); return fail(ctx, CKC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
 
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* mesh input                                                                                                         */
@@ -421,6 +431,7 @@ extern "C" int ckc_num_pairs(const ckc_ctx* ctx) { return ctx ? ctx->world.npair
 
 static thread_local std::string g_create_error;
 extern "C" const char* ckc_create_error(void) { return g_create_error.c_str(); }
+extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int device);
 
 extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int device) {
     if (!out || (env != 1 && env != 2) || !mesh_path) { g_create_error = "bad argument"; return CKC_ERR_ARG; }
@@ -559,9 +570,10 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
 
 extern "C" void ckc_destroy(ckc_ctx* ctx) {
     if (!ctx) return;
+    if (!ctx->children.empty()) { for (ckc_ctx* c : ctx->children) ckc_destroy(c); delete ctx; return; }
     cudaSetDevice(ctx->device);
     dev_buf* bufs[] = { &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_pairhits, &ctx->d_pairorder, &ctx->rbs_seg[0], &ctx->rbs_seg[1],
-                        &ctx->rbs_cand, &ctx->rbs_pool, &ctx->rbs_eok, &ctx->rbs_nck, &ctx->rbs_hit, &ctx->rbs_eac, &ctx->rbs_eik };
+                        &ctx->rbs_cand, &ctx->rbs_pool, &ctx->rbs_eok, &ctx->rbs_nck, &ctx->rbs_hit, &ctx->rbs_eac, &ctx->rbs_eik, &ctx->rbs_nt };
     for (dev_buf* b : bufs) b->release();
     for (int l = 0; l < CKC_NUM_LANES; l++) { ctx->lanes[l].release(); if (ctx->lanes[l].ev_done) cudaEventDestroy(ctx->lanes[l].ev_done); if (ctx->lanes[l].ev_p) cudaEventDestroy(ctx->lanes[l].ev_p); if (ctx->lanes[l].ev_c) cudaEventDestroy(ctx->lanes[l].ev_c);
         if (ctx->lanes[l].st_hi) cudaStreamDestroy(ctx->lanes[l].st_hi); if (ctx->lanes[l].st) cudaStreamDestroy(ctx->lanes[l].st); }
@@ -571,7 +583,50 @@ extern "C" void ckc_destroy(ckc_ctx* ctx) {
     delete ctx;
 }
 
+static void drain_lanes(ckc_ctx* ctx) {
+    if (!ctx) return;
+    for (int l = 0; l < CKC_NUM_LANES; l++) if (ctx->lanes[l].st) cudaStreamSynchronize(ctx->lanes[l].st);
+}
+
+/* multi-device dispatch: range [off, off + cnt) of an n-unit batch goes to child g; one host thread per child */
+static int multi_dispatch(ckc_ctx* ctx, int64_t n, const std::function<int(ckc_ctx*, int64_t, int64_t)>& fn) {
+    const int G = (int)ctx->children.size();
+    std::vector<int> rc(G, CKC_OK);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++) {
+        const int64_t lo = n * g / G, hi = n * (g + 1) / G;
+        if (hi <= lo) continue;
+        th.emplace_back([&, g, lo, hi] { rc[g] = fn(ctx->children[g], lo, hi - lo); });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; g++)
+        if (rc[g] != CKC_OK) { ctx->err = "device " + std::to_string(ctx->children[g]->device) + ": " + ctx->children[g]->err; return rc[g]; }
+    return CKC_OK;
+}
+#define MULTI(n, expr) do { if (ctx && !ctx->children.empty()) { if ((n) < 0) return fail(ctx, CKC_ERR_ARG, "bad argument"); \
+    return multi_dispatch(ctx, (n), [&](ckc_ctx* c, int64_t off, int64_t cnt) -> int { (void)off; (void)cnt; return (expr); }); } } while (0)
+#define OFF(p, stride) ((p) ? (p) + off * (stride) : nullptr)
+
+extern "C" int ckc_create_multi(ckc_ctx** out, int env, const char* mesh_path, const int* devices, int ndev) {
+    if (!out || !devices || ndev < 1 || ndev > 64) { g_create_error = "bad argument"; return CKC_ERR_ARG; }
+    *out = nullptr;
+    ckc_ctx* m = new ckc_ctx();
+    m->env = env; m->device = devices[0];
+    memset(&m->host_stats, 0, sizeof(m->host_stats));
+    for (int g = 0; g < ndev; g++) {
+        ckc_ctx* c = nullptr;
+        const int rc = ckc_create(&c, env, mesh_path, devices[g]);
+        if (rc != CKC_OK) { for (ckc_ctx* x : m->children) ckc_destroy(x); delete m; return rc; }
+        m->children.push_back(c);
+    }
+    m->world.npairs = m->children[0]->world.npairs;
+    *out = m;
+    return CKC_OK;
+}
+extern "C" int ckc_num_devices(const ckc_ctx* ctx) { return !ctx ? CKC_ERR_ARG : (ctx->children.empty() ? 1 : (int)ctx->children.size()); }
+
 extern "C" int ckc_synchronize(ckc_ctx* ctx) {
+    MULTI(ctx->children.size(), ckc_synchronize(c));
     if (!ctx) return CKC_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     for (int l = 0; l < CKC_NUM_LANES; l++) CU(cudaStreamSynchronize(ctx->lanes[l].st));
@@ -583,6 +638,15 @@ extern "C" int ckc_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? 
 
 extern "C" int ckc_get_stats(ckc_ctx* ctx, ckc_stats* out) {
     if (!ctx || !out) return CKC_ERR_ARG;
+    if (!ctx->children.empty()) {          /* sums over the devices */
+        memset(out, 0, sizeof(*out));
+        for (ckc_ctx* c : ctx->children) {
+            ckc_stats s; const int rc = ckc_get_stats(c, &s); if (rc) return rc;
+            int64_t* a = (int64_t*)out; const int64_t* b = (const int64_t*)&s;
+            for (size_t i = 0; i < sizeof(ckc_stats) / sizeof(int64_t); i++) a[i] += b[i];
+        }
+        return CKC_OK;
+    }
     CU(cudaSetDevice(ctx->device));
     ckc_counters_dev c;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -597,6 +661,7 @@ extern "C" int ckc_get_stats(ckc_ctx* ctx, ckc_stats* out) {
 
 extern "C" int ckc_reset_stats(ckc_ctx* ctx) {
     if (!ctx) return CKC_ERR_ARG;
+    if (!ctx->children.empty()) { for (ckc_ctx* c : ctx->children) { const int rc = ckc_reset_stats(c); if (rc) return rc; } return CKC_OK; }
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaMemset(ctx->d_ctr.p, 0, sizeof(ckc_counters_dev)));
@@ -616,7 +681,7 @@ static int run_collision_stage(ckc_ctx* ctx, ckc_lane& L, int64_t m_max, const d
                                uint8_t* d_hit, uint8_t* d_valid, uint8_t* d_pair_flags, cudaStream_t st, bool allow_hop = true) {
     if (m_max <= 0) return CKC_OK;
     CU(L.ovf.reserve((size_t)m_max * 4));
-    CU(L.bigstack.reserve((size_t)16 * 8 * 65536 * 4));
+    CU(L.bigstack.reserve((size_t)160 * 65536 * 4));      /* k_collide_heavy: one 65 536-entry stack per block (<= 160 blocks); diagnostic form: 128 warps */
     /* on the lane's own stream the collision stage moves to the lane's HIGH-PRIORITY stream: its blocks then win the SM slots
      * that free up while the persistent projection kernels of the other lanes are still queued */
     const bool hop = allow_hop && ctx->overlap && st == L.st && L.st_hi;      /* RBS levels run alone: no hop, four stream operations less per level */
@@ -703,35 +768,35 @@ static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, co
         const int64_t c = std::min(C, n - off);
         ckc_lane& L = ctx->lanes[k % ctx->host_lanes];
         cudaStream_t st = L.st;
-        CU(L.qin.reserve((size_t)C * 96)); CU(L.qout.reserve((size_t)C * 96)); CU(L.ok.reserve((size_t)C)); CU(L.valid.reserve((size_t)C));
-        CU(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        CUS(L.qin.reserve((size_t)C * 96)); CUS(L.qout.reserve((size_t)C * 96)); CUS(L.ok.reserve((size_t)C)); CUS(L.valid.reserve((size_t)C));
+        CUS(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
         int rc;
         if (flavour == 0) {
-            CU(L.ac.reserve((size_t)C)); CU(L.ik.reserve((size_t)C));
-            if (ac) CU(cudaMemcpyAsync(L.ac.p, ac + off, (size_t)c, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(L.ik.p, ik + off, (size_t)c, cudaMemcpyHostToDevice, st));
+            CUS(L.ac.reserve((size_t)C)); CUS(L.ik.reserve((size_t)C));
+            if (ac) CUS(cudaMemcpyAsync(L.ac.p, ac + off, (size_t)c, cudaMemcpyHostToDevice, st));
+            CUS(cudaMemcpyAsync(L.ik.p, ik + off, (size_t)c, cudaMemcpyHostToDevice, st));
             rc = run_pcs_chunk(ctx, L, c, L.qin.as<double>(), AOS, ac ? L.ac.as<int8_t>() : nullptr, L.ik.as<int8_t>(), 0, 0, 0, L.qout.as<double>(), AOS,
                                L.ok.as<uint8_t>(), L.valid.as<uint8_t>(), collide, st);
         } else {
-            CU(L.aux.reserve((size_t)C)); CU(L.aux2.reserve((size_t)C * 4));
+            CUS(L.aux.reserve((size_t)C)); CUS(L.aux2.reserve((size_t)C * 4));
             rc = run_gd_chunk(ctx, L, c, L.qin.as<double>(), AOS, 0, 0, 0, L.qout.as<double>(), AOS, L.ok.as<uint8_t>(), L.aux.as<uint8_t>(),
                               L.aux2.as<int32_t>(), L.valid.as<uint8_t>(), collide, st);
         }
-        if (rc) return rc;
-        if (q_out) CU(cudaMemcpyAsync(q_out + off * 12, L.qout.p, (size_t)c * 96, cudaMemcpyDeviceToHost, st));
-        if (ok) CU(cudaMemcpyAsync(ok + off, L.ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
-        if (conv) CU(cudaMemcpyAsync(conv + off, L.aux.p, (size_t)c, cudaMemcpyDeviceToHost, st));
-        if (iters) CU(cudaMemcpyAsync(iters + off, L.aux2.p, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
-        if (valid) CU(cudaMemcpyAsync(valid + off, L.valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (rc) { drain_lanes(ctx); return rc; }
+        if (q_out) CUS(cudaMemcpyAsync(q_out + off * 12, L.qout.p, (size_t)c * 96, cudaMemcpyDeviceToHost, st));
+        if (ok) CUS(cudaMemcpyAsync(ok + off, L.ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (conv) CUS(cudaMemcpyAsync(conv + off, L.aux.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if (iters) CUS(cudaMemcpyAsync(iters + off, L.aux2.p, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+        if (valid) CUS(cudaMemcpyAsync(valid + off, L.valid.p, (size_t)c, cudaMemcpyDeviceToHost, st));
         if (co) {
             int32_t* dci = ctx->d_cidx.as<int32_t>() + off; double* dcq = ctx->d_cq.as<double>() + off * 12; int32_t* dcc = ctx->d_ccount.as<int32_t>() + k;
             ckc_launch_compact_valid(c, (int32_t)off, L.valid.as<uint8_t>(), L.qout.as<double>(), AOS, dci, dcq, dcc, st);
             ctx->launches++;
-            CU(cudaGetLastError());
+            CUS(cudaGetLastError());
             const int64_t cc = std::min(ccopy, c);
-            CU(cudaMemcpyAsync(h_cnt + k, dcc, 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(h_idx + (size_t)k * ccopy, dci, (size_t)cc * 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(h_q + (size_t)k * ccopy * 12, dcq, (size_t)cc * 96, cudaMemcpyDeviceToHost, st));
+            CUS(cudaMemcpyAsync(h_cnt + k, dcc, 4, cudaMemcpyDeviceToHost, st));
+            CUS(cudaMemcpyAsync(h_idx + (size_t)k * ccopy, dci, (size_t)cc * 4, cudaMemcpyDeviceToHost, st));
+            CUS(cudaMemcpyAsync(h_q + (size_t)k * ccopy * 12, dcq, (size_t)cc * 96, cudaMemcpyDeviceToHost, st));
         }
     }
     for (int l = 0; l < CKC_NUM_LANES; l++) CU(cudaStreamSynchronize(ctx->lanes[l].st));
@@ -758,19 +823,47 @@ static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, co
 }
 
 extern "C" int ckc_pcs_project(ckc_ctx* ctx, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out, uint8_t* ok) {
+    MULTI(n, ckc_pcs_project(c, cnt, OFF(q, 12), OFF(ac, 1), OFF(ik, 1), OFF(q_out, 12), OFF(ok, 1)));
     return project_host(ctx, 0, n, q, ac, ik, q_out, ok, nullptr, nullptr, nullptr, false);
 }
 extern "C" int ckc_pcs_validate(ckc_ctx* ctx, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out, uint8_t* ok, uint8_t* valid) {
+    MULTI(n, ckc_pcs_validate(c, cnt, OFF(q, 12), OFF(ac, 1), OFF(ik, 1), OFF(q_out, 12), OFF(ok, 1), OFF(valid, 1)));
     if (!valid) return fail(ctx, CKC_ERR_ARG, "valid must not be NULL");
     if (ctx) ctx->host_stats.is_valid_calls += n;
     return project_host(ctx, 0, n, q, ac, ik, q_out, ok, nullptr, nullptr, valid, true);
 }
 extern "C" int ckc_gd_project(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* ok, uint8_t* converged, int32_t* iters) {
+    MULTI(n, ckc_gd_project(c, cnt, OFF(q, 12), OFF(q_out, 12), OFF(ok, 1), OFF(converged, 1), OFF(iters, 1)));
     return project_host(ctx, 1, n, q, nullptr, nullptr, q_out, ok, converged, iters, nullptr, false);
 }
+/* compact results of a multi-device context: every child fills a private buffer, the parts are concatenated in device order */
+static int compact_multi(ckc_ctx* ctx, int flavour, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, uint8_t* valid,
+                         int64_t* n_valid, int32_t* idx, double* q_valid, int64_t cap) {
+    const int G = (int)ctx->children.size();
+    std::vector<std::vector<int32_t>> pi(G); std::vector<std::vector<double>> pq(G); std::vector<int64_t> cntv(G, 0), offv(G, 0);
+    int rc = multi_dispatch(ctx, n, [&](ckc_ctx* c, int64_t off, int64_t cnt) -> int {
+        int g = 0; while (ctx->children[g] != c) g++;
+        const int64_t room = std::min(cnt, cap);
+        pi[g].resize((size_t)room); pq[g].resize((size_t)room * 12); offv[g] = off;
+        return flavour == 0 ? ckc_pcs_validate_compact(c, cnt, q + off * 12, OFF(ac, 1), ik + off, OFF(valid, 1), &cntv[g], pi[g].data(), pq[g].data(), room)
+                            : ckc_gd_validate_compact(c, cnt, q + off * 12, OFF(valid, 1), &cntv[g], pi[g].data(), pq[g].data(), room);
+    });
+    if (rc != CKC_OK && rc != CKC_ERR_CAPACITY) return rc;
+    int64_t total = 0;
+    for (int g = 0; g < G; g++) {
+        const int64_t have = std::min<int64_t>(cntv[g], (int64_t)pi[g].size()), take = std::max<int64_t>(0, std::min(have, cap - total));
+        for (int64_t i = 0; i < take; i++) idx[total + i] = pi[g][(size_t)i] + (int32_t)offv[g];
+        if (take > 0) memcpy(q_valid + total * 12, pq[g].data(), (size_t)take * 96);
+        total += cntv[g];
+    }
+    *n_valid = total;
+    return total > cap ? fail(ctx, CKC_ERR_CAPACITY, "compact output capacity too small") : CKC_OK;
+}
+
 extern "C" int ckc_pcs_validate_compact(ckc_ctx* ctx, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, uint8_t* valid,
                                         int64_t* n_valid, int32_t* idx, double* q_valid, int64_t cap) {
     if (!n_valid || !idx || !q_valid || cap < 0) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    if (ctx && !ctx->children.empty()) return (n < 0 || !q || !ik) ? fail(ctx, CKC_ERR_ARG, "bad argument") : compact_multi(ctx, 0, n, q, ac, ik, valid, n_valid, idx, q_valid, cap);
     if (ctx) ctx->host_stats.is_valid_calls += n;
     *n_valid = 0;
     compact_out co = { n_valid, idx, q_valid, cap };
@@ -778,12 +871,14 @@ extern "C" int ckc_pcs_validate_compact(ckc_ctx* ctx, int64_t n, const double* q
 }
 extern "C" int ckc_gd_validate_compact(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* valid, int64_t* n_valid, int32_t* idx, double* q_valid, int64_t cap) {
     if (!n_valid || !idx || !q_valid || cap < 0) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    if (ctx && !ctx->children.empty()) return (n < 0 || !q) ? fail(ctx, CKC_ERR_ARG, "bad argument") : compact_multi(ctx, 1, n, q, nullptr, nullptr, valid, n_valid, idx, q_valid, cap);
     if (ctx) ctx->host_stats.is_valid_calls += n;
     *n_valid = 0;
     compact_out co = { n_valid, idx, q_valid, cap };
     return project_host(ctx, 1, n, q, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, valid, true, &co);
 }
 extern "C" int ckc_gd_validate(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* valid) {
+    MULTI(n, ckc_gd_validate(c, cnt, OFF(q, 12), OFF(q_out, 12), OFF(valid, 1)));
     if (!valid) return fail(ctx, CKC_ERR_ARG, "valid must not be NULL");
     if (ctx) ctx->host_stats.is_valid_calls += n;
     return project_host(ctx, 1, n, q, nullptr, nullptr, q_out, nullptr, nullptr, nullptr, valid, true);
@@ -825,6 +920,7 @@ static int dev_fanout(ckc_ctx* ctx, cudaStream_t user, int64_t n, bool fan, F bo
 }
 
 extern "C" int ckc_set_overlap(ckc_ctx* ctx, int enable) {
+    if (ctx && !ctx->children.empty()) return multi_dispatch(ctx, (int64_t)ctx->children.size(), [&](ckc_ctx* c, int64_t, int64_t) { return ckc_set_overlap(c, enable); });
     if (!ctx) return CKC_ERR_ARG;
     ctx->overlap = enable != 0;
     return CKC_OK;
@@ -832,6 +928,7 @@ extern "C" int ckc_set_overlap(ckc_ctx* ctx, int enable) {
 
 extern "C" int ckc_pcs_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, const int8_t* d_ac, const int8_t* d_ik, double* d_q_out,
                                     uint8_t* d_ok, uint8_t* d_valid, void* stream) {
+    if (ctx && !ctx->children.empty()) return fail(ctx, CKC_ERR_ARG, "device-resident entry points take a single-device context");
     if (!ctx || n < 0 || !d_q || !d_ik || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     return dev_fanout(ctx, (cudaStream_t)stream, n, true, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
@@ -845,6 +942,7 @@ extern "C" int ckc_pcs_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, 
 }
 
 extern "C" int ckc_spcs_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out, uint8_t* d_ok, uint8_t* d_valid, void* stream) {
+    if (ctx && !ctx->children.empty()) return fail(ctx, CKC_ERR_ARG, "device-resident entry points take a single-device context");
     if (!ctx || n < 0 || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     return dev_fanout(ctx, (cudaStream_t)stream, n, true, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
@@ -856,6 +954,7 @@ extern "C" int ckc_spcs_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_
 }
 
 extern "C" int ckc_gd_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, double* d_q_out, uint8_t* d_valid, void* stream) {
+    if (ctx && !ctx->children.empty()) return fail(ctx, CKC_ERR_ARG, "device-resident entry points take a single-device context");
     if (!ctx || n < 0 || !d_q || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     return dev_fanout(ctx, (cudaStream_t)stream, n, ctx->gd_fan /* off by default: the persistent Newton kernel fills the GPU; chunk tails cost more than the overlap gains (measured) */, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
@@ -867,6 +966,7 @@ extern "C" int ckc_gd_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, d
 }
 
 extern "C" int ckc_sgd_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out, uint8_t* d_ok, uint8_t* d_valid, void* stream) {
+    if (ctx && !ctx->children.empty()) return fail(ctx, CKC_ERR_ARG, "device-resident entry points take a single-device context");
     if (!ctx || n < 0 || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     return dev_fanout(ctx, (cudaStream_t)stream, n, ctx->gd_fan /* off by default: the persistent Newton kernel fills the GPU; chunk tails cost more than the overlap gains (measured) */, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
@@ -900,11 +1000,29 @@ static int collide_host(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* hit, 
     }
     return CKC_OK;
 }
-extern "C" int ckc_collide(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* hit) { return collide_host(ctx, n, q, hit, nullptr); }
-extern "C" int ckc_collide_pairs(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* flags) { return collide_host(ctx, n, q, nullptr, flags); }
+extern "C" int ckc_collide(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* hit) {
+    MULTI(n, ckc_collide(c, cnt, OFF(q, 12), OFF(hit, 1))); return collide_host(ctx, n, q, hit, nullptr); }
+extern "C" int ckc_collide_pairs(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* flags) {
+    MULTI(n, ckc_collide_pairs(c, cnt, OFF(q, 12), OFF(flags, CKC_MAX_PAIRS))); return collide_host(ctx, n, q, nullptr, flags); }
+
+/* debug aid (not part of include/ckc.h): box rounds | triangle steps << 16 that k_collide spent on each configuration */
+extern uint32_t* g_ckc_dbg_rounds;
+extern "C" int ckc_debug_collide_rounds(ckc_ctx* ctx, int64_t n, const double* q, uint32_t* rounds) {
+    if (!ctx || !ctx->children.empty() || n <= 0 || n > (1 << 18) || !q || !rounds) return CKC_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    dev_buf d; CU(d.reserve((size_t)n * 4));
+    std::vector<uint8_t> hit((size_t)n);
+    g_ckc_dbg_rounds = d.as<uint32_t>();
+    const int rc = collide_host(ctx, n, q, hit.data(), nullptr);
+    g_ckc_dbg_rounds = nullptr;
+    if (rc == CKC_OK) cudaMemcpy(rounds, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    d.release();
+    return rc;
+}
 
 /* ---------------------------------------------------------------------------------------------------------------- */
 extern "C" int ckc_check_angle_limits(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* ok) {
+    MULTI(n, ckc_check_angle_limits(c, cnt, OFF(q, 12), OFF(ok, 1)));
     if (!ctx || n < 0 || (n > 0 && (!q || !ok))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     ckc_lane& L = ctx->lanes[0];
@@ -923,6 +1041,7 @@ extern "C" int ckc_check_angle_limits(ckc_ctx* ctx, int64_t n, const double* q, 
 }
 
 extern "C" int ckc_identify_ik(ckc_ctx* ctx, int64_t n, const double* q, int8_t* ik01) {
+    MULTI(n, ckc_identify_ik(c, cnt, OFF(q, 12), OFF(ik01, 2)));
     if (!ctx || n < 0 || (n > 0 && (!q || !ik01))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     ckc_lane& L = ctx->lanes[0];
@@ -942,6 +1061,7 @@ extern "C" int ckc_identify_ik(ckc_ctx* ctx, int64_t n, const double* q, int8_t*
 
 /* isValid(const ob::State*)  StateValidityCheckerPCS.cpp:323-357 */
 extern "C" int ckc_pcs_is_valid(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* valid) {
+    MULTI(n, ckc_pcs_is_valid(c, cnt, OFF(q, 12), OFF(valid, 1)));
     if (!ctx || n < 0 || (n > 0 && (!q || !valid))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     ckc_lane& L = ctx->lanes[0];
@@ -969,7 +1089,65 @@ extern "C" int ckc_pcs_is_valid(ckc_ctx* ctx, int64_t n, const double* q, uint8_
     return CKC_OK;
 }
 
+/* FKsolve_rob / IKsolve_rob / kdl::FK one to one (the drop-in classes expose them; the batched entry points above fuse them) */
+extern "C" int ckc_fk(ckc_ctx* ctx, int64_t n, const double* q6, const int8_t* robot, double* T16) {
+    MULTI(n, ckc_fk(c, cnt, OFF(q6, 6), OFF(robot, 1), OFF(T16, 16)));
+    if (!ctx || n < 0 || (n > 0 && (!q6 || !robot || !T16))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    ckc_lane& L = ctx->lanes[0]; cudaStream_t st = L.st;
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        CU(L.qin.reserve((size_t)c * 48)); CU(L.ik.reserve((size_t)c)); CU(L.qout.reserve((size_t)c * 128));
+        CU(cudaMemcpyAsync(L.qin.p, q6 + off * 6, (size_t)c * 48, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(L.ik.p, robot + off, (size_t)c, cudaMemcpyHostToDevice, st));
+        ckc_launch_fk(ctx->kin, c, L.qin.as<double>(), L.ik.as<int8_t>(), L.qout.as<double>(), st);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(T16 + off * 16, L.qout.p, (size_t)c * 128, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return CKC_OK;
+}
+extern "C" int ckc_ik(ckc_ctx* ctx, int64_t n, const double* T16, const int8_t* robot, const int8_t* sol, double* q6, uint8_t* ok) {
+    MULTI(n, ckc_ik(c, cnt, OFF(T16, 16), OFF(robot, 1), OFF(sol, 1), OFF(q6, 6), OFF(ok, 1)));
+    if (!ctx || n < 0 || (n > 0 && (!T16 || !robot || !sol || !q6 || !ok))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    ckc_lane& L = ctx->lanes[0]; cudaStream_t st = L.st;
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        CU(L.qin.reserve((size_t)c * 128)); CU(L.ik.reserve((size_t)c)); CU(L.ac.reserve((size_t)c)); CU(L.qout.reserve((size_t)c * 48)); CU(L.ok.reserve((size_t)c));
+        CU(cudaMemcpyAsync(L.qin.p, T16 + off * 16, (size_t)c * 128, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(L.ac.p, robot + off, (size_t)c, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(L.ik.p, sol + off, (size_t)c, cudaMemcpyHostToDevice, st));
+        ckc_launch_ik(ctx->kin, c, L.qin.as<double>(), L.ac.as<int8_t>(), L.ik.as<int8_t>(), L.qout.as<double>(), L.ok.as<uint8_t>(), st);
+        ctx->launches++; ctx->host_stats.ik_calls += c;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(q6 + off * 6, L.qout.p, (size_t)c * 48, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ok + off, L.ok.p, (size_t)c, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return CKC_OK;
+}
+extern "C" int ckc_kdl_fk(ckc_ctx* ctx, int64_t n, const double* q12, double* T16) {
+    MULTI(n, ckc_kdl_fk(c, cnt, OFF(q12, 12), OFF(T16, 16)));
+    if (!ctx || n < 0 || (n > 0 && (!q12 || !T16))) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    ckc_lane& L = ctx->lanes[0]; cudaStream_t st = L.st;
+    for (int64_t off = 0; off < n; off += ctx->chunk) {
+        const int64_t c = std::min(ctx->chunk, n - off);
+        CU(L.qin.reserve((size_t)c * 96)); CU(L.qout.reserve((size_t)c * 128));
+        CU(cudaMemcpyAsync(L.qin.p, q12 + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        ckc_launch_kdl_fk(ctx->kin, c, L.qin.as<double>(), L.qout.as<double>(), st);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(T16 + off * 16, L.qout.p, (size_t)c * 128, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return CKC_OK;
+}
+
 extern "C" int ckc_measure_fma_peak(ckc_ctx* ctx, int precision, double* tflops) {
+    if (ctx && !ctx->children.empty()) return ckc_measure_fma_peak(ctx->children[0], precision, tflops);
     if (!ctx || !tflops || (precision != 32 && precision != 64)) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     ckc_lane& L = ctx->lanes[0];
@@ -1001,6 +1179,7 @@ extern "C" int ckc_measure_fma_peak(ckc_ctx* ctx, int precision, double* tflops)
 /* GD / RX entry points                                                                                               */
 /* ---------------------------------------------------------------------------------------------------------------- */
 extern "C" int ckc_rx_validate(ckc_ctx* ctx, int64_t n, const double* q, double epsilon, uint8_t* valid, double* resid) {
+    MULTI(n, ckc_rx_validate(c, cnt, OFF(q, 12), epsilon, OFF(valid, 1), OFF(resid, 1)));
     if (!ctx || n < 0 || (n > 0 && (!q || !valid))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     ckc_lane& L = ctx->lanes[0];
@@ -1040,8 +1219,10 @@ static cudaError_t reserve_keep(dev_buf& b, size_t bytes, size_t used, cudaStrea
     return cudaSuccess;
 }
 
+struct rbs_recon { double* confs; int64_t cap; int64_t* n_confs; };       /* reconstructRBS: ordered configurations of ONE edge */
+
 static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa, const double* qb, const int8_t* ac, const int8_t* ik,
-                    uint8_t* ok, int32_t* nchecks) {
+                    uint8_t* ok, int32_t* nchecks, const rbs_recon* rec = nullptr) {
     if (!ctx || n_edges < 0 || n_edges > (1 << 28) || (n_edges > 0 && (!qa || !qb || !ok || (flavour == 0 && !ik)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     if (n_edges == 0) return CKC_OK;
     CU(cudaSetDevice(ctx->device));
@@ -1054,6 +1235,8 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
     CU(seg[0].reserve((size_t)seg_cap * 16)); CU(seg[1].reserve((size_t)seg_cap * 16)); CU(cand.reserve((size_t)seg_cap * 8));
     CU(pool.reserve((size_t)(2 * (int64_t)ne + seg_cap) * 96));
     CU(eok.reserve(ne)); CU(nck.reserve((size_t)ne * 4)); CU(eac.reserve(ne)); CU(eik.reserve(ne));
+    dev_buf& nt = ctx->rbs_nt;
+    if (rec) CU(nt.reserve(pool.cap / 12));
     /* endpoints interleaved: node 2e = a, node 2e+1 = b */
     CU(cudaMemcpy2DAsync(pool.p, 192, qa, 96, 96, ne, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpy2DAsync((char*)pool.p + 96, 192, qb, 96, 96, ne, cudaMemcpyHostToDevice, st));
@@ -1065,6 +1248,7 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
     auto make = [&](int c) {
         ckc_rbs_dev r;
         r.nodes = pool.as<double>();
+        r.node_t = rec ? nt.as<double>() : nullptr;
         int32_t* s0 = seg[c].as<int32_t>(); int32_t* s1 = seg[1 - c].as<int32_t>();
         const int64_t cap0 = (int64_t)(seg[c].cap / 16), cap1 = (int64_t)(seg[1 - c].cap / 16);
         r.seg_a = s0; r.seg_b = s0 + cap0; r.seg_edge = s0 + 2 * cap0; r.seg_depth = s0 + 3 * cap0;
@@ -1085,6 +1269,7 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
         if ((int64_t)(cand.cap / 8) < nseg) { cand.release(); CU(cand.reserve((size_t)(nseg + 1024) * 8)); }
         /* grow geometrically: a cudaMalloc / cudaFree pair per level would dominate the deep, thin tail of the frontier */
         if ((size_t)(nnodes + nseg) * 96 > pool.cap) CU(reserve_keep(pool, (size_t)((nnodes + nseg) * 3 / 2 + 4096) * 96, (size_t)nnodes * 96, st));
+        if (rec && (size_t)(nnodes + nseg) * 8 > nt.cap) CU(reserve_keep(nt, pool.cap / 12, (size_t)nnodes * 8, st));
         if ((size_t)(nnodes + nseg) > hit.cap) CU(hit.reserve((size_t)((nnodes + nseg) * 3 / 2 + 4096)));
         ckc_rbs_dev r = make(cur);
         CU(cudaMemsetAsync(d_cnt, 0, 8, st));
@@ -1124,15 +1309,45 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
     CU(cudaMemcpyAsync(ok, eok.p, ne, cudaMemcpyDeviceToHost, st));
     if (nchecks) CU(cudaMemcpyAsync(nchecks, nck.p, (size_t)ne * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (rec) {
+        /* every node of the bisection tree with its position t along the edge (dyadic, exact for the depths a valid edge reaches):
+         * sorted by t they are the matrix reconstructRBS builds -- a, the midpoints in order, b */
+        std::vector<double> hn((size_t)nnodes * 12), ht((size_t)nnodes);
+        CU(cudaMemcpy(hn.data(), pool.p, (size_t)nnodes * 96, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(ht.data(), nt.p, (size_t)nnodes * 8, cudaMemcpyDeviceToHost));
+        std::vector<int> order((size_t)nnodes);
+        for (int64_t i = 0; i < nnodes; i++) order[(size_t)i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ht[x] < ht[y]; });
+        *rec->n_confs = nnodes;
+        for (int64_t i = 0; i < std::min(nnodes, rec->cap); i++) memcpy(rec->confs + i * 12, hn.data() + (size_t)order[(size_t)i] * 12, 96);
+        if (nnodes > rec->cap) return fail(ctx, CKC_ERR_CAPACITY, "reconstructRBS: output capacity too small");
+    }
     return CKC_OK;
 }
 
 extern "C" int ckc_pcs_check_motion_rbs(ckc_ctx* ctx, int64_t n_edges, const double* qa, const double* qb, const int8_t* ac, const int8_t* ik,
                                         uint8_t* ok, int32_t* nchecks) {
+    MULTI(n_edges, ckc_pcs_check_motion_rbs(c, cnt, OFF(qa, 12), OFF(qb, 12), OFF(ac, 1), OFF(ik, 1), OFF(ok, 1), OFF(nchecks, 1)));
     return rbs_host(ctx, 0, n_edges, qa, qb, ac, ik, ok, nchecks);
 }
 extern "C" int ckc_gd_check_motion_rbs(ckc_ctx* ctx, int64_t n_edges, const double* qa, const double* qb, uint8_t* ok, int32_t* nchecks) {
+    MULTI(n_edges, ckc_gd_check_motion_rbs(c, cnt, OFF(qa, 12), OFF(qb, 12), OFF(ok, 1), OFF(nchecks, 1)));
     return rbs_host(ctx, 1, n_edges, qa, qb, nullptr, nullptr, ok, nchecks);
+}
+/* reconstructRBS: the same bisection with the node positions kept; one edge per call (post-processing of a solved path) */
+extern "C" int ckc_pcs_reconstruct_rbs(ckc_ctx* ctx, const double* qa, const double* qb, int active_chain, int ik_sol, double* confs, int64_t cap,
+                                       int64_t* n_confs, uint8_t* ok) {
+    if (!ctx || !confs || !n_confs || !ok || cap < 2) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    if (!ctx->children.empty()) return ckc_pcs_reconstruct_rbs(ctx->children[0], qa, qb, active_chain, ik_sol, confs, cap, n_confs, ok);
+    const int8_t ac = (int8_t)active_chain, ik = (int8_t)ik_sol;
+    rbs_recon rec = { confs, cap, n_confs };
+    return rbs_host(ctx, 0, 1, qa, qb, &ac, &ik, ok, nullptr, &rec);
+}
+extern "C" int ckc_gd_reconstruct_rbs(ckc_ctx* ctx, const double* qa, const double* qb, double* confs, int64_t cap, int64_t* n_confs, uint8_t* ok) {
+    if (!ctx || !confs || !n_confs || !ok || cap < 2) return fail(ctx, CKC_ERR_ARG, "bad argument");
+    if (!ctx->children.empty()) return ckc_gd_reconstruct_rbs(ctx->children[0], qa, qb, confs, cap, n_confs, ok);
+    rbs_recon rec = { confs, cap, n_confs };
+    return rbs_host(ctx, 1, 1, qa, qb, nullptr, nullptr, ok, nullptr, &rec);
 }
 
 
@@ -1140,6 +1355,7 @@ extern "C" int ckc_gd_check_motion_rbs(ckc_ctx* ctx, int64_t n_edges, const doub
 /* per-stage timing                                                                                                   */
 /* ---------------------------------------------------------------------------------------------------------------- */
 extern "C" int ckc_set_stage_timing(ckc_ctx* ctx, int enable) {
+    if (ctx && !ctx->children.empty()) return multi_dispatch(ctx, (int64_t)ctx->children.size(), [&](ckc_ctx* c, int64_t, int64_t) { return ckc_set_stage_timing(c, enable); });
     if (!ctx) return CKC_ERR_ARG;
     ctx->stage_timing = enable != 0;
     for (auto& p : ctx->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
@@ -1149,6 +1365,7 @@ extern "C" int ckc_set_stage_timing(ckc_ctx* ctx, int enable) {
 }
 
 extern "C" int ckc_get_stage_times(ckc_ctx* ctx, double ms[4], int64_t launches[4]) {
+    if (ctx && !ctx->children.empty()) return ckc_get_stage_times(ctx->children[0], ms, launches);
     if (!ctx || !ms || !launches) return CKC_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     for (auto& p : ctx->pending) {

@@ -80,6 +80,7 @@ struct ckc_counters_dev {       /* device-side accumulators, one struct per cont
 /* RBS frontier state (device pointers). Nodes = configurations (AoS, 12 doubles); a segment joins two nodes. */
 struct ckc_rbs_dev {
     double* nodes;                       /* node pool: [2*n_edges endpoints | midpoints ...] */
+    double* node_t;                      /* reconstructRBS only (else NULL): position of each node along its edge, 0 = a, 1 = b, midpoints (ta + tb) / 2 */
     int32_t *seg_a, *seg_b, *seg_edge, *seg_depth;          /* current level */
     int32_t *next_a, *next_b, *next_edge, *next_depth;      /* next level */
     int32_t *cand_node, *cand_seg;       /* midpoints that passed projection and await the collision check */
@@ -121,6 +122,10 @@ void ckc_launch_rx_check(const ckc_kin_dev& kin, int64_t n, const double* q, ckc
 void ckc_launch_fma_peak(int precision, int num_sms, int iters, float* sink, cudaStream_t st);
 void ckc_launch_compact_valid(int64_t n, int32_t index_base, const uint8_t* valid, const double* q, ckc_layout l, int32_t* idx_out, double* q_out,
                               int32_t* count, cudaStream_t st);
+/* single-arm kinematics exposed one to one: FKsolve_rob / IKsolve_rob (apc_class.cpp:51-76, :114-245), kdl::FK (kdl_class.cpp:251-278) */
+void ckc_launch_fk(const ckc_kin_dev& kin, int64_t n, const double* q6, const int8_t* robot, double* T16, cudaStream_t st);
+void ckc_launch_ik(const ckc_kin_dev& kin, int64_t n, const double* T16, const int8_t* robot, const int8_t* sol, double* q6, uint8_t* ok, cudaStream_t st);
+void ckc_launch_kdl_fk(const ckc_kin_dev& kin, int64_t n, const double* q12, double* T16, cudaStream_t st);
 void ckc_launch_transpose(const double* src, ckc_layout ls, double* dst, ckc_layout ld, int64_t n, cudaStream_t st);
 
 #endif

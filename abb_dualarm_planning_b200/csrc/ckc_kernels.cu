@@ -19,10 +19,13 @@
  */
 #include "ckc_device.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 using namespace ckc;
 
-#define CKC_STACK_CAP 640           /* per-warp shared-memory task stack (entries) */
+#ifndef CKC_STACK_CAP
+#define CKC_STACK_CAP 512           /* per-warp shared-memory task stack (entries); 8 warps x (2016 + 1008 + 2048 + 256) B + 3712 B = 46.3 kB per block: two blocks stay inside the 100 kB shared-memory carve-out (the L1 keeps 156 kB for the hierarchy nodes) */
+#endif
 #define CKC_BIG_STACK_CAP 65536     /* per-warp global-memory stack of the overflow path */
 #define CKC_TRIQ_CAP 64
 #define CKC_COLLIDE_WARPS 8
@@ -126,6 +129,8 @@ struct collide_args {
     float deep_gap;              /* face-axis gap below which a box pair counts as interpenetrating (children pushed on top) */
     int count_rounds;            /* debug: the bv / tri counters count ROUNDS (warp steps) instead of tests */
     int wide_cnt;                /* rounds with at most this many tasks split BOTH boxes of a task (4 children) */
+    uint32_t* dbg_rounds;        /* debug (may be NULL): per sample box rounds | triangle steps << 16 */
+    int defer_rounds, defer_tri; /* a configuration still undecided after this many box rounds / triangle steps goes to k_collide_heavy */
 };
 
 __device__ __forceinline__ ckc_pair_dev smem_pair(const int4* sp, int p) {
@@ -161,55 +166,74 @@ __device__ __forceinline__ void load_leaf_pair(const ckc_world_dev& w, const dou
 #ifndef CKC_COLLIDE_MINBLOCKS
 #define CKC_COLLIDE_MINBLOCKS 2
 #endif
-/* dynamic shared memory of one block (8 warps): FP64 frames 8 x 2016 B, FP32 frames 8 x 1008 B, task stacks 8 x 2560 B,
- * triangle queues 8 x 256 B, pair table 3712 B = 50.3 kB (2 blocks per SM) */
-#define CKC_COLLIDE_SMEM(big) ((size_t)CKC_COLLIDE_WARPS * (CKC_NUM_FRAMES * 12 * (8 + 4) + ((big) ? 0 : CKC_STACK_CAP * 4) + CKC_TRIQ_CAP * 4) + CKC_MAX_PAIRS * 32)
-template <bool kBigStack>
+/* root pre-test of one pair-table entry: spheres around the two root boxes (centre = box centre, radius sum + tolerance + FP32 slack
+ * precomputed per entry); NaN poses stay in (the reference reports them in collision) */
+__device__ __forceinline__ bool root_spheres_close(const ckc_world_dev& w, const ckc_pair_dev pr, const float* F) {
+    const float4 ca = __ldg(reinterpret_cast<const float4*>(w.nodes + pr.node_a));      /* root box centre (mesh frame) */
+    const float4 cb = __ldg(reinterpret_cast<const float4*>(w.nodes + pr.node_b));
+    const float* Fa = F + 12 * pr.frame_a; const float* Fb = F + 12 * pr.frame_b;
+    float d2 = 0;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const float xa = Fa[3 * r] * ca.x + Fa[3 * r + 1] * ca.y + Fa[3 * r + 2] * ca.z + Fa[9 + r];
+        const float xb = Fb[3 * r] * cb.x + Fb[3 * r + 1] * cb.y + Fb[3 * r + 2] * cb.z + Fb[9 + r];
+        d2 += (xb - xa) * (xb - xa);
+    }
+    const float rs = __int_as_float(pr.pad0);
+    return !(d2 > rs * rs);
+}
+
+/* static shared memory of one block (8 warps): FP64 frames 8 x 2016 B, FP32 frames 8 x 1008 B, task stacks 8 x 2048 B, triangle
+ * queues 8 x 256 B, pair table 3712 B = 46.3 kB (static __shared__ arrays: the compiler keeps the shared address space -- with one
+ * carved-up extern buffer it fell back to generic loads / stores plus a window-base computation in every round).
+ * kPerPair = the diagnostic form (ckc_collide_pairs): per-pair flags, no early exit, task stack in global memory, no deferral. */
+template <bool kPerPair>
 __global__ void __launch_bounds__(CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_MINBLOCKS)
 k_collide(const ckc_world_dev w, const collide_args a) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ double s_f64[CKC_COLLIDE_WARPS][CKC_NUM_FRAMES * 12];
+    __shared__ float s_f32[CKC_COLLIDE_WARPS][CKC_NUM_FRAMES * 12];
+    __shared__ uint32_t s_stack[kPerPair ? 1 : CKC_COLLIDE_WARPS][kPerPair ? 1 : CKC_STACK_CAP];
+    __shared__ uint32_t s_triq[CKC_COLLIDE_WARPS][CKC_TRIQ_CAP];
+    __shared__ int4 s_pairs[CKC_MAX_PAIRS * 2];       /* the pair table, once per block (32 bytes per entry) */
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    int4* s_pairs = reinterpret_cast<int4*>(s_raw);                                   /* the pair table, once per block (32 bytes per entry) */
-    double* F64 = reinterpret_cast<double*>(s_raw + CKC_MAX_PAIRS * 32) + wib * (CKC_NUM_FRAMES * 12);
-    float* F = reinterpret_cast<float*>(s_raw + CKC_MAX_PAIRS * 32 + CKC_COLLIDE_WARPS * CKC_NUM_FRAMES * 12 * 8) + wib * (CKC_NUM_FRAMES * 12);
-    uint32_t* triq = reinterpret_cast<uint32_t*>(s_raw + CKC_MAX_PAIRS * 32 + CKC_COLLIDE_WARPS * CKC_NUM_FRAMES * 12 * 12) + wib * CKC_TRIQ_CAP;
-    uint32_t* s_stack = reinterpret_cast<uint32_t*>(s_raw + CKC_MAX_PAIRS * 32 + CKC_COLLIDE_WARPS * (CKC_NUM_FRAMES * 12 * 12 + CKC_TRIQ_CAP * 4));
+    double* F64 = s_f64[wib];
+    float* F = s_f32[wib];
+    uint32_t* triq = s_triq[wib];
     for (int e = threadIdx.x; e < w.npairs * 2; e += blockDim.x) s_pairs[e] = __ldg(reinterpret_cast<const int4*>(w.pair_tab) + e);
     /* the three static obstacle poses never change: once per warp, in both precisions */
     for (int e = lane; e < 36; e += 32) { const double v = w.static_frames_dev[e]; F64[CKC_FRAME_DOUBLES + e] = v; F[CKC_FRAME_DOUBLES + e] = (float)v; }
     __syncthreads();
 
     const unsigned lt_mask = (1u << lane) - 1;
-    uint32_t* stack = kBigStack ? a.big_stack + (size_t)(blockIdx.x * CKC_COLLIDE_WARPS + wib) * CKC_BIG_STACK_CAP : s_stack + wib * CKC_STACK_CAP;
-    const int cap = kBigStack ? CKC_BIG_STACK_CAP : CKC_STACK_CAP;
+    uint32_t* stack = kPerPair ? a.big_stack + (size_t)(blockIdx.x * CKC_COLLIDE_WARPS + wib) * CKC_BIG_STACK_CAP : s_stack[kPerPair ? 0 : wib];
+    const int cap = kPerPair ? CKC_BIG_STACK_CAP : CKC_STACK_CAP;
 
-    int64_t m = kBigStack ? (int64_t)*a.ovf_count : (a.d_m ? (int64_t)*a.d_m : a.m_max);
+    int64_t m = a.d_m ? (int64_t)*a.d_m : a.m_max;
     if (m > a.m_max) m = a.m_max;
-    const bool per_pair = a.pair_flags != nullptr;
 
-    unsigned long long n_bv = 0, n_tri = 0, n_cfg = 0, n_hit = 0;
+    unsigned int n_bv = 0, n_tri = 0, n_cfg = 0, n_hit = 0;      /* per warp and launch: far below 2^32 */
 
     for (;;) {
         int k = 0;
         if (lane == 0) k = atomicAdd(a.work_counter, 1);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= m) break;
-        const int cfg = kBigStack ? a.ovf_list[k] : k;                 /* index into list[] */
+        const int cfg = k;                                             /* index into list[] */
         const int64_t sample = a.list ? (int64_t)a.list[cfg] : (int64_t)cfg;
 
-        /* this configuration's 18 link frames, FP64, by the warp itself (lane j < 12 fetches joint j), then the FP32 copy the
-         * box tests read */
+        /* this configuration's 18 link frames, FP64, by the warp itself (lane j < 12 fetches joint j), then the FP32 copy the box
+         * tests read.  Measured and rejected: an FP32 chain for the box tests with the FP64 frames computed only when a configuration
+         * reaches its first leaf pair -- colliding configurations then pay both chains (94 k feasible: 0.97 -> 1.08 ms) and the
+         * collision-free ones gain nothing (0.39 ms either way): the chain is latency, not issue slots. */
         const double qj = lane < 12 ? a.q[sample * a.lq.stride_i + lane * a.lq.stride_j] : 0.0;
         warp_link_frames(w.static_frames_dev + 36, qj, lane, F64);
         __syncwarp();
         for (int e = lane; e < CKC_FRAME_DOUBLES; e += 32) F[e] = (float)F64[e];
-        /* seed the stack with the root task of every table entry, first entry on top */
-        /* processing order = table entries by decreasing (decayed) first-hit frequency: a colliding configuration usually
-         * reaches its hit inside the first 32 root tasks and leaves through the ballot early-out */
-        /* root pre-test: a sphere around each root box (centre = box centre, radius = |half extents|); only the pairs whose
-         * spheres come within the tolerance get a root task.  Most of the 116 entries are far apart in most configurations,
-         * so this replaces ~2 of the ~4 root rounds (480 instructions per lane each) by ~35 instructions per lane and entry */
+        /* seed the stack with the root task of every table entry that passes the sphere pre-test, in decreasing order of each
+         * entry's (decayed) first-hit frequency, first entry on top: a colliding configuration usually reaches its hit inside the
+         * first round and leaves through the ballot early-out.  Most of the 116 entries are far apart in most configurations: the
+         * pre-test replaces ~3 of the ~4 root rounds (480 instructions per lane each) by ~35 instructions per lane and entry */
         __syncwarp();
         int top = 0;
         {
@@ -220,19 +244,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                 keep[it] = false; task[it] = 0;
                 if (k2 < w.npairs) {
                     const int p = __ldg(w.pair_order + k2);
-                    const ckc_pair_dev pr = smem_pair(s_pairs, p);
-                    const float4 ca = __ldg(reinterpret_cast<const float4*>(w.nodes + pr.node_a));      /* root box centre (mesh frame) */
-                    const float4 cb = __ldg(reinterpret_cast<const float4*>(w.nodes + pr.node_b));
-                    const float* Fa = F + 12 * pr.frame_a; const float* Fb = F + 12 * pr.frame_b;
-                    float d2 = 0;
-#pragma unroll
-                    for (int r = 0; r < 3; r++) {
-                        const float xa = Fa[3 * r] * ca.x + Fa[3 * r + 1] * ca.y + Fa[3 * r + 2] * ca.z + Fa[9 + r];
-                        const float xb = Fb[3 * r] * cb.x + Fb[3 * r + 1] * cb.y + Fb[3 * r + 2] * cb.z + Fb[9 + r];
-                        d2 += (xb - xa) * (xb - xa);
-                    }
-                    const float rs = __int_as_float(pr.pad0);
-                    keep[it] = !(d2 > rs * rs);                  /* NaN poses stay in (the reference reports them in collision) */
+                    keep[it] = root_spheres_close(w, smem_pair(s_pairs, p), F);
                     task[it] = (uint32_t)p << 22;
                 }
                 const unsigned mk = __ballot_sync(0xffffffffu, keep[it]);
@@ -244,12 +256,18 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                 if (keep[it]) stack[top - 1 - before[it]] = task[it];      /* first entry of the order on top */
         }
         int ntri = 0;
-        bool hit = false, overflow = false, hot = false, draining = false;      /* hot: a queued triangle pair looks like a hit -> test it now */
+        int rounds_box = 0, steps_tri = 0;
+        bool hit = false, defer = false, hot = false, draining = false;      /* hot: a queued triangle pair looks like a hit -> test it now */
         /* env 2: "path not from above" rule, collisionDetection.cpp:427-428 */
         if (w.env == 2 && (F64[7 * 12 + 11] > 800.0 || F64[15 * 12 + 11] > 800.0)) { hit = true; top = 0; }
         __syncwarp();
 
         while (!hit) {
+            /* a configuration that is still undecided after this much work (defaults: 64 box rounds or 24 triangle steps, ~0.1 % of
+             * the IK-feasible S-PCS configurations: hundreds of triangle pairs within a few mm of the tolerance) would keep one
+             * warp busy for 0.1 - 0.3 ms and set the duration of a small launch.  It goes to k_collide_heavy, where a block works on
+             * it with one thread per test (~25 us of one SM per configuration, whatever its weight: lower thresholds lose, measured). */
+            if (!kPerPair && (rounds_box > a.defer_rounds || steps_tri > a.defer_tri)) { defer = true; break; }
             if (ntri > 0 && (draining || ntri >= a.flush_n || top == 0 || hot)) {
                 hot = false; draining = ntri > 3;
                 /* ---- exact triangle tests: three pairs per step, nine lanes (one per edge pair) each ---- */
@@ -266,8 +284,9 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                 const double d = tri_dist_coop(act, lane, S0, S1, S2, T0, T1, T2);
                 const bool h = act && (lane - 9 * g) == 0 && d <= w.tol;      /* PQP: closer_than_tolerance iff d <= tolerance */
                 n_tri += a.count_rounds ? 1 : take;
+                steps_tri++;
                 ntri -= take;
-                if (per_pair) {
+                if (kPerPair) {
                     if (h) a.pair_flags[sample * CKC_MAX_PAIRS + (t >> 20)] = 1;
                 } else {
                     const unsigned hm = __ballot_sync(0xffffffffu, h);
@@ -291,7 +310,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                 const int p = t >> 22, na = (t >> 11) & 2047, nb = t & 2047;
                 const ckc_pair_dev pr = smem_pair(s_pairs, p);
                 bool skip = false;
-                if (per_pair) skip = a.pair_flags[sample * CKC_MAX_PAIRS + p] != 0;      /* pair already decided */
+                if (kPerPair) skip = a.pair_flags[sample * CKC_MAX_PAIRS + p] != 0;      /* pair already decided */
                 if (!skip) {
                     const box32 A = load_box(w.nodes + pr.node_a + na);
                     const box32 B = load_box(w.nodes + pr.node_b + nb);
@@ -321,9 +340,10 @@ k_collide(const ckc_world_dev w, const collide_args a) {
                 }
             }
             n_bv += a.count_rounds ? 1 : cnt;
+            rounds_box++;
             top -= cnt;
             __syncwarp();
-            if (!per_pair && __any_sync(0xffffffffu, likely)) hot = true;
+            if (!kPerPair && __any_sync(0xffffffffu, likely)) hot = true;
             const unsigned mt = __ballot_sync(0xffffffffu, leafpair);
             const unsigned me = __ballot_sync(0xffffffffu, expand);
             const unsigned m4 = __ballot_sync(0xffffffffu, expand4);
@@ -333,7 +353,7 @@ k_collide(const ckc_world_dev w, const collide_args a) {
              * configuration to its hit in fewer rounds (any order gives the same boolean) */
             const unsigned md = __ballot_sync(0xffffffffu, expand && deep);
             const int npush = 2 * __popc(me) + 4 * __popc(m4);
-            if (top + npush > cap) { overflow = true; break; }
+            if (top + npush > cap) { defer = true; break; }           /* stack overflow: the heavy kernel's stack lives in global memory */
             const unsigned mshallow = me & ~md;
             int pos = top + 4 * __popc(m4 & lt_mask);
             if (expand) pos = top + 4 * __popc(m4) + (deep ? 2 * __popc(mshallow) + 2 * __popc(md & lt_mask) : 2 * __popc(mshallow & lt_mask));
@@ -343,23 +363,23 @@ k_collide(const ckc_world_dev w, const collide_args a) {
             __syncwarp();
         }
 
-        if (overflow) {
-            if (!kBigStack) {
+        if (defer) {
+            if (!kPerPair) {
                 if (lane == 0) { const int o = atomicAdd(a.ovf_count, 1); a.ovf_list[o] = cfg; }
-                if (per_pair) for (int p = lane; p < CKC_MAX_PAIRS; p += 32) a.pair_flags[sample * CKC_MAX_PAIRS + p] = 0;
                 __syncwarp();
-                continue;                                             /* redone by the big-stack launch */
+                continue;                                             /* decided by k_collide_heavy */
             }
-            hit = true;                                               /* capacity exhausted even there: report conservatively */
+            hit = true;                                               /* diagnostic form, 65 536-entry stack exhausted: report conservatively */
             if (lane == 0 && a.ctr) atomicAdd(&a.ctr->queue_overflows, 1ull << 32);
         }
-        if (per_pair) {
+        if (kPerPair) {
             __syncwarp();
             unsigned any = 0;
             for (int p = lane; p < CKC_MAX_PAIRS; p += 32) any |= a.pair_flags[sample * CKC_MAX_PAIRS + p];
             hit = __any_sync(0xffffffffu, any != 0) || hit;
         }
         if (lane == 0) {
+            if (a.dbg_rounds) a.dbg_rounds[sample] = (unsigned)rounds_box | ((unsigned)steps_tri << 16);
             if (a.hit_out) a.hit_out[sample] = hit ? 1 : 0;
             if (a.valid_out) a.valid_out[sample] = hit ? 0 : 1;
         }
@@ -367,12 +387,139 @@ k_collide(const ckc_world_dev w, const collide_args a) {
         __syncwarp();
     }
     if (lane == 0 && a.ctr) {
-        atomicAdd(&a.ctr->bv_tests, n_bv);
-        atomicAdd(&a.ctr->tri_tests, n_tri);
-        atomicAdd(&a.ctr->collision_calls, n_cfg);
-        atomicAdd(&a.ctr->collisions, n_hit);
-        if (kBigStack) atomicAdd(&a.ctr->queue_overflows, n_cfg);
+        atomicAdd(&a.ctr->bv_tests, (unsigned long long)n_bv);
+        atomicAdd(&a.ctr->tri_tests, (unsigned long long)n_tri);
+        atomicAdd(&a.ctr->collision_calls, (unsigned long long)n_cfg);
+        atomicAdd(&a.ctr->collisions, (unsigned long long)n_hit);
     }
+}
+
+/* ---- K3h: the heavy configurations, one BLOCK per configuration ---------------------------------------------------
+ * The configurations k_collide gave up on (work above its thresholds, or a task-stack overflow) are started again from the pair
+ * table by a whole block: every round pops up to 256 tasks -- one box test per THREAD --, leaf pairs collect in a 1024-entry
+ * queue that is drained with one exact FP64 TriDist per thread (tri_dist_seq: same arithmetic as the cooperative routine, 256 pairs
+ * per step instead of 3), the task stack lives in global memory (65 536 entries per block).  A configuration with 450 near-tolerance
+ * triangle pairs and 50 descent rounds costs one warp ~0.3 ms; here it is two triangle steps and ~25 rounds.  Same boolean:
+ * the pruning test and the leaf test are the same functions, only the order of evaluation differs. */
+#define CKC_HEAVY_THREADS 256
+#define CKC_HEAVY_MAX_BLOCKS 160     /* size of the global stack buffer (ckc_host.cu reserves CKC_HEAVY_MAX_BLOCKS x 65 536 entries) */
+#define CKC_HEAVY_TRIQ 1024
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp_tot, int& total) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp_tot[wib] = inc;
+    __syncthreads();
+    int base = 0; total = 0;
+#pragma unroll
+    for (int i = 0; i < CKC_HEAVY_THREADS / 32; i++) { const int t = s_warp_tot[i]; if (i < wib) base += t; total += t; }
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(CKC_HEAVY_THREADS, 1)
+k_collide_heavy(const ckc_world_dev w, const collide_args a) {
+    __shared__ double F64[CKC_NUM_FRAMES * 12];
+    __shared__ float F[CKC_NUM_FRAMES * 12];
+    __shared__ uint32_t triq[CKC_HEAVY_TRIQ];
+    __shared__ int4 s_pairs[CKC_MAX_PAIRS * 2];
+    __shared__ int s_tot[CKC_HEAVY_THREADS / 32];
+    __shared__ int s_k, s_hit;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int e = tid; e < w.npairs * 2; e += blockDim.x) s_pairs[e] = __ldg(reinterpret_cast<const int4*>(w.pair_tab) + e);
+    for (int e = tid; e < 36; e += blockDim.x) { const double v = w.static_frames_dev[e]; F64[CKC_FRAME_DOUBLES + e] = v; F[CKC_FRAME_DOUBLES + e] = (float)v; }
+    uint32_t* stack = a.big_stack + (size_t)blockIdx.x * CKC_BIG_STACK_CAP;
+    const int m = *a.ovf_count;
+    unsigned int n_bv = 0, n_tri = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_k = atomicAdd(a.work_counter, 1); s_hit = 0; }
+        __syncthreads();
+        const int k = s_k;
+        if (k >= m) break;
+        const int cfg = a.ovf_list[k];
+        const int64_t sample = a.list ? (int64_t)a.list[cfg] : (int64_t)cfg;
+        if (tid < 32) {                 /* warp 0: exact frames, then the FP32 copy (rounded from FP64: inside the guard band like the FP32 chain) */
+            warp_link_frames(w.static_frames_dev + 36, lane < 12 ? a.q[sample * a.lq.stride_i + lane * a.lq.stride_j] : 0.0, lane, F64);
+            __syncwarp();
+            for (int e = lane; e < CKC_FRAME_DOUBLES; e += 32) F[e] = (float)F64[e];
+        }
+        __syncthreads();
+        int top, ntri = 0;
+        {   /* root tasks of the entries that pass the sphere pre-test */
+            bool keep = false; int p = 0;
+            if (tid < w.npairs) { p = tid; keep = root_spheres_close(w, smem_pair(s_pairs, p), F); }
+            const int pos = block_exclusive_scan(keep ? 1 : 0, s_tot, top);
+            if (keep) stack[pos] = (uint32_t)p << 22;
+        }
+        bool hit = w.env == 2 && (F64[7 * 12 + 11] > 800.0 || F64[15 * 12 + 11] > 800.0);
+        bool overflow = false;
+        __syncthreads();
+        while (!hit) {
+            if (ntri > 0 && (top == 0 || ntri > CKC_HEAVY_TRIQ - CKC_HEAVY_THREADS)) {
+                /* ---- exact triangle tests, one pair per thread ---- */
+                const int take = ntri < CKC_HEAVY_THREADS ? ntri : CKC_HEAVY_THREADS;
+                bool h = false;
+                if (tid < take) {
+                    const uint32_t t = triq[ntri - 1 - tid];
+                    v3 S0, S1, S2, T0, T1, T2;
+                    load_leaf_pair(w, F64, smem_pair(s_pairs, t >> 20), (t >> 10) & 1023, t & 1023, S0, S1, S2, T0, T1, T2);
+                    h = tri_dist_seq(S0, S1, S2, T0, T1, T2) <= w.tol;
+                    if (h) { s_hit = 1; atomicAdd(w.pair_hits + (t >> 20), 1u); }
+                }
+                n_tri += tid == 0 ? take : 0;
+                ntri -= take;
+                __syncthreads();
+                hit = s_hit != 0;
+                continue;
+            }
+            if (top == 0) break;
+            /* ---- box tests, one task per thread ---- */
+            const int cnt = top < CKC_HEAVY_THREADS ? top : CKC_HEAVY_THREADS;
+            int nchild = 0; bool leafpair = false;
+            uint32_t c0 = 0, c1 = 0, tt = 0; bool four = false;
+            if (tid < cnt) {
+                const uint32_t t = stack[top - 1 - tid];
+                const int p = t >> 22, na = (t >> 11) & 2047, nb = t & 2047;
+                const ckc_pair_dev pr = smem_pair(s_pairs, p);
+                const box32 A = load_box(w.nodes + pr.node_a + na);
+                const box32 B = load_box(w.nodes + pr.node_b + nb);
+                float gap6;
+                if (!boxes_farther_than(A, F + 12 * pr.frame_a, B, F + 12 * pr.frame_b, w.cull_tol, gap6)) {
+                    if (A.child < 0 && B.child < 0) { leafpair = true; tt = ((uint32_t)p << 20) | ((uint32_t)(~A.child) << 10) | (uint32_t)(~B.child); }
+                    else if (A.child >= 0 && B.child >= 0) {          /* both boxes split at once: half the descent rounds */
+                        four = true; nchild = 4;
+                        c0 = ((uint32_t)p << 22) | ((uint32_t)A.child << 11) | (uint32_t)B.child;
+                    } else {
+                        nchild = 2;
+                        if (B.child < 0) { c0 = ((uint32_t)p << 22) | ((uint32_t)A.child << 11) | (uint32_t)nb; c1 = c0 + (1u << 11); }
+                        else { c0 = ((uint32_t)p << 22) | ((uint32_t)na << 11) | (uint32_t)B.child; c1 = c0 + 1u; }
+                    }
+                }
+            }
+            n_bv += tid == 0 ? cnt : 0;
+            __syncthreads();                                       /* every task of this round has been read */
+            top -= cnt;
+            int npush, nleaf;
+            const int cpos = block_exclusive_scan(nchild, s_tot, npush);
+            const int lpos = block_exclusive_scan(leafpair ? 1 : 0, s_tot, nleaf);
+            if (top + npush > CKC_BIG_STACK_CAP) { overflow = true; break; }
+            if (nchild == 2) { stack[top + cpos] = c1; stack[top + cpos + 1] = c0; }
+            if (four) { stack[top + cpos] = c0 + (1u << 11) + 1u; stack[top + cpos + 1] = c0 + (1u << 11); stack[top + cpos + 2] = c0 + 1u; stack[top + cpos + 3] = c0; }
+            if (leafpair) triq[ntri + lpos] = tt;
+            top += npush; ntri += nleaf;
+            __syncthreads();
+        }
+        if (overflow) { hit = true; if (tid == 0 && a.ctr) atomicAdd(&a.ctr->queue_overflows, 1ull << 32); }      /* 65 536 tasks: report conservatively */
+        if (tid == 0) {
+            if (a.dbg_rounds) a.dbg_rounds[sample] = 0xffffffffu;
+            if (a.hit_out) a.hit_out[sample] = hit ? 1 : 0;
+            if (a.valid_out) a.valid_out[sample] = hit ? 0 : 1;
+            if (a.ctr) { atomicAdd(&a.ctr->collision_calls, 1ull); if (hit) atomicAdd(&a.ctr->collisions, 1ull); atomicAdd(&a.ctr->queue_overflows, 1ull); }
+        }
+    }
+    if (tid == 0 && a.ctr) { atomicAdd(&a.ctr->bv_tests, (unsigned long long)n_bv); atomicAdd(&a.ctr->tri_tests, (unsigned long long)n_tri); }
 }
 
 /* rank sort of the (decayed) first-hit counters -> processing order for the next launches; one tiny block */
@@ -392,6 +539,7 @@ void ckc_launch_update_pair_order(const ckc_world_dev& w, int* order_out, cudaSt
     k_update_pair_order<<<1, 128, 0, st>>>(w.pair_hits, order_out, w.npairs);
 }
 
+uint32_t* g_ckc_dbg_rounds = nullptr;      /* debug hook (ckc_debug_collide_rounds): device array indexed by sample */
 void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const double* q, ckc_layout lq, const int32_t* list, const int32_t* d_m,
                         int64_t m_max, uint8_t* hit_out, uint8_t* valid_out, uint8_t* pair_flags, int32_t* work_counter,
                         int32_t* ovf_list, int32_t* ovf_count, uint32_t* big_stack, ckc_counters_dev* ctr, cudaStream_t st) {
@@ -399,6 +547,7 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     collide_args a;
     a.q = q; a.lq = lq; a.list = list; a.d_m = d_m; a.m_max = m_max; a.hit_out = hit_out; a.valid_out = valid_out; a.pair_flags = pair_flags;
     a.work_counter = work_counter; a.ovf_list = ovf_list; a.ovf_count = ovf_count; a.big_stack = big_stack; a.ctr = ctr;
+    a.dbg_rounds = g_ckc_dbg_rounds;
     /* tuning / debug knobs, read once (function-local statics: initialisation is thread safe, contexts may live on several threads) */
     static const int wide_cnt = [] { const char* e = getenv("CKC_WIDE_CNT"); return e ? atoi(e) : 8; }();
     static const int count_rounds = [] { const char* e = getenv("CKC_COUNT_ROUNDS"); return e ? atoi(e) : 0; }();
@@ -412,22 +561,27 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     static const float likely_gap = [] { const char* e = getenv("CKC_LIKELY_GAP"); return e ? (float)atof(e) : 2.0125f; }();
     a.flush_n = flush_n < 1 ? 1 : (flush_n > CKC_TRIQ_CAP - 32 ? CKC_TRIQ_CAP - 32 : flush_n);      /* a round queues up to 32 leaf pairs on top of flush_n - 1 */
     a.likely_gap = likely_gap;
-    static const bool smem_ok = [] {
-        return cudaFuncSetAttribute(k_collide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CKC_COLLIDE_SMEM(false)) == cudaSuccess &&
-               cudaFuncSetAttribute(k_collide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CKC_COLLIDE_SMEM(true)) == cudaSuccess;
-    }();
-    (void)smem_ok;
-    /* work_counter[0] main pass, [1] overflow pass; the overflow count sits right behind them in the lanes' scratch block */
+
+    static const int defer_rounds = [] { const char* e = getenv("CKC_DEFER_ROUNDS"); return e ? atoi(e) : 64; }();
+    static const int defer_tri = [] { const char* e = getenv("CKC_DEFER_TRI"); return e ? atoi(e) : 24; }();
+    a.defer_rounds = defer_rounds; a.defer_tri = defer_tri;
+    /* work_counter[0] main pass, [1] heavy pass; the heavy count sits right behind them in the lanes' scratch block */
     if (ovf_count == work_counter + 2) cudaMemsetAsync(work_counter, 0, 3 * sizeof(int32_t), st);
     else { cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st); cudaMemsetAsync(ovf_count, 0, sizeof(int32_t), st); }
+    if (pair_flags) {           /* diagnostic form: global-memory stacks, 16 blocks (the big-stack buffer holds 128 warps) */
+        k_collide<true><<<16, CKC_COLLIDE_WARPS * 32, 0, st>>>(w, a);
+        return;
+    }
     int64_t blocks = (m_max + CKC_COLLIDE_WARPS - 1) / CKC_COLLIDE_WARPS;
     const int64_t resident = (int64_t)cfg.num_sms * CKC_COLLIDE_MINBLOCKS * 3;
     if (blocks > resident) blocks = resident;
-    k_collide<false><<<(unsigned)blocks, CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_SMEM(false), st>>>(w, a);
-    /* overflow pass: tiny grid, global-memory stacks; exits immediately when nothing overflowed */
+    k_collide<false><<<(unsigned)blocks, CKC_COLLIDE_WARPS * 32, 0, st>>>(w, a);
+    /* heavy pass: one block per SM at most (its global-memory stacks: 65 536 entries per block), exits at once when nothing was deferred */
     collide_args b = a;
     b.work_counter = work_counter + 1;
-    k_collide<true><<<16, CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_SMEM(true), st>>>(w, b);
+    int64_t hb = std::min<int64_t>(cfg.num_sms, m_max);      /* the number of deferred configurations is only known on the device */
+    if (hb > CKC_HEAVY_MAX_BLOCKS) hb = CKC_HEAVY_MAX_BLOCKS;
+    k_collide_heavy<<<(unsigned)hb, CKC_HEAVY_THREADS, 0, st>>>(w, b);
 }
 
 /* ================================================================================================================ */
@@ -590,6 +744,59 @@ void ckc_launch_compact_valid(int64_t n, int32_t index_base, const uint8_t* vali
     k_compact_valid<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, index_base, valid, q, l, idx_out, q_out, count);
 }
 
+/* FKsolve_rob / IKsolve_rob / kdl::FK as batch kernels (one thread per sample); robot numbers are the reference's 1 and 2 */
+__global__ void __launch_bounds__(128)
+k_fk(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q6, const int8_t* __restrict__ robot, double* __restrict__ T16) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double q[6], R[9], p[3];
+#pragma unroll
+    for (int j = 0; j < 6; j++) q[j] = q6[6 * i + j];
+    fk_arm(kin, q, robot[i] == 2 ? 1 : 0, R, p);
+    double* T = T16 + 16 * i;
+#pragma unroll
+    for (int r = 0; r < 3; r++) { T[4 * r] = R[3 * r]; T[4 * r + 1] = R[3 * r + 1]; T[4 * r + 2] = R[3 * r + 2]; T[4 * r + 3] = p[r]; }
+    T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+}
+__global__ void __launch_bounds__(128)
+k_ik(const ckc_kin_dev kin, int64_t n, const double* __restrict__ T16, const int8_t* __restrict__ robot, const int8_t* __restrict__ sol,
+     double* __restrict__ q6, uint8_t* __restrict__ ok) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* T = T16 + 16 * i;
+    double Rt[9], pt[3], q[6] = { 0, 0, 0, 0, 0, 0 };
+#pragma unroll
+    for (int r = 0; r < 3; r++) { Rt[3 * r] = T[4 * r]; Rt[3 * r + 1] = T[4 * r + 1]; Rt[3 * r + 2] = T[4 * r + 2]; pt[r] = T[4 * r + 3]; }
+    const bool v = ik_arm(kin, Rt, pt, robot[i] == 2 ? 1 : 0, sol[i] & 7, q);
+    ok[i] = v ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) q6[6 * i + j] = q[j];          /* meaningful when ok[i] == 1 */
+}
+__global__ void __launch_bounds__(128)
+k_kdl_fk(const ckc_kin_dev kin, int64_t n, const double* __restrict__ q12, double* __restrict__ T16) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double qc[12], R[9], p[3];
+    const double* q = q12 + 12 * i;
+#pragma unroll
+    for (int j = 0; j < 6; j++) { qc[j] = q[j]; qc[6 + j] = q[11 - j]; }      /* kdl_class.cpp:254-259 */
+    qc[11] = -qc[11];
+    chain_fk<false>(kin, qc, R, p, nullptr);
+    double* T = T16 + 16 * i;
+#pragma unroll
+    for (int r = 0; r < 3; r++) { T[4 * r] = R[3 * r]; T[4 * r + 1] = R[3 * r + 1]; T[4 * r + 2] = R[3 * r + 2]; T[4 * r + 3] = p[r]; }
+    T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+}
+void ckc_launch_fk(const ckc_kin_dev& kin, int64_t n, const double* q6, const int8_t* robot, double* T16, cudaStream_t st) {
+    if (n > 0) k_fk<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kin, n, q6, robot, T16);
+}
+void ckc_launch_ik(const ckc_kin_dev& kin, int64_t n, const double* T16, const int8_t* robot, const int8_t* sol, double* q6, uint8_t* ok, cudaStream_t st) {
+    if (n > 0) k_ik<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kin, n, T16, robot, sol, q6, ok);
+}
+void ckc_launch_kdl_fk(const ckc_kin_dev& kin, int64_t n, const double* q12, double* T16, cudaStream_t st) {
+    if (n > 0) k_kdl_fk<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kin, n, q12, T16);
+}
+
 __global__ void k_transpose(const double* __restrict__ src, ckc_layout ls, double* __restrict__ dst, ckc_layout ld, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -615,7 +822,7 @@ void ckc_launch_transpose(const double* src, ckc_layout ls, double* dst, ckc_lay
 #define CKC_GD_MINBLOCKS_U 4        /* the unrolled walks keep more values live: 128 registers */
 #endif
 #ifndef CKC_GD_DEFAULT_VARIANT
-#define CKC_GD_DEFAULT_VARIANT 0
+#define CKC_GD_DEFAULT_VARIANT 2
 #endif
 /* kVariant: 0 = rolled joint loops (gd_iterate), 1 = unrolled chain (gd_iterate_u), 2 = unrolled + collinear joints 5 / 6 merged */
 template <bool seeded, int kVariant>
@@ -814,6 +1021,7 @@ k_rbs_expand(const ckc_kin_dev kin, const ckc_rbs_dev r, int nseg, int node_base
         if (cand) {
             const int c = base + __popc(mk & ((1u << lane) - 1));
             my_node = node_base + c;
+            if (r.node_t) r.node_t[my_node] = (r.node_t[r.seg_a[s]] + r.node_t[r.seg_b[s]]) / 2;
             double* dst = r.nodes + 12 * (int64_t)my_node;
 #pragma unroll
             for (int j = 0; j < 12; j++) dst[j] = m[j];
@@ -873,6 +1081,7 @@ __global__ void k_rbs_init(const ckc_rbs_dev r, int n_edges) {
     r.seg_a[e] = 2 * e; r.seg_b[e] = 2 * e + 1; r.seg_edge[e] = e; r.seg_depth[e] = 0;
     r.edge_ok[e] = 1;
     if (r.nchecks) r.nchecks[e] = 0;
+    if (r.node_t) { r.node_t[2 * e] = 0.0; r.node_t[2 * e + 1] = 1.0; }
 }
 
 void ckc_launch_rbs_init(const ckc_rbs_dev& r, int n_edges, cudaStream_t st) {

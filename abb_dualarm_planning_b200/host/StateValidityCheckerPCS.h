@@ -15,12 +15,39 @@ public:
     StateValidityChecker(const ob::SpaceInformationPtr& si, int env = 1) : mysi_(si.get()), ckc_(env) { init(env); }
     StateValidityChecker(int env = 1) : mysi_(nullptr), ckc_(env) { init(env); }
 
-    /* ---- two_robots (proj_classes/apc_class.h) ---- */
+    /* ---- two_robots (proj_classes/apc_class.h:47-119), every public member ---- */
+    void FKsolve_rob(State q, int robot_num);                                    /* apc_class.cpp:51-76 */
+    Matrix get_FK_solution_T1() { return T_fk_solution_1; }
+    State get_FK_solution_p1() { return p_fk_solution_1; }
+    Matrix get_FK_solution_T2() { return T_fk_solution_2; }
+    State get_FK_solution_p2() { return p_fk_solution_2; }
+    bool IKsolve_rob(Matrix T, int robot_num, int solution_num);                 /* apc_class.cpp:114-245 */
     bool calc_specific_IK_solution_R1(Matrix T, State q1, int IKsol);            /* apc_class.cpp:356-371 */
     bool calc_specific_IK_solution_R2(Matrix T, State q2, int IKsol);            /* apc_class.cpp:373-389 */
     State get_IK_solution_q1() { return q_IK_solution_1; }
     State get_IK_solution_q2() { return q_IK_solution_2; }
+    bool IsRobotsFeasible_R1(Matrix T, State q1);                                /* apc_class.cpp:392-407 */
+    bool IsRobotsFeasible_R2(Matrix T, State q2);                                /* apc_class.cpp:409-424 */
+    int calc_all_IK_solutions_1(Matrix T);                                       /* apc_class.cpp:249-262: the 8 branches in one batch */
+    int calc_all_IK_solutions_2(Matrix T);                                       /* apc_class.cpp:264-277 */
+    State get_all_IK_solutions_1(int i) { return Q_IK_solutions_1[i]; }
+    State get_all_IK_solutions_2(int i) { return Q_IK_solutions_2[i]; }
+    int get_valid_IK_solutions_indices_1(int i) { return (int)valid_IK_solutions_indices_1[i]; }
+    int get_valid_IK_solutions_indices_2(int i) { return (int)valid_IK_solutions_indices_2[i]; }
+    int get_IK_number() { return IK_number; }
+    Matrix get_T2() { return T2_; }
     bool check_angle_limits(State q);                                            /* apc_class.cpp:304-334 */
+    void initVector(State& V, int n) { V.resize(n); }
+    void initMatrix(Matrix& M, int n, int m) { M.resize(n); for (int i = 0; i < n; ++i) M[i].resize(m); }
+    double deg2rad(double deg) { return deg * PI_ / 180.0; }
+    void printMatrix(Matrix M);
+    void printVector(State p);
+    Matrix MatricesMult(Matrix M1, Matrix M2);                                   /* apc_class.cpp:427-436 */
+    bool InvertMatrix(Matrix M, Matrix& Minv);                                   /* apc_class.cpp:439-575 (4x4 cofactor inverse) */
+    void clearMatrix(Matrix& M) { for (auto& r : M) for (double& v : r) v = 0; }
+    State rand_q_ambient();                                                      /* apc_class.cpp:643-661 */
+    State get_robots_properties() { return { 166, 124, 270, 70, 149.6, 152.4, 72 - 13. / 2, 60 + 13. / 2 }; }   /* apc_class.cpp:5-12 */
+    bool include_joint_limits = true;
     int get_IK_counter() { return IK_counter; }
     double get_IK_time() { return IK_time; }
     int IK_counter; double IK_time;
@@ -42,7 +69,9 @@ public:
     bool reconstructRBS(State, State, State, State, int, int, Matrix&, int, int, int);   /* PCS.cpp:545-577 */
     double normDistanceDuo(State, State, State, State);
     void midpoint(State, State, State, State, State&, State&);
+    void retrieveStateVector(const ob::State*, State&);                          /* 12-vector form (HB.h:83) */
     void retrieveStateVector(const ob::State*, State&, State&);
+    void updateStateVector(const ob::State*, State);                             /* 12-vector form (HB.h:87) */
     void updateStateVector(const ob::State*, State, State);
     void printStateVector(const ob::State*);
     void defaultSettings() {}
@@ -50,13 +79,21 @@ public:
     double stateDistance(const ob::State*, const ob::State*);
     State sample_q();                                                            /* PCS.cpp:234-259 */
     bool sample_q(ob::State* st);                                                /* PCS.cpp:196-231 */
+    bool close_chain(const ob::State*, int);                                     /* PCS.cpp:59-92 */
     bool IKproject(State&, State&, int, int);                                    /* PCS.cpp:140-162 */
+    bool IKproject(State&, State&, int);                                         /* PCS.cpp:165-193: first of the 8 branches (random order) that projects and is identified */
     bool IKproject(State&, State&, State&, int&, State);                         /* PCS.cpp:94-138 */
     State identify_state_ik(const ob::State*, State = {-1, -1});                 /* PCS.cpp:261-273 */
     State identify_state_ik(State, State, State = {-1, -1});                     /* PCS.cpp:275-316 */
     State join_Vectors(State, State);
     void seperate_Vector(State, State&, State&);
-    void log_q(State, State);
+    void log_q(ob::State*);                                                      /* PCS.cpp:602-608 */
+    void log_q(State, State);                                                    /* PCS.cpp:610-626 */
+    int get_valid_solution_index() { return valid_solution_index; }
+    double iden = 0;
+    double get_iden() { return iden; }                                           /* PCS.h:166-167: time spent in identify_state_ik */
+    void setQ();                                                                 /* PCS.h:136-147 */
+    void setP();                                                                 /* PCS.h:150-158 */
     Matrix getPMatrix() { return P; }
     Matrix getQ() { return Q; }
     double get_RBS_tol() { return RBS_tol; }
@@ -74,17 +111,31 @@ public:
      *      projection, local connection by the APC bisection ---- */
     bool GD(State q);                                                            /* kdl_class.cpp:68-140 */
     State get_GD_result() { return q_solution; }
-    bool IKproject(const ob::State*);                                            /* HB.cpp:109-122 */
-    bool IKproject(State&);                                                      /* GD projection of all 12 joints + collision */
-    State sample_q_gd();                                                         /* HB.cpp sample_q: GD from uniform seeds */
+    void FK(State q);                                                            /* kdl_class.cpp:251-278 */
+    Matrix get_FK_solution() { return T_fk; }
+    Matrix T_fk;
+    bool IKproject(const ob::State*, bool = true);                               /* HB.cpp:95-106 */
+    bool IKproject(State&, bool = true);                                         /* HB.cpp:109-122: GD projection of all 12 joints (+ collision) */
+    State sample_q_gd();                                                         /* HB.cpp:73-93 sample_q: GD from uniform seeds */
+    bool checkMotion(const ob::State*, const ob::State*);                        /* HB.cpp:233-271: serial grid, each point through isValid (GD) */
+    bool isValidSew(State&);                                                     /* HB.cpp:405-421 */
+    bool checkMotionSew(const ob::State*, const ob::State*);                     /* HB.cpp:423-441 */
+    bool reconstructSew(const ob::State*, const ob::State*, Matrix&);            /* HB.cpp:446-453 */
+    bool reconstructSew(State, State, Matrix&);                                  /* HB.cpp:455-480 */
+    double maxDistance(State, State);
+    double MaxAngleDistance(State, State);
+    void Join_States(State&, State, State);
+    int get_n() { return 12; }
 #endif
 #ifdef CKC_FLAVOUR_RSS
     /* ---- random singular sampling checker (validity_checkers/StateValidityCheckerRSS.{h,cpp}) ---- */
     bool sampleSingular(ob::State*);                                             /* RSS.cpp:255-306 */
     bool checkMotionRBS(const ob::State*, const ob::State*, int sg, int active_chain, int ik_sol);          /* RSS.cpp:566-583 */
     bool checkMotionRBS(State, State, State, State, State, State, int, int, int, int);                      /* RSS.cpp:586-613 */
-    int get_countSolutions() { return countSolutions; }
+    bool reconstructRBS(const ob::State*, const ob::State*, Matrix&, int sg, int active_chain, int ik_sol); /* RSS.cpp:684-700 */
+    bool reconstructRBS(State, State, State, State, State, State, int, int, Matrix&, int, int, int);        /* RSS.cpp:702-741 */
 #endif
+    int get_countSolutions() { return countSolutions; }                          /* apc_class.h:62 */
 
     /* ---- batch forms (new): what a planner calls to submit whole batches ---- */
     /** n configurations (q[i] = 12 joints), per-sample active chain / IK branch; returns valid flags, projects q in place */
@@ -99,6 +150,11 @@ private:
     ob::SpaceInformation* mysi_;
     CkcContext ckc_;
     State q_IK_solution_1, q_IK_solution_2, q_solution;
+    Matrix T_fk_solution_1, T_fk_solution_2, Q_IK_solutions_1, Q_IK_solutions_2, T2_;
+    State p_fk_solution_1, p_fk_solution_2, valid_IK_solutions_indices_1, valid_IK_solutions_indices_2;
+    int IK_number = 0, valid_solution_index = 0;
+    int calc_all(const Matrix& T, int robot, Matrix& sols, State& idx);
+    void ckc_check(int rc);                                                      /* a failed device call ends the process like the reference's exit(-1) */
     int countSolutions = 0;
     double L;
     Matrix Q, P;

@@ -17,8 +17,8 @@
  *   - `_dev` entry points take DEVICE pointers (structure of arrays: q[j*n + i]) and a cudaStream_t (as void*);
  *     they only enqueue work -- the caller synchronises.
  *   - return value: 0 = CKC_OK, negative = error (never throws, never exits).  Output flags are 0/1 bytes.
- *   - a context is bound to one CUDA device and may be used from one host thread at a time.  Multi-GPU = one context
- *     per device (samples/edges are independent: no collective, no peer access).
+ *   - a context is bound to one CUDA device (ckc_create) or owns one sub-context per device (ckc_create_multi) and may be
+ *     used from one host thread at a time.  Samples / edges are independent: no collective, no peer access.
  */
 #ifndef CKC_H_
 #define CKC_H_
@@ -55,6 +55,13 @@ typedef struct ckc_stats {          /* mirrors the reference's public counters (
  * (collisionDetection.cpp:496-963).  mesh_path: a directory holding the reference's .tris files (e.g. "./simulator")
  * or a packed .ckcmesh file (tools/pack_meshes.py).  device: CUDA ordinal. */
 int  ckc_create(ckc_ctx** ctx, int env, const char* mesh_path, int device);
+/* The same with ndev devices behind ONE context: every host entry point splits its batch into ndev contiguous
+ * index ranges and drives each device from its own host thread (samples and edges are independent: no collective, no peer
+ * access; meshes and hierarchies are replicated).  A planner process that owns one checker object thereby uses every GPU of the
+ * box without a launcher.  Counters (ckc_get_stats) are summed over the devices; the `_dev` entry points need a single-device
+ * context.  mesh limits: each mesh at most 1024 triangles (CKC_ERR_ARG otherwise; the reference's largest has 1000). */
+int  ckc_create_multi(ckc_ctx** ctx, int env, const char* mesh_path, const int* devices, int ndev);
+int  ckc_num_devices(const ckc_ctx* ctx);
 void ckc_destroy(ckc_ctx* ctx);
 const char* ckc_last_error(const ckc_ctx* ctx);     /* human readable text of the last failure on this context */
 const char* ckc_version(void);
@@ -108,6 +115,23 @@ int ckc_check_angle_limits(ckc_ctx* ctx, int64_t n, const double* q, uint8_t* ok
 int ckc_pcs_check_motion_rbs(ckc_ctx* ctx, int64_t n_edges, const double* qa, const double* qb,
                              const int8_t* ac, const int8_t* ik, uint8_t* ok, int32_t* nchecks);
 
+/* reconstructRBS(State qa1, qa2, qb1, qb2, active_chain, ik_sol, Matrix& M, 0, 1, 1)  StateValidityCheckerPCS.cpp:531-577
+ * (post-processing of a solved path: the configurations the bisection visits, in order along the edge).  ONE edge per call:
+ * confs[0] = qa, confs[*n_confs - 1] = qb, the valid (projected) midpoints in between; *ok = 1 iff the edge is valid -- the only
+ * case the reference uses the matrix in; for an invalid edge the reference stops at the first invalid midpoint of its depth-first
+ * order and leaves a partial matrix, here every midpoint evaluated before the frontier died is returned.  CKC_ERR_CAPACITY if
+ * the edge needs more than `cap` rows (*n_confs then holds the number required). */
+int ckc_pcs_reconstruct_rbs(ckc_ctx* ctx, const double* qa, const double* qb, int active_chain, int ik_sol, double* confs, int64_t cap,
+                            int64_t* n_confs, uint8_t* ok);
+
+/* ---- single-arm kinematics, one to one (the batched entry points above fuse them; the drop-in classes expose these members) ---- */
+/* two_robots::FKsolve_rob(State q, int robot_num) + get_FK_solution_T1/T2  apc_class.cpp:51-76, :78-112.  robot[i] = 1 or 2;
+ * T16[i] = 4x4 row-major tool pose in the world frame. */
+int ckc_fk(ckc_ctx* ctx, int64_t n, const double* q6, const int8_t* robot, double* T16);
+/* two_robots::IKsolve_rob(Matrix T, int robot_num, int solution_num) + get_IK_solution_q1/q2  apc_class.cpp:114-245.
+ * ok[i] = 0 on the reference's early returns (joint limit, unreachable); q6[i] is meaningful when ok[i] = 1. */
+int ckc_ik(ckc_ctx* ctx, int64_t n, const double* T16, const int8_t* robot, const int8_t* sol, double* q6, uint8_t* ok);
+
 /* ---- collision ------------------------------------------------------------------------------------------------ */
 /* int collisionDetection::collision_state(Matrix P, State q1, State q2)  collisionDetection.cpp:31-494
  * hit[i] = 1 iff any of the pair-table tolerance queries (8 mm) reports closer-than-tolerance (plus the env-2
@@ -125,6 +149,12 @@ int ckc_gd_project(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint
 int ckc_gd_validate(ckc_ctx* ctx, int64_t n, const double* q, double* q_out, uint8_t* valid);
 /* checkMotionRBS(State s1, State s2, 0, 0)  StateValidityCheckerGD.cpp:214-241 */
 int ckc_gd_check_motion_rbs(ckc_ctx* ctx, int64_t n_edges, const double* qa, const double* qb, uint8_t* ok, int32_t* nchecks);
+
+/* reconstructRBS(State q1, State q2, Matrix& M, 0, 1, 1)  StateValidityCheckerGD.cpp:258-296 -- see ckc_pcs_reconstruct_rbs */
+int ckc_gd_reconstruct_rbs(ckc_ctx* ctx, const double* qa, const double* qb, double* confs, int64_t cap, int64_t* n_confs, uint8_t* ok);
+/* kdl::FK(State q) + get_FK_solution()  kdl_class.cpp:251-285: tip frame of the 12-joint chain base 1 -> base 2 (4x4 row-major);
+ * a closed configuration gives Trans(D, 0, 0) */
+int ckc_kdl_fk(ckc_ctx* ctx, int64_t n, const double* q12, double* T16);
 
 /* ---- RX (relaxed constraint) flavour -------------------------------------------------------------------------- */
 /* isValidRBS(State q)  StateValidityCheckerRX.cpp:201-214 : check_relax_constraint (:105-135) && joint limits && !collision.

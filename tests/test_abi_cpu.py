@@ -122,3 +122,39 @@ def test_two_rank_sharding_gloo(tmp_path):
                           "--master-port", "29531", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "SHARD_OK" in out.stdout
+
+
+# ---- the drop-in C++ surface: every checker member the reference's planners call exists, flavour by flavour ----
+FLAVOURS = ("PCS", "GD", "HB", "RX", "SG")
+
+
+def _scanner():
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import scan_dropin_surface as S
+    return S
+
+
+def test_dropin_headers_declare_every_member_the_planners_call():
+    """tests/golden/dropin_surface.json (tools/scan_dropin_surface.py over planners/*_{PCS,GD,HB,RX,SG}*.cpp and run/plan_*.cpp of the
+    reference) lists every StateValidityChecker / two_robots / kdl / collisionDetection member those files call, with the argument
+    counts used; the drop-in header of each flavour (run through the preprocessor) must declare an overload for each."""
+    import json
+    S = _scanner()
+    surface = json.load(open(os.path.join(REPO, "tests", "golden", "dropin_surface.json")))
+    assert sorted(surface) == sorted(FLAVOURS)
+    assert sum(len(v) for v in surface.values()) >= 80
+    for flav in FLAVOURS:
+        assert S.missing(surface, flav) == [], "flavour %s" % flav
+    if os.path.isdir(S.REF):                      # in the build container: the fixture is what a fresh scan produces
+        fresh = S.scan_reference()
+        assert {f: sorted(v) for f, v in fresh.items()} == {f: sorted(v) for f, v in surface.items()}
+
+
+@pytest.mark.parametrize("flav", FLAVOURS)
+def test_planner_style_subclass_compiles(flav):
+    """host/surface_check.cpp: a class that inherits the drop-in checker publicly (as the reference's planners do) and calls each of
+    those members with the reference's argument types -- syntax-checked by g++ for every flavour"""
+    host = os.path.join(REPO, "abb_dualarm_planning_b200", "host")
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-DSURFACE_" + flav, os.path.join(host, "surface_check.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
