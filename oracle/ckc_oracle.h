@@ -122,6 +122,18 @@ int  ckco_gd_check_motion_rbs(const ckco_kin* k, const ckco_world* w, const doub
 /* RX check_relax_constraint RX.cpp:105-135: residual (returned through *resid) < eps */
 int  ckco_rx_check(const ckco_kin* k, const double q[12], double eps, double* resid);
 
+/* ---- members added in round 2 (ckc_oracle_more.cpp) ---- */
+/* reconstructRBS PCS.cpp:531-577 / GD.cpp:246-296: rows (cap x 12) receives the matrix {a, ordered valid midpoints, b} the reference
+ * builds (partial when the edge is invalid: its recursion stops at the first invalid midpoint); returns the reference's bool */
+int ckco_pcs_reconstruct_rbs(const ckco_kin* k, const ckco_world* w, const double qa[12], const double qb[12], int ac, int ik,
+                             double* rows, int cap, int* nrows);
+int ckco_gd_reconstruct_rbs(const ckco_kin* k, const ckco_world* w, const double qa[12], const double qb[12], double* rows, int cap, int* nrows);
+/* checkMotion PCS.cpp:389-432 (fixed grid, breadth-first bisection order) / GD.cpp:136-175 (serial grid) */
+int ckco_pcs_check_motion(const ckco_kin* k, const ckco_world* w, const double qa[12], const double qb[12], int ac, int ik, int* nchecks);
+int ckco_gd_check_motion(const ckco_kin* k, const ckco_world* w, const double qa[12], const double qb[12], int* nchecks);
+/* IKproject(q1, q2, ik, active_chain, ik_nn) PCS.cpp:94-138 */
+int ckco_pcs_ikproject5(const ckco_kin* k, const ckco_world* w, double q[12], int ik_out[2], int* ac, const int ik_nn[2]);
+
 /* ---- batch drivers (OpenMP-free, single thread; bench.py forks processes for multi-core) ---- */
 /* S-PCS validate: out_ok[i] = IK feasible, out_valid[i] = feasible && !collision; q_out (n*12, AoS) optional */
 void ckco_batch_pcs_validate(const ckco_kin* k, const ckco_world* w, int64_t n, const double* q_aos,

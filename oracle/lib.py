@@ -231,3 +231,41 @@ class Oracle:
         for i in range(n):
             ok[i] = self.L.ckco_rx_check(C.byref(self.kin), _p(q[i]), C.c_double(eps), C.byref(r)); res[i] = r.value
         return ok, res
+
+    # ---- members added in round 2 (ckc_oracle_more.cpp) ----
+    def pcs_reconstruct_rbs(self, qa, qb, ac, ik, cap=8192):
+        qa = np.ascontiguousarray(qa, np.float64).reshape(12); qb = np.ascontiguousarray(qb, np.float64).reshape(12)
+        rows = np.empty((cap, 12)); n = C.c_int()
+        ok = self.L.ckco_pcs_reconstruct_rbs(C.byref(self.kin), self._w, _p(qa), _p(qb), int(ac), int(ik), _p(rows), cap, C.byref(n))
+        return bool(ok), rows[:n.value].copy()
+
+    def gd_reconstruct_rbs(self, qa, qb, cap=8192):
+        qa = np.ascontiguousarray(qa, np.float64).reshape(12); qb = np.ascontiguousarray(qb, np.float64).reshape(12)
+        rows = np.empty((cap, 12)); n = C.c_int()
+        ok = self.L.ckco_gd_reconstruct_rbs(C.byref(self.kin), self._w, _p(qa), _p(qb), _p(rows), cap, C.byref(n))
+        return bool(ok), rows[:n.value].copy()
+
+    def pcs_check_motion(self, qa, qb, ac, ik):
+        qa = np.ascontiguousarray(qa, np.float64).reshape(-1, 12); qb = np.ascontiguousarray(qb, np.float64).reshape(-1, 12); n = len(qa)
+        ac = np.broadcast_to(np.asarray(ac, np.int8), (n,)); ik = np.broadcast_to(np.asarray(ik, np.int8), (n,))
+        ok = np.zeros(n, np.uint8); nc = np.zeros(n, np.int32); t = C.c_int()
+        for i in range(n):
+            ok[i] = self.L.ckco_pcs_check_motion(C.byref(self.kin), self._w, _p(qa[i]), _p(qb[i]), int(ac[i]), int(ik[i]), C.byref(t)); nc[i] = t.value
+        return ok, nc
+
+    def gd_check_motion(self, qa, qb):
+        qa = np.ascontiguousarray(qa, np.float64).reshape(-1, 12); qb = np.ascontiguousarray(qb, np.float64).reshape(-1, 12); n = len(qa)
+        ok = np.zeros(n, np.uint8); nc = np.zeros(n, np.int32); t = C.c_int()
+        for i in range(n):
+            ok[i] = self.L.ckco_gd_check_motion(C.byref(self.kin), self._w, _p(qa[i]), _p(qb[i]), C.byref(t)); nc[i] = t.value
+        return ok, nc
+
+    def pcs_ikproject5(self, q, ac, ik_nn):
+        q = np.array(q, np.float64).reshape(-1, 12).copy(); n = len(q)
+        ac = np.broadcast_to(np.asarray(ac, np.int32), (n,)).copy(); nn = np.ascontiguousarray(ik_nn, np.int32).reshape(n, 2)
+        valid = np.zeros(n, np.uint8); ik = np.zeros((n, 2), np.int32)
+        for i in range(n):
+            a = C.c_int(int(ac[i]))
+            valid[i] = self.L.ckco_pcs_ikproject5(C.byref(self.kin), self._w, _p(q[i]), _p(ik[i], C.c_int), C.byref(a), _p(nn[i], C.c_int))
+            ac[i] = a.value
+        return valid, ac.astype(np.int8), ik, q

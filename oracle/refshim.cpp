@@ -36,7 +36,8 @@ typedef std::vector<double> State;
 typedef std::vector<std::vector<double> > Matrix;
 
 enum { OP_PCS_PROJECT = 1, OP_COLLIDE = 2, OP_PCS_VALIDATE = 3, OP_RBS = 4, OP_TRIDIST = 5, OP_PAIR_COUNTERS = 6,
-       OP_IDENTIFY_IK = 7, OP_MIN_DISTANCE = 8, OP_FK = 9, OP_IK = 10, OP_SPCS_SEEDED = 11, OP_ISVALID_FULL = 12 };
+       OP_IDENTIFY_IK = 7, OP_MIN_DISTANCE = 8, OP_FK = 9, OP_IK = 10, OP_SPCS_SEEDED = 11, OP_ISVALID_FULL = 12,
+       OP_RECONSTRUCT_RBS = 13, OP_IKPROJECT5 = 14 };
 
 /* ---------------- symbol resolution from the executable's .symtab ---------------- */
 static const char* g_map; static size_t g_map_len;
@@ -73,11 +74,13 @@ typedef int (*madd_t)(void*, const double*, const double*, const double*, int);
 typedef int (*mend_t)(void*);
 typedef int (*tol_t)(void*, double (*)[3], double*, void*, double (*)[3], double*, void*, double, int);
 typedef bool (*isvalid_t)(void*, const void*);
+typedef bool (*recon_t)(void*, State*, State*, State*, State*, int, int, Matrix*, int, int, int);
+typedef bool (*ikp5_t)(void*, State*, State*, State*, int*, State*);
 typedef int (*dist_t)(void*, double (*)[3], double*, void*, double (*)[3], double*, void*, double, double, int);
 
 static ctor_t f_ctor; static ikR_t f_r1, f_r2; static getq_t f_getq1, f_getq2; static coll_t f_coll; static vrbs_t f_vrbs;
 static rbs_t f_rbs; static ident_t f_ident; static tridist_t f_tridist; static fk_t f_fk; static getT_t f_getT1, f_getT2; static ik_t f_ik;
-static isvalid_t f_isvalid;
+static isvalid_t f_isvalid; static recon_t f_recon; static ikp5_t f_ikp5;
 static mctor_t f_mctor; static mbegin_t f_mbegin; static madd_t f_madd; static mend_t f_mend; static tol_t f_tol; static dist_t f_dist;
 
 static void resolve_all() {
@@ -96,6 +99,8 @@ static void resolve_all() {
     f_getT2 = (getT_t)sym("_ZN10two_robots18get_FK_solution_T2Ev");
     f_ik = (ik_t)sym("_ZN10two_robots11IKsolve_robESt6vectorIS0_IdSaIdEESaIS2_EEii");
     f_isvalid = (isvalid_t)sym("_ZN20StateValidityChecker7isValidEPKN4ompl4base5StateE");
+    f_recon = (recon_t)sym("_ZN20StateValidityChecker14reconstructRBSESt6vectorIdSaIdEES2_S2_S2_iiRS0_IS2_SaIS2_EEiii");
+    f_ikp5 = (ikp5_t)sym("_ZN20StateValidityChecker9IKprojectERSt6vectorIdSaIdEES3_S3_RiS2_");
     f_mctor = (mctor_t)sym("_ZN9PQP_ModelC1Ev");
     f_mbegin = (mbegin_t)sym("_ZN9PQP_Model10BeginModelEi");
     f_madd = (madd_t)sym("_ZN9PQP_Model6AddTriEPKdS1_S1_i");
@@ -290,6 +295,35 @@ static int shim_main(int, char**, char**) {
             if (ok[i]) { State r; (rb[i] == 1 ? f_getq1 : f_getq2)(&r, g_self); for (int j = 0; j < 6; j++) qo[6 * i + j] = r[j]; }
         }
         secs = now() - t0; put(out, ok.data(), n); put(out, qo.data(), qo.size());
+    } else if (op == OP_RECONSTRUCT_RBS) {
+        /* reconstructRBS(qa1, qa2, qb1, qb2, ac, ik, M = {a, b}, 0, 1, 1)  PCS.cpp:531-577.  payload: n*24 doubles (a, b), n int8 ac, n int8 ik
+         * -> n uint8 ok, n int32 rows, then the rows of every edge (12 doubles each) back to back */
+        const double* q = (const double*)pay; const int8_t* ac = (const int8_t*)(pay + (size_t)n * 192); const int8_t* ik = ac + n;
+        std::vector<uint8_t> ok(n); std::vector<int32_t> nrows(n); std::vector<double> rows;
+        double t0 = now();
+        for (int i = 0; i < n; i++) {
+            const double* a = q + 24 * i; const double* b = a + 12;
+            State a1(a, a + 6), a2(a + 6, a + 12), b1(b, b + 6), b2(b + 6, b + 12);
+            Matrix M; M.push_back(State(a, a + 12)); M.push_back(State(b, b + 12));
+            ok[i] = f_recon(g_self, &a1, &a2, &b1, &b2, ac[i], ik[i], &M, 0, 1, 1);
+            nrows[i] = (int32_t)M.size();
+            for (size_t r = 0; r < M.size(); r++) rows.insert(rows.end(), M[r].begin(), M[r].end());
+        }
+        secs = now() - t0; put(out, ok.data(), n); put(out, nrows.data(), n); put(out, rows.data(), rows.size());
+    } else if (op == OP_IKPROJECT5) {
+        /* IKproject(q1, q2, ik, active_chain, ik_nn)  PCS.cpp:94-138.  payload: n*12 q, n int8 ac, n*2 int8 ik_nn
+         * -> n uint8 valid, n int8 ac_out, n*2 int32 ik, n*12 q */
+        const double* q = (const double*)pay; const int8_t* ac = (const int8_t*)(pay + (size_t)n * 96); const int8_t* nn = ac + n;
+        std::vector<uint8_t> v(n); std::vector<int8_t> aco(n); std::vector<int32_t> iko((size_t)n * 2); std::vector<double> qo((size_t)n * 12);
+        double t0 = now();
+        for (int i = 0; i < n; i++) {
+            State q1(q + 12 * i, q + 12 * i + 6), q2(q + 12 * i + 6, q + 12 * i + 12), ikv(2), iknn = { (double)nn[2 * i], (double)nn[2 * i + 1] };
+            int a = ac[i];
+            v[i] = f_ikp5(g_self, &q1, &q2, &ikv, &a, &iknn);
+            aco[i] = (int8_t)a; iko[2 * i] = (int32_t)ikv[0]; iko[2 * i + 1] = (int32_t)ikv[1];
+            for (int j = 0; j < 6; j++) { qo[12 * i + j] = q1[j]; qo[12 * i + 6 + j] = q2[j]; }
+        }
+        secs = now() - t0; put(out, v.data(), n); put(out, aco.data(), n); put(out, iko.data(), iko.size()); put(out, qo.data(), qo.size());
     } else { fprintf(stderr, "refshim: unknown op %d\n", op); _Exit(2); }
 
     FILE* o = fopen(outp, "wb"); if (!o) _Exit(2);

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(_HERE, "_ref")
 OPS = dict(pcs_project=1, collide=2, pcs_validate=3, rbs=4, tridist=5, pair_counters=6, identify_ik=7, min_distance=8,
-           fk=9, ik=10, spcs_seeded=11, isvalid_full=12)
+           fk=9, ik=10, spcs_seeded=11, isvalid_full=12, reconstruct_rbs=13, ikproject5=14)
 MAX_PAIRS = 116
 
 
@@ -124,3 +124,26 @@ def ik(T, robot, sol, env=1):
     T = np.ascontiguousarray(T, np.float64).reshape(-1, 16); n = len(T)
     d, s = _run("ik", n, env, 0, T.tobytes() + _i8(robot, n).tobytes() + _i8(sol, n).tobytes())
     return np.frombuffer(d[:n], np.uint8).copy(), np.frombuffer(d[n:], np.float64).reshape(n, 6).copy()
+
+
+def reconstruct_rbs(qa, qb, ac, ik, env=1):
+    """the binary's reconstructRBS(qa1, qa2, qb1, qb2, ac, ik, M = {a, b}, 0, 1, 1): (ok [n], list of row matrices)"""
+    qa = _q(qa); qb = _q(qb); n = len(qa)
+    pay = np.concatenate([qa, qb], axis=1).tobytes() + _i8(ac, n).tobytes() + _i8(ik, n).tobytes()
+    d, s = _run("reconstruct_rbs", n, env, 0, pay)
+    ok = np.frombuffer(d[:n], np.uint8).copy(); nrows = np.frombuffer(d[n:5 * n], np.int32).copy()
+    rows = np.frombuffer(d[5 * n:], np.float64).reshape(-1, 12)
+    out, o = [], 0
+    for r in nrows:
+        out.append(rows[o:o + r].copy()); o += r
+    return ok, out
+
+
+def ikproject5(q, ac, ik_nn, env=1):
+    """the binary's IKproject(q1, q2, ik, active_chain, ik_nn): (valid, ac_out, ik [n, 2], q [n, 12])"""
+    q = _q(q); n = len(q)
+    nn = np.ascontiguousarray(ik_nn, np.int8).reshape(n, 2)
+    d, s = _run("ikproject5", n, env, 0, q.tobytes() + _i8(ac, n).tobytes() + nn.tobytes())
+    v = np.frombuffer(d[:n], np.uint8).copy(); aco = np.frombuffer(d[n:2 * n], np.int8).copy()
+    iko = np.frombuffer(d[2 * n:10 * n], np.int32).reshape(n, 2).copy(); qo = np.frombuffer(d[10 * n:], np.float64).reshape(n, 12).copy()
+    return v, aco, iko, qo

@@ -380,3 +380,62 @@ def test_tris_directory_loader_equals_packed_meshes(oracle):
     assert (ra[0] == rb[0]).all() and (ra[1] == rb[1]).all() and (ra[2] == rb[2]).all()
     assert ra[1].sum() > 1000
     a.close(); b.close()
+
+
+# ---- round 2: single-arm kinematics, reconstructRBS and the multi-device context through the C ABI ----
+def test_fk_ik_kdl_fk_entry_points(ck, oracle, gold):
+    q, ik = oracle.sample_pcs(15, 0, 400)
+    for robot in (1, 2):
+        T = ck.fk(q[:, 6 * (robot - 1):6 * robot], robot)
+        To = np.array([oracle.fk(r[6 * (robot - 1):6 * robot], robot) for r in q])
+        assert np.abs(T - To).max() < 1e-9
+        for s in range(8):
+            ok, q6 = ck.ik(T, robot, s)
+            oo = [oracle.ik(t, robot, s) for t in To]
+            assert (ok == np.array([o[0] for o in oo])).all()
+            m = ok == 1
+            if m.any():
+                assert np.abs(q6[m] - np.array([o[1] for o in oo])[m]).max() < TOL_Q
+    Tk = ck.kdl_fk(q)
+    assert np.abs(Tk - np.array([oracle.kdl_fk(r) for r in q])).max() < 1e-9
+    path = gold("ref_path.npz")["path"]                       # the reference's solved path closes the chain: Trans(D, 0, 0)
+    Tp = ck.kdl_fk(path)
+    assert np.abs(Tp[:, 0, 3] - 900).max() < 0.05 and np.abs(Tp[:, :3, :3] - np.eye(3)).max() < 2e-3
+
+
+def test_reconstruct_rbs_vs_reference_binary_golden(ck, gold):
+    g = gold("reconstruct_rbs.npz")
+    off = 0
+    for i in range(len(g["qa"])):
+        ok, rows = ck.pcs_reconstruct_rbs(g["qa"][i], g["qb"][i], 0, int(g["ik"][i]))
+        want = g["rows"][off:off + g["nrows"][i]]; off += g["nrows"][i]
+        assert ok == bool(g["ok"][i])
+        if ok:
+            assert len(rows) == len(want) and np.abs(rows - want).max() < TOL_Q
+
+
+def test_multi_device_context_matches_single(ck, oracle):
+    """ckc_create_multi: one context, several devices, every host entry point split into contiguous ranges.  With one GPU in
+    the box the same device is listed twice (two sub-contexts, two host threads); with two or more, real devices."""
+    import torch
+    from abb_dualarm_planning_b200 import Checker, sampling
+    devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    m = Checker(env=1, devices=devs + [0])
+    assert m.num_devices == 3
+    q, ik = sampling.sample_pcs(19, 0, 200001)
+    ok1, v1, q1 = ck.pcs_validate(q, 0, ik)
+    ok2, v2, q2 = m.pcs_validate(q, 0, ik)
+    assert (ok1 == ok2).all() and (v1 == v2).all() and (q1 == q2).all()
+    vc, idx, qv = m.pcs_validate_compact(q, 0, ik)
+    assert (vc == v1).all() and sorted(idx.tolist()) == np.nonzero(v1)[0].tolist()
+    assert np.abs(qv[np.argsort(idx)] - q1[v1 == 1]).max() == 0
+    g = sampling.sample_gd(19, 0, 50001)
+    assert (m.gd_validate(g)[0] == ck.gd_validate(g)[0]).all()
+    a = q1[v1 == 1][:301]; b = a + 0.01
+    _, vb, qb = ck.pcs_validate(b, 0, ik[v1 == 1][:301])
+    r1, n1 = ck.pcs_check_motion_rbs(a, qb, 0, ik[v1 == 1][:301]); r2, n2 = m.pcs_check_motion_rbs(a, qb, 0, ik[v1 == 1][:301])
+    assert (r1 == r2).all() and (n1 == n2).all()
+    assert (m.collide(q1[:5001]) == ck.collide(q1[:5001])).all() and (m.identify_ik(q1[:999]) == ck.identify_ik(q1[:999])).all()
+    s = m.stats()
+    assert s["collision_calls"] > 0 and s["kernel_launches"] > 0
+    m.close()
