@@ -47,7 +47,7 @@ struct ckc_lane {
     cudaStream_t st = nullptr;
     cudaStream_t st_hi = nullptr;       /* high-priority stream for the collision stage of this lane's chunk */
     cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_c = nullptr;
-    dev_buf qin, qout, ac, ik, ok, valid, list, ovf, bigstack, flags, aux, aux2, small, gdstate, pairstat;
+    dev_buf qin, qout, ac, ik, ok, valid, list, ovf, bigstack, flags, aux, aux2, small, gdstate, pairstat, smallio;
     int64_t collide_launches = 0;
     /* this lane's own first-hit statistics and processing order of the pair table: [0, MAX_PAIRS) hits, [MAX_PAIRS, 2 MAX_PAIRS)
      * order.  They are read and rewritten only by kernels on this lane's stream -- a table shared by the lanes would be
@@ -59,7 +59,7 @@ struct ckc_lane {
     int32_t* ovf_count() const { return small.as<int32_t>() + 4; }
     int32_t* rbs_counts() const { return small.as<int32_t>() + 8; }        /* 2 ints */
     unsigned long long* gd_counter() const { return (unsigned long long*)(small.as<int32_t>() + 12); }
-    void release() { dev_buf* b[] = { &qin, &qout, &ac, &ik, &ok, &valid, &list, &ovf, &bigstack, &flags, &aux, &aux2, &small, &gdstate, &pairstat }; for (dev_buf* x : b) x->release(); }
+    void release() { dev_buf* b[] = { &qin, &qout, &ac, &ik, &ok, &valid, &list, &ovf, &bigstack, &flags, &aux, &aux2, &small, &gdstate, &pairstat, &smallio }; for (dev_buf* x : b) x->release(); }
 };
 
 struct ckc_ctx {
@@ -77,7 +77,8 @@ struct ckc_ctx {
     dev_buf d_nodes, d_tris, d_ctr, d_pairtab, d_static, d_pairhits, d_pairorder;
     dev_buf d_cidx, d_cq, d_ccount;                     /* compact outputs of the *_compact entry points (per chunk regions) */
     void* h_stage = nullptr; size_t h_stage_cap = 0;    /* pinned staging of the compact outputs */
-    dev_buf rbs_seg[2], rbs_cand, rbs_pool, rbs_eok, rbs_nck, rbs_hit, rbs_eac, rbs_eik, rbs_nt;      /* RBS frontier storage, kept between calls */
+    void* h_small = nullptr;                            /* pinned staging of the small-batch path (project_small) */
+    dev_buf rbs_seg[2], rbs_cand, rbs_pool, rbs_eok, rbs_nck, rbs_hit, rbs_eac, rbs_eik, rbs_nt, rbs_in;      /* RBS frontier storage, kept between calls */
     /* per-chunk work buffers: CKC_NUM_LANES independent sets, each with its own stream, so that the host entry points
      * can overlap the H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 */
     ckc_lane lanes[CKC_NUM_LANES];
@@ -573,13 +574,14 @@ extern "C" void ckc_destroy(ckc_ctx* ctx) {
     if (!ctx->children.empty()) { for (ckc_ctx* c : ctx->children) ckc_destroy(c); delete ctx; return; }
     cudaSetDevice(ctx->device);
     dev_buf* bufs[] = { &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_pairhits, &ctx->d_pairorder, &ctx->rbs_seg[0], &ctx->rbs_seg[1],
-                        &ctx->rbs_cand, &ctx->rbs_pool, &ctx->rbs_eok, &ctx->rbs_nck, &ctx->rbs_hit, &ctx->rbs_eac, &ctx->rbs_eik, &ctx->rbs_nt };
+                        &ctx->rbs_cand, &ctx->rbs_pool, &ctx->rbs_eok, &ctx->rbs_nck, &ctx->rbs_hit, &ctx->rbs_eac, &ctx->rbs_eik, &ctx->rbs_nt, &ctx->rbs_in };
     for (dev_buf* b : bufs) b->release();
     for (int l = 0; l < CKC_NUM_LANES; l++) { ctx->lanes[l].release(); if (ctx->lanes[l].ev_done) cudaEventDestroy(ctx->lanes[l].ev_done); if (ctx->lanes[l].ev_p) cudaEventDestroy(ctx->lanes[l].ev_p); if (ctx->lanes[l].ev_c) cudaEventDestroy(ctx->lanes[l].ev_c);
         if (ctx->lanes[l].st_hi) cudaStreamDestroy(ctx->lanes[l].st_hi); if (ctx->lanes[l].st) cudaStreamDestroy(ctx->lanes[l].st); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     ctx->d_cidx.release(); ctx->d_cq.release(); ctx->d_ccount.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
     delete ctx;
 }
 
@@ -738,10 +740,48 @@ static int run_gd_chunk(ckc_ctx* ctx, ckc_lane& L, int64_t n, const double* d_q,
 /* ---------------------------------------------------------------------------------------------------------------- */
 struct compact_out { int64_t* n_valid; int32_t* idx; double* q_valid; int64_t cap; };
 
+/* Small batches (a planner's single questions: 1 .. 2048 samples): latency, not bandwidth.  Inputs are packed into ONE pinned staging
+ * block and uploaded with one copy, all outputs come back with one copy, one lane, one stream synchronisation, no priority-stream hop:
+ * 5 runtime calls around the kernels instead of ~25 (88 -> ~35 us per single-sample ckc_pcs_validate). */
+#define CKC_SMALL_MAX 2048
+static int project_small(ckc_ctx* ctx, int flavour, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out,
+                         uint8_t* ok, uint8_t* conv, int32_t* iters, uint8_t* valid, bool collide) {
+    ckc_lane& L = ctx->lanes[0];
+    cudaStream_t st = L.st;
+    const size_t in_bytes = ((size_t)n * 98 + 255) & ~(size_t)255, out_bytes = (size_t)n * 103;
+    if (!ctx->h_small) CU(cudaMallocHost(&ctx->h_small, ((size_t)CKC_SMALL_MAX * 98 + 256) + (size_t)CKC_SMALL_MAX * 103));
+    CU(L.smallio.reserve(((size_t)CKC_SMALL_MAX * 98 + 256) + (size_t)CKC_SMALL_MAX * 103));
+    char* h = (char*)ctx->h_small; char* d = (char*)L.smallio.p;
+    memcpy(h, q, (size_t)n * 96);
+    if (ac) memcpy(h + (size_t)n * 96, ac, (size_t)n); else memset(h + (size_t)n * 96, 0, (size_t)n);
+    if (ik) memcpy(h + (size_t)n * 97, ik, (size_t)n);
+    CU(cudaMemcpyAsync(d, h, (size_t)n * 98, cudaMemcpyHostToDevice, st));
+    double* d_qout = (double*)(d + in_bytes); int32_t* d_it = (int32_t*)(d + in_bytes + (size_t)n * 96);
+    uint8_t* d_ok = (uint8_t*)(d + in_bytes + (size_t)n * 100); uint8_t* d_valid = d_ok + n; uint8_t* d_conv = d_valid + n;
+    const bool saved = ctx->overlap;
+    ctx->overlap = false;                 /* no hop to the high-priority stream: nothing to overlap with */
+    int rc;
+    if (flavour == 0) rc = run_pcs_chunk(ctx, L, n, (const double*)d, AOS, (const int8_t*)(d + (size_t)n * 96), (const int8_t*)(d + (size_t)n * 97), 0, 0, 0, d_qout, AOS,
+                                         d_ok, d_valid, collide, st);
+    else { CU(L.gdstate.reserve((size_t)CKC_SMALL_MAX * 4)); rc = run_gd_chunk(ctx, L, n, (const double*)d, AOS, 0, 0, 0, d_qout, AOS, d_ok, d_conv, d_it, d_valid, collide, st); }
+    ctx->overlap = saved;
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CU(cudaMemcpyAsync(h + in_bytes, d + in_bytes, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const char* o = h + in_bytes;
+    if (q_out) memcpy(q_out, o, (size_t)n * 96);
+    if (iters) memcpy(iters, o + (size_t)n * 96, (size_t)n * 4);
+    if (ok) memcpy(ok, o + (size_t)n * 100, (size_t)n);
+    if (valid) memcpy(valid, o + (size_t)n * 101, (size_t)n);
+    if (conv) memcpy(conv, o + (size_t)n * 102, (size_t)n);
+    return CKC_OK;
+}
+
 static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, const double* q, const int8_t* ac, const int8_t* ik, double* q_out,
                         uint8_t* ok, uint8_t* conv, int32_t* iters, uint8_t* valid, bool collide, const compact_out* co = nullptr) {
     if (!ctx || n < 0 || n > 0x7fffffff || (n > 0 && (!q || (flavour == 0 && !ik)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
+    if (n > 0 && n <= CKC_SMALL_MAX && !co) return project_small(ctx, flavour, n, q, ac, ik, q_out, ok, conv, iters, valid, collide);
     const int64_t C = std::max<int64_t>(1, std::min<int64_t>(ctx->pipe_chunk, std::max<int64_t>(std::min<int64_t>(n, 1 << 16), (n + 3) / 4)));
     /* compact mode: each chunk appends its valid (index, configuration) pairs to its own device region; a fixed-size prefix
      * (5 % of the chunk + 1024 entries) of every region is copied back inside the pipeline, the rare overflow afterwards */
@@ -1230,18 +1270,37 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
     cudaStream_t st = L.st;
     const int ne = (int)n_edges;
     dev_buf (&seg)[2] = ctx->rbs_seg;
-    dev_buf &cand = ctx->rbs_cand, &pool = ctx->rbs_pool, &eok = ctx->rbs_eok, &nck = ctx->rbs_nck, &hit = ctx->rbs_hit, &eac = ctx->rbs_eac, &eik = ctx->rbs_eik;
-    int64_t seg_cap = std::max<int64_t>(2 * (int64_t)ne, 1024);
+    dev_buf &cand = ctx->rbs_cand, &pool = ctx->rbs_pool, &nck = ctx->rbs_nck, &hit = ctx->rbs_hit;
+    /* thin-tail kernel (PCS flavour): frontiers of at most tail_max segments are bisected to the end inside ONE cooperative launch */
+    static const int tail_max_env = [] { const char* e = getenv("CKC_RBS_TAIL"); return e ? atoi(e) : 4096; }();
+    const int64_t tail_max = flavour == 0 ? tail_max_env : 0;
+    int64_t seg_cap = std::max<int64_t>(std::max<int64_t>(2 * (int64_t)ne, 1024), 4 * tail_max + 1024);
     CU(seg[0].reserve((size_t)seg_cap * 16)); CU(seg[1].reserve((size_t)seg_cap * 16)); CU(cand.reserve((size_t)seg_cap * 8));
     CU(pool.reserve((size_t)(2 * (int64_t)ne + seg_cap) * 96));
-    CU(eok.reserve(ne)); CU(nck.reserve((size_t)ne * 4)); CU(eac.reserve(ne)); CU(eik.reserve(ne));
+    /* per-edge results live in ONE allocation, [nchecks (4 ne) | edge_ok (ne)], so that a small call reads them back with one copy */
+    CU(nck.reserve((size_t)ne * 5));
+    uint8_t* d_eok = nck.as<uint8_t>() + (size_t)ne * 4;
     dev_buf& nt = ctx->rbs_nt;
     if (rec) CU(nt.reserve(pool.cap / 12));
-    /* endpoints interleaved: node 2e = a, node 2e+1 = b */
-    CU(cudaMemcpy2DAsync(pool.p, 192, qa, 96, 96, ne, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpy2DAsync((char*)pool.p + 96, 192, qb, 96, 96, ne, cudaMemcpyHostToDevice, st));
-    if (ac) CU(cudaMemcpyAsync(eac.p, ac, ne, cudaMemcpyHostToDevice, st));
-    if (ik) CU(cudaMemcpyAsync(eik.p, ik, ne, cudaMemcpyHostToDevice, st));
+    /* inputs: [qa | qb | ac | ik] in one device block; k_rbs_init interleaves the end points: node 2e = a, node 2e+1 = b.  Small calls
+     * (a planner's edges) pack them into the pinned staging block first: one upload instead of four */
+    dev_buf& ein = ctx->rbs_in;
+    CU(ein.reserve((size_t)ne * 194));
+    const bool small_call = ne <= CKC_SMALL_MAX;
+    if (small_call) {
+        if (!ctx->h_small) CU(cudaMallocHost(&ctx->h_small, ((size_t)CKC_SMALL_MAX * 98 + 256) + (size_t)CKC_SMALL_MAX * 103));
+        char* h = (char*)ctx->h_small;
+        memcpy(h, qa, (size_t)ne * 96); memcpy(h + (size_t)ne * 96, qb, (size_t)ne * 96);
+        if (ac) memcpy(h + (size_t)ne * 192, ac, ne);
+        if (ik) memcpy(h + (size_t)ne * 193, ik, ne);
+        CU(cudaMemcpyAsync(ein.p, h, (size_t)ne * 194, cudaMemcpyHostToDevice, st));
+    } else {
+        CU(cudaMemcpyAsync(ein.p, qa, (size_t)ne * 96, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync((char*)ein.p + (size_t)ne * 96, qb, (size_t)ne * 96, cudaMemcpyHostToDevice, st));
+        if (ac) CU(cudaMemcpyAsync((char*)ein.p + (size_t)ne * 192, ac, ne, cudaMemcpyHostToDevice, st));
+        if (ik) CU(cudaMemcpyAsync((char*)ein.p + (size_t)ne * 193, ik, ne, cudaMemcpyHostToDevice, st));
+    }
+    const int8_t* d_eac = (const int8_t*)((char*)ein.p + (size_t)ne * 192); const int8_t* d_eik = d_eac + ne;
     int32_t* d_cnt = L.rbs_counts();                       /* [0] candidates, [1] next segments */
     int cur = 0;
     int64_t nseg = ne, nnodes = 2 * (int64_t)ne;
@@ -1255,15 +1314,64 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
         r.next_a = s1; r.next_b = s1 + cap1; r.next_edge = s1 + 2 * cap1; r.next_depth = s1 + 3 * cap1;
         r.cand_node = cand.as<int32_t>(); r.cand_seg = cand.as<int32_t>() + (int64_t)(cand.cap / 8);
         r.cand_count = d_cnt; r.next_count = d_cnt + 1;
-        r.edge_ok = eok.as<uint8_t>(); r.nchecks = nck.as<int32_t>();
-        r.edge_ac = ac ? eac.as<int8_t>() : nullptr; r.edge_ik = eik.as<int8_t>();
+        r.edge_ok = d_eok; r.nchecks = nck.as<int32_t>();
+        r.edge_ac = ac ? d_eac : nullptr; r.edge_ik = d_eik;
         r.tol = 0.05; r.max_depth = 150;                    /* StateValidityCheckerPCS.h:218-220 */
         return r;
     };
-    ckc_launch_rbs_init(make(cur), ne, st);
+    ckc_launch_rbs_init(make(cur), ne, ein.as<double>(), st);
     ctx->launches++;
     int rounds = 0;
+    bool tail_ok = tail_max > 0, results_staged = false;
     while (nseg > 0) {
+        if (tail_ok && nseg <= tail_max) {
+            /* ---- the rest of the bisection in one cooperative launch (k_rbs_tail) ---- */
+            const int64_t want_nodes = nnodes + 16 * tail_max;
+            if ((size_t)want_nodes * 96 > pool.cap) CU(reserve_keep(pool, (size_t)(want_nodes + want_nodes / 2) * 96, (size_t)nnodes * 96, st));
+            if ((size_t)want_nodes > hit.cap) CU(hit.reserve((size_t)(want_nodes + want_nodes / 2)));
+            if (rec && (size_t)want_nodes * 8 > nt.cap) CU(reserve_keep(nt, (size_t)(want_nodes + want_nodes / 2) * 8, (size_t)nnodes * 8, st));
+            CU(L.ovf.reserve((size_t)(4 * tail_max) * 4));
+            CU(L.bigstack.reserve((size_t)160 * 65536 * 4));
+            ckc_rbs_tail_state hs;
+            hs.nseg = (int32_t)nseg; hs.nnodes = (int32_t)nnodes; hs.cur = cur; hs.levels = 0; hs.status = -1; hs.total_cand = 0;
+            hs.max_seg = (int32_t)(2 * tail_max);
+            hs.seg_cap = (int32_t)std::min<int64_t>(seg[0].cap / 16, seg[1].cap / 16);
+            hs.cand_cap = (int32_t)(cand.cap / 8);
+            hs.node_cap = (int32_t)std::min<int64_t>(std::min<int64_t>((int64_t)(pool.cap / 96), (int64_t)hit.cap), rec ? (int64_t)(nt.cap / 8) : (int64_t)1 << 30);
+            hs.max_levels = 400;
+            /* one upload zeroes the level counters (ints 2..9 of the lane's scratch block) and sets the kernel's state (ints 16..26) */
+            int32_t blk[25]; memset(blk, 0, sizeof(blk));
+            memcpy(blk + 14, &hs, sizeof(hs));
+            void* dstate = (void*)(L.small.as<int32_t>() + 16);
+            CU(cudaMemcpyAsync(L.small.as<int32_t>() + 2, blk, sizeof(blk), cudaMemcpyHostToDevice, st));
+            ckc_world_dev w = ctx->world; w.pair_hits = L.pair_hits(); w.pair_order = L.pair_order();
+            ckc_launch_cfg cfg = { ctx->num_sms };
+            int lrc;
+            { stage_scope ts(ctx, st, 3);
+              lrc = ckc_launch_rbs_tail(ctx->kin, w, cfg, make(0), make(1), L.work_counter(), L.ovf.as<int32_t>(), L.ovf_count(), L.bigstack.as<uint32_t>(),
+                                        ctx->d_ctr.as<ckc_counters_dev>(), dstate, hit.as<uint8_t>(), st); }
+            if (lrc != 0) { cudaGetLastError(); tail_ok = false; continue; }      /* no cooperative launch on this device: host-driven levels */
+            ctx->launches++;
+            CU(cudaMemcpyAsync(&hs, dstate, sizeof(hs), cudaMemcpyDeviceToHost, st));
+            if (small_call) { CU(cudaMemcpyAsync((char*)ctx->h_small + (size_t)ne * 194, nck.p, (size_t)ne * 5, cudaMemcpyDeviceToHost, st)); results_staged = true; }
+            CU(cudaStreamSynchronize(st));
+            CU(cudaGetLastError());
+            ctx->host_stats.is_valid_calls += hs.total_cand;
+            nnodes = hs.nnodes; nseg = hs.nseg; cur = hs.cur; rounds += hs.levels;
+            if (hs.status == 0) break;
+            if (hs.status == 2) {          /* a buffer would overflow: grow the node storage and go on */
+                const int64_t more = nnodes + 64 * tail_max + 2 * nseg;
+                CU(reserve_keep(pool, (size_t)more * 96, (size_t)nnodes * 96, st));
+                CU(hit.reserve((size_t)more));
+                if (rec) CU(reserve_keep(nt, (size_t)more * 8, (size_t)nnodes * 8, st));
+                if (2 * nseg > hs.seg_cap || nseg > hs.cand_cap) tail_ok = false;   /* cannot happen below max_seg; be safe */
+                continue;
+            }
+            if (hs.status == 3 && rounds > 400) return fail(ctx, CKC_ERR_CAPACITY, "RBS did not terminate");
+            if (hs.status != 1) continue;
+            /* status 1: the frontier grew beyond the tail's limit again -- host-driven levels until it is thin */
+        }
+        results_staged = false;
         /* capacity for this level: <= nseg new nodes / candidates, <= 2 nseg next segments */
         if ((int64_t)(seg[1 - cur].cap / 16) < 2 * nseg) { seg[1 - cur].release(); CU(seg[1 - cur].reserve((size_t)(2 * nseg + 1024) * 16)); }
         if ((int64_t)(cand.cap / 8) < nseg) { cand.release(); CU(cand.reserve((size_t)(nseg + 1024) * 8)); }
@@ -1306,9 +1414,15 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
         cur = 1 - cur;
         if (++rounds > 200) return fail(ctx, CKC_ERR_CAPACITY, "RBS did not terminate");
     }
-    CU(cudaMemcpyAsync(ok, eok.p, ne, cudaMemcpyDeviceToHost, st));
-    if (nchecks) CU(cudaMemcpyAsync(nchecks, nck.p, (size_t)ne * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    if (results_staged) {              /* came back together with the tail kernel's state */
+        const char* o = (const char*)ctx->h_small + (size_t)ne * 194;
+        memcpy(ok, o + (size_t)ne * 4, ne);
+        if (nchecks) memcpy(nchecks, o, (size_t)ne * 4);
+    } else {
+        CU(cudaMemcpyAsync(ok, d_eok, ne, cudaMemcpyDeviceToHost, st));
+        if (nchecks) CU(cudaMemcpyAsync(nchecks, nck.p, (size_t)ne * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
     if (rec) {
         /* every node of the bisection tree with its position t along the edge (dyadic, exact for the depths a valid edge reaches):
          * sorted by t they are the matrix reconstructRBS builds -- a, the midpoints in order, b */

@@ -93,10 +93,15 @@ struct ckc_rbs_dev {
 };
 
 /* ---- launchers implemented in ckc_kernels.cu (all asynchronous on `st`) ---- */
-void ckc_launch_rbs_init(const ckc_rbs_dev& r, int n_edges, cudaStream_t st);
+void ckc_launch_rbs_init(const ckc_rbs_dev& r, int n_edges, const double* in, cudaStream_t st);
 void ckc_launch_rbs_expand(const ckc_kin_dev& kin, const ckc_rbs_dev& r, int flavour, int nseg, int node_base, cudaStream_t st);
 void ckc_launch_rbs_push(const ckc_rbs_dev& r, int max_cand, const int32_t* d_ncand, const uint8_t* hit, cudaStream_t st);
 struct ckc_launch_cfg { int num_sms; };
+/* host mirror of the state block of the RBS tail kernel (ckc_kernels.cu: rbs_tail_state) */
+struct ckc_rbs_tail_state { int32_t nseg, nnodes, cur, levels, status, total_cand, max_seg, seg_cap, cand_cap, node_cap, max_levels; };
+int ckc_launch_rbs_tail(const ckc_kin_dev& kin, const ckc_world_dev& w, const ckc_launch_cfg& cfg, const ckc_rbs_dev& r0, const ckc_rbs_dev& r1,
+                        int32_t* work_counter, int32_t* ovf_list, int32_t* ovf_count, uint32_t* big_stack, ckc_counters_dev* ctr, void* dstate, uint8_t* hit,
+                        cudaStream_t st);
 
 /* K1: projection. src == NULL => generate S-PCS samples (seed, i0).  Writes q_out (layout lo), ok, zeroes valid,
  * appends feasible sample indices to list[] (count in *list_count). */

@@ -19,6 +19,7 @@
  */
 #include "ckc_device.cuh"
 #include <cstdlib>
+#include <cstring>
 #include <algorithm>
 
 using namespace ckc;
@@ -187,26 +188,35 @@ __device__ __forceinline__ bool root_spheres_close(const ckc_world_dev& w, const
  * queues 8 x 256 B, pair table 3712 B = 46.3 kB (static __shared__ arrays: the compiler keeps the shared address space -- with one
  * carved-up extern buffer it fell back to generic loads / stores plus a window-base computation in every round).
  * kPerPair = the diagnostic form (ckc_collide_pairs): per-pair flags, no early exit, task stack in global memory, no deferral. */
+/* shared memory of one 8-warp block of the collision kernels, declared by the KERNEL and handed to the block routines below (the RBS tail
+ * kernel runs the warp routine, the heavy routine and the frontier steps in one launch and lets them share this storage) */
+struct collide_smem {
+    double f64[CKC_COLLIDE_WARPS][CKC_NUM_FRAMES * 12];
+    float f32[CKC_COLLIDE_WARPS][CKC_NUM_FRAMES * 12];
+    uint32_t stack[CKC_COLLIDE_WARPS][CKC_STACK_CAP];
+    uint32_t triq[CKC_COLLIDE_WARPS][CKC_TRIQ_CAP];
+    int4 pairs[CKC_MAX_PAIRS * 2];       /* the pair table, once per block (32 bytes per entry) */
+};
+__device__ __forceinline__ void collide_smem_init(const ckc_world_dev& w, collide_smem& sm) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < w.npairs * 2; e += blockDim.x) sm.pairs[e] = __ldg(reinterpret_cast<const int4*>(w.pair_tab) + e);
+    /* the three static obstacle poses never change: once per warp, in both precisions */
+    for (int e = lane; e < 36; e += 32) { const double v = w.static_frames_dev[e]; sm.f64[wib][CKC_FRAME_DOUBLES + e] = v; sm.f32[wib][CKC_FRAME_DOUBLES + e] = (float)v; }
+    __syncthreads();
+}
+
+/* the warps of one block take configurations from the work counter until it runs out (collide_smem_init done by the caller) */
 template <bool kPerPair>
-__global__ void __launch_bounds__(CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_MINBLOCKS)
-k_collide(const ckc_world_dev w, const collide_args a) {
-    __shared__ double s_f64[CKC_COLLIDE_WARPS][CKC_NUM_FRAMES * 12];
-    __shared__ float s_f32[CKC_COLLIDE_WARPS][CKC_NUM_FRAMES * 12];
-    __shared__ uint32_t s_stack[kPerPair ? 1 : CKC_COLLIDE_WARPS][kPerPair ? 1 : CKC_STACK_CAP];
-    __shared__ uint32_t s_triq[CKC_COLLIDE_WARPS][CKC_TRIQ_CAP];
-    __shared__ int4 s_pairs[CKC_MAX_PAIRS * 2];       /* the pair table, once per block (32 bytes per entry) */
+__device__ __forceinline__ void collide_block(const ckc_world_dev& w, const collide_args& a, collide_smem& sm) {
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    double* F64 = s_f64[wib];
-    float* F = s_f32[wib];
-    uint32_t* triq = s_triq[wib];
-    for (int e = threadIdx.x; e < w.npairs * 2; e += blockDim.x) s_pairs[e] = __ldg(reinterpret_cast<const int4*>(w.pair_tab) + e);
-    /* the three static obstacle poses never change: once per warp, in both precisions */
-    for (int e = lane; e < 36; e += 32) { const double v = w.static_frames_dev[e]; F64[CKC_FRAME_DOUBLES + e] = v; F[CKC_FRAME_DOUBLES + e] = (float)v; }
-    __syncthreads();
+    double* F64 = sm.f64[wib];
+    float* F = sm.f32[wib];
+    uint32_t* triq = sm.triq[wib];
+    const int4* s_pairs = sm.pairs;
 
     const unsigned lt_mask = (1u << lane) - 1;
-    uint32_t* stack = kPerPair ? a.big_stack + (size_t)(blockIdx.x * CKC_COLLIDE_WARPS + wib) * CKC_BIG_STACK_CAP : s_stack[kPerPair ? 0 : wib];
+    uint32_t* stack = kPerPair ? a.big_stack + (size_t)(blockIdx.x * CKC_COLLIDE_WARPS + wib) * CKC_BIG_STACK_CAP : sm.stack[wib];
     const int cap = kPerPair ? CKC_BIG_STACK_CAP : CKC_STACK_CAP;
 
     int64_t m = a.d_m ? (int64_t)*a.d_m : a.m_max;
@@ -386,12 +396,20 @@ k_collide(const ckc_world_dev w, const collide_args a) {
         n_cfg++; n_hit += hit ? 1 : 0;
         __syncwarp();
     }
-    if (lane == 0 && a.ctr) {
+    if (lane == 0 && a.ctr && n_cfg) {
         atomicAdd(&a.ctr->bv_tests, (unsigned long long)n_bv);
         atomicAdd(&a.ctr->tri_tests, (unsigned long long)n_tri);
         atomicAdd(&a.ctr->collision_calls, (unsigned long long)n_cfg);
         atomicAdd(&a.ctr->collisions, (unsigned long long)n_hit);
     }
+}
+
+template <bool kPerPair>
+__global__ void __launch_bounds__(CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_MINBLOCKS)
+k_collide(const ckc_world_dev w, const collide_args a) {
+    __shared__ collide_smem sm;
+    collide_smem_init(w, sm);
+    collide_block<kPerPair>(w, a, sm);
 }
 
 /* ---- K3h: the heavy configurations, one BLOCK per configuration ---------------------------------------------------
@@ -418,17 +436,16 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp_tot, int&
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(CKC_HEAVY_THREADS, 1)
-k_collide_heavy(const ckc_world_dev w, const collide_args a) {
-    __shared__ double F64[CKC_NUM_FRAMES * 12];
-    __shared__ float F[CKC_NUM_FRAMES * 12];
-    __shared__ uint32_t triq[CKC_HEAVY_TRIQ];
-    __shared__ int4 s_pairs[CKC_MAX_PAIRS * 2];
+/* storage: warp 0's frame tables, the first 1024 entries of the warps' stacks as the leaf-pair queue, the block's pair table */
+__device__ __forceinline__ void collide_heavy_block(const ckc_world_dev& w, const collide_args& a, collide_smem& sm) {
+    static_assert(CKC_HEAVY_TRIQ <= CKC_COLLIDE_WARPS * CKC_STACK_CAP && CKC_HEAVY_THREADS == CKC_COLLIDE_WARPS * 32, "heavy routine reuses the warp routine's shared memory");
     __shared__ int s_tot[CKC_HEAVY_THREADS / 32];
     __shared__ int s_k, s_hit;
+    double* F64 = sm.f64[0];
+    float* F = sm.f32[0];
+    uint32_t* triq = &sm.stack[0][0];
+    const int4* s_pairs = sm.pairs;
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int e = tid; e < w.npairs * 2; e += blockDim.x) s_pairs[e] = __ldg(reinterpret_cast<const int4*>(w.pair_tab) + e);
-    for (int e = tid; e < 36; e += blockDim.x) { const double v = w.static_frames_dev[e]; F64[CKC_FRAME_DOUBLES + e] = v; F[CKC_FRAME_DOUBLES + e] = (float)v; }
     uint32_t* stack = a.big_stack + (size_t)blockIdx.x * CKC_BIG_STACK_CAP;
     const int m = *a.ovf_count;
     unsigned int n_bv = 0, n_tri = 0;
@@ -520,6 +537,13 @@ k_collide_heavy(const ckc_world_dev w, const collide_args a) {
         }
     }
     if (tid == 0 && a.ctr) { atomicAdd(&a.ctr->bv_tests, (unsigned long long)n_bv); atomicAdd(&a.ctr->tri_tests, (unsigned long long)n_tri); }
+}
+
+__global__ void __launch_bounds__(CKC_HEAVY_THREADS, 1)
+k_collide_heavy(const ckc_world_dev w, const collide_args a) {
+    __shared__ collide_smem sm;
+    collide_smem_init(w, sm);
+    collide_heavy_block(w, a, sm);
 }
 
 /* rank sort of the (decayed) first-hit counters -> processing order for the next launches; one tiny block */
@@ -974,12 +998,10 @@ void ckc_launch_rx_check(const ckc_kin_dev& kin, int64_t n, const double* q, ckc
 /*   stops at the first invalid midpoint; the boolean it returns is "every node of the bisection tree is valid and no  */
 /*   branch passes depth 150", which is order independent, so all segments of one level are evaluated together.        */
 /* ================================================================================================================ */
-/* flavour 0 = PCS (analytic projection of the passive arm), 1 = GD (Newton projection of all 12 joints) */
+/* flavour 0 = PCS (analytic projection of the passive arm), 1 = GD (Newton projection of all 12 joints).
+ * One segment per thread; called with a segment index that is the same for all lanes of a warp up to + lane (ballots inside). */
 template <int kFlavour>
-__global__ void __launch_bounds__(CKC_GD_BLOCK)
-k_rbs_expand(const ckc_kin_dev kin, const ckc_rbs_dev r, int nseg, int node_base) {
-    __shared__ double sh_state[kFlavour == 1 ? 36 * CKC_GD_BLOCK : 1];
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void rbs_expand_one(const ckc_kin_dev& kin, const ckc_rbs_dev& r, int s, int nseg, int node_base, double* sh_state) {
     bool cand = false;
     int my_node = -1;
     double m[12];
@@ -1031,10 +1053,15 @@ k_rbs_expand(const ckc_kin_dev kin, const ckc_rbs_dev r, int nseg, int node_base
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_rbs_push(const ckc_rbs_dev r, const int32_t* __restrict__ d_ncand, const uint8_t* __restrict__ hit) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ncand = *d_ncand;
+template <int kFlavour>
+__global__ void __launch_bounds__(CKC_GD_BLOCK)
+k_rbs_expand(const ckc_kin_dev kin, const ckc_rbs_dev r, int nseg, int node_base) {
+    __shared__ double sh_state[kFlavour == 1 ? 36 * CKC_GD_BLOCK : 1];
+    rbs_expand_one<kFlavour>(kin, r, blockIdx.x * blockDim.x + threadIdx.x, nseg, node_base, sh_state);
+}
+
+/* one candidate per thread (index c the same for all lanes of a warp up to + lane) */
+__device__ __forceinline__ void rbs_push_one(const ckc_rbs_dev& r, int c, int ncand, const uint8_t* __restrict__ hit) {
     bool push = false;
     int s = 0, node = 0;
     if (c < ncand) {
@@ -1075,18 +1102,110 @@ k_rbs_push(const ckc_rbs_dev r, const int32_t* __restrict__ d_ncand, const uint8
     }
 }
 
-__global__ void k_rbs_init(const ckc_rbs_dev r, int n_edges) {
+__global__ void __launch_bounds__(256)
+k_rbs_push(const ckc_rbs_dev r, const int32_t* __restrict__ d_ncand, const uint8_t* __restrict__ hit) {
+    rbs_push_one(r, blockIdx.x * blockDim.x + threadIdx.x, *d_ncand, hit);
+}
+
+/* ---- the thin tail of the frontier in ONE launch --------------------------------------------------------------------
+ * The deep levels of a bisection hold few segments (a planner's single edge: 1, 2, 4 ... 32; the 1e5-edge sweep: ~60 of its ~70 levels
+ * below a few thousand), and a host-driven level costs a stream synchronisation, an 8-byte read-back and five launches.  Once the
+ * frontier is small the host hands it to this cooperative kernel (one block per SM): expand -> grid sync -> collide (warp per
+ * midpoint) -> heavy configurations (block per configuration) -> push -> swap, level after level, until the frontier is empty, grows
+ * beyond `max_seg` again or a buffer would overflow (the host then grows it and continues).  Same routines as the per-level kernels. */
+struct rbs_tail_state {
+    int32_t nseg, nnodes, cur, levels;       /* in / out */
+    int32_t status;                          /* out: 0 = frontier empty, 1 = frontier above max_seg, 2 = capacity, 3 = level cap */
+    int32_t total_cand;                      /* out: isValidRBS evaluations made */
+    int32_t max_seg, seg_cap, cand_cap, node_cap, max_levels;
+};
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+__global__ void __launch_bounds__(CKC_COLLIDE_WARPS * 32, 1)
+k_rbs_tail(const ckc_kin_dev kin, const ckc_world_dev w, ckc_rbs_dev r0, ckc_rbs_dev r1, collide_args ca, rbs_tail_state* st, uint8_t* hit) {
+    __shared__ collide_smem sm;
+    cg::grid_group grid = cg::this_grid();
+    collide_smem_init(w, sm);
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const int gwarp0 = (gtid >> 5) << 5;            /* first thread index of this warp */
+    for (;;) {
+        const int nseg = st->nseg, nnodes = st->nnodes, cur = st->cur, levels = st->levels;
+        int status = -1;
+        if (nseg == 0) status = 0;
+        else if (nseg > st->max_seg) status = 1;
+        else if (2 * nseg > st->seg_cap || nseg > st->cand_cap || nnodes + nseg > st->node_cap) status = 2;
+        else if (levels >= st->max_levels) status = 3;
+        if (status >= 0) { if (gtid == 0) st->status = status; break; }
+        const ckc_rbs_dev& r = cur ? r1 : r0;
+        /* ---- expand: one segment per thread ---- */
+        for (int base = gwarp0; base < nseg; base += gthreads) rbs_expand_one<0>(kin, r, base + (threadIdx.x & 31), nseg, nnodes, nullptr);
+        grid.sync();
+        const int ncand = *r.cand_count;
+        /* ---- collide the surviving midpoints (list = candidate node ids, flags indexed by node) ---- */
+        collide_args a = ca;
+        a.list = r.cand_node; a.d_m = r.cand_count; a.m_max = ncand; a.hit_out = hit; a.valid_out = nullptr;
+        collide_block<false>(w, a, sm);
+        grid.sync();
+        if (*a.ovf_count > 0) {                     /* warp-uniform across the grid: every block sees the same count */
+            collide_args b = a; b.work_counter = a.work_counter + 1;
+            collide_heavy_block(w, b, sm);
+            __syncthreads();
+            collide_smem_init(w, sm);               /* the heavy routine used warp 0's tables and the stacks: restore the static poses */
+        }
+        grid.sync();
+        /* ---- push the children of the valid midpoints ---- */
+        for (int base = gwarp0; base < ncand; base += gthreads) rbs_push_one(r, base + (threadIdx.x & 31), ncand, hit);
+        grid.sync();
+        if (gtid == 0) {
+            st->nnodes = nnodes + ncand; st->nseg = *r.next_count; st->cur = cur ^ 1; st->levels = levels + 1; st->total_cand += ncand;
+            *r.cand_count = 0; *r.next_count = 0;
+            a.work_counter[0] = 0; a.work_counter[1] = 0; *a.ovf_count = 0;
+        }
+        grid.sync();
+    }
+}
+
+/* in: the end points as uploaded, [qa (n_edges x 12) | qb (n_edges x 12)] (two contiguous H2D copies); nodes 2e / 2e + 1 of the pool */
+__global__ void k_rbs_init(const ckc_rbs_dev r, int n_edges, const double* __restrict__ in) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
+#pragma unroll
+    for (int j = 0; j < 12; j++) { r.nodes[24 * (int64_t)e + j] = in[12 * (int64_t)e + j]; r.nodes[24 * (int64_t)e + 12 + j] = in[12 * ((int64_t)n_edges + e) + j]; }
     r.seg_a[e] = 2 * e; r.seg_b[e] = 2 * e + 1; r.seg_edge[e] = e; r.seg_depth[e] = 0;
     r.edge_ok[e] = 1;
     if (r.nchecks) r.nchecks[e] = 0;
     if (r.node_t) { r.node_t[2 * e] = 0.0; r.node_t[2 * e + 1] = 1.0; }
 }
 
-void ckc_launch_rbs_init(const ckc_rbs_dev& r, int n_edges, cudaStream_t st) {
+/* cooperative launch of the thin-tail kernel: one block per SM (all resident); dstate = device copy of rbs_tail_state */
+int ckc_launch_rbs_tail(const ckc_kin_dev& kin, const ckc_world_dev& w, const ckc_launch_cfg& cfg, const ckc_rbs_dev& r0, const ckc_rbs_dev& r1,
+                        int32_t* work_counter, int32_t* ovf_list, int32_t* ovf_count, uint32_t* big_stack, ckc_counters_dev* ctr, void* dstate, uint8_t* hit,
+                        cudaStream_t st) {
+    collide_args a;
+    memset(&a, 0, sizeof(a));
+    a.work_counter = work_counter; a.ovf_list = ovf_list; a.ovf_count = ovf_count; a.big_stack = big_stack; a.ctr = ctr;
+    a.q = r0.nodes; a.lq.stride_i = 12; a.lq.stride_j = 1;
+    a.wide_cnt = 8; a.deep_gap = 0.0f; a.deep4 = 1; a.flush_n = 6; a.likely_gap = 2.0125f; a.count_rounds = 0;
+    a.defer_rounds = 64; a.defer_tri = 24; a.dbg_rounds = nullptr; a.pair_flags = nullptr;
+    static const int blocks_per_sm = [] {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_rbs_tail, CKC_COLLIDE_WARPS * 32, 0) != cudaSuccess) b = 0;
+        return b;
+    }();
+    if (blocks_per_sm < 1) return -1;
+    int blocks = cfg.num_sms;
+    if (blocks > CKC_HEAVY_MAX_BLOCKS) blocks = CKC_HEAVY_MAX_BLOCKS;
+    ckc_kin_dev kin_c = kin; ckc_world_dev w_c = w; ckc_rbs_dev r0_c = r0, r1_c = r1;
+    rbs_tail_state* ds = (rbs_tail_state*)dstate;
+    void* args[] = { &kin_c, &w_c, &r0_c, &r1_c, &a, &ds, &hit };
+    return cudaLaunchCooperativeKernel((const void*)k_rbs_tail, dim3(blocks), dim3(CKC_COLLIDE_WARPS * 32), args, 0, st) == cudaSuccess ? 0 : -1;
+}
+
+void ckc_launch_rbs_init(const ckc_rbs_dev& r, int n_edges, const double* in, cudaStream_t st) {
     if (n_edges <= 0) return;
-    k_rbs_init<<<(n_edges + 255) / 256, 256, 0, st>>>(r, n_edges);
+    k_rbs_init<<<(n_edges + 255) / 256, 256, 0, st>>>(r, n_edges, in);
 }
 void ckc_launch_rbs_expand(const ckc_kin_dev& kin, const ckc_rbs_dev& r, int flavour, int nseg, int node_base, cudaStream_t st) {
     if (nseg <= 0) return;

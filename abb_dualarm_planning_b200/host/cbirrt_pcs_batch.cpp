@@ -340,6 +340,9 @@ struct Ensemble {
 int main(int argc, char** argv) {
     if (argc < 6) { fprintf(stderr, "usage: %s <env> <n_queries> <max_step> <seed> <out.txt> [workers] [pcs|gd] [max_rounds]\n", argv[0]); return 2; }
     const int env = atoi(argv[1]), nq = atoi(argv[2]); const double max_step = atof(argv[3]); const uint64_t seed = strtoull(argv[4], nullptr, 10);
+    /* workers = 0: SEQUENTIAL mode -- the queries run one after another, each alone on the device (single-query latency, what the
+     * reference's 500-repetition benchmark measures); the summary then also carries latency_mean / median / max */
+    const bool sequential = argc > 6 && atoi(argv[6]) == 0;
     const int workers = std::max(1, std::min(argc > 6 ? atoi(argv[6]) : 1, std::max(nq, 1)));
     const bool gd = argc > 7 && strcmp(argv[7], "gd") == 0;
     const int max_rounds = argc > 8 ? atoi(argv[8]) : 20000;
@@ -375,8 +378,21 @@ int main(int argc, char** argv) {
         if (gd) { ckc_gd_validate(E[w].ctx, 1, wq, o, &k1); ckc_gd_check_motion_rbs(E[w].ctx, 1, start, start, &k1, &nc); }
         else { b = b < 0 ? 0 : b; ckc_pcs_validate(E[w].ctx, 1, wq, &a, &b, o, &k1, &k2); ckc_pcs_check_motion_rbs(E[w].ctx, 1, start, start, &a, &b, &k1, &nc); }
     }
+    std::vector<double> lat;
     const auto t0 = std::chrono::steady_clock::now();
-    if (workers == 1) E[0].run(max_rounds);
+    if (sequential) {
+        std::vector<Query> all_q; all_q.swap(E[0].qs);
+        std::vector<Query> done;
+        for (auto& Q : all_q) {
+            E[0].qs.clear(); E[0].qs.push_back(std::move(Q));
+            const auto q0 = std::chrono::steady_clock::now();
+            E[0].run(max_rounds);
+            lat.push_back(1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - q0).count());
+            done.push_back(std::move(E[0].qs[0]));
+        }
+        E[0].qs.swap(done);
+    }
+    else if (workers == 1) E[0].run(max_rounds);
     else {
         std::vector<std::thread> th;
         for (int w = 0; w < workers; w++) th.emplace_back([&E, w, max_rounds]() { E[w].run(max_rounds); });
@@ -419,9 +435,15 @@ int main(int argc, char** argv) {
         calls += n; items += it;
         printf("  %-8s %6ld calls %8ld items  %.3f s summed over workers (%.1f us per call)\n", kn[k], n, it, t, n ? 1e6 * t / n : 0.0);
     }
-    fprintf(fp, "summary queries %d solved %d seconds %.6f ms_per_query %.4f workers %d gpu_calls %ld items %ld mean_rounds %.1f mean_path_nodes %.1f mean_tree_nodes %.1f max_step %.3f env %d flavour %s\n",
-            nq, solved, secs, 1e3 * secs / std::max(nq, 1), workers, calls, items, solved ? (double)rounds / solved : 0.0, solved ? (double)path_nodes / solved : 0.0,
-            (double)nodes_trees / std::max(nq, 1), max_step, env, gd ? "gd" : "pcs");
+    double lmean = 0, lmed = 0, lmax = 0;
+    if (!lat.empty()) {
+        std::vector<double> sl(lat); std::sort(sl.begin(), sl.end());
+        for (double v : sl) lmean += v;
+        lmean /= sl.size(); lmed = sl[sl.size() / 2]; lmax = sl.back();
+    }
+    fprintf(fp, "summary queries %d solved %d seconds %.6f ms_per_query %.4f workers %d gpu_calls %ld items %ld mean_rounds %.1f mean_path_nodes %.1f mean_tree_nodes %.1f max_step %.3f env %d flavour %s sequential %d latency_mean_ms %.4f latency_median_ms %.4f latency_max_ms %.4f\n",
+            nq, solved, secs, 1e3 * secs / std::max(nq, 1), sequential ? 0 : workers, calls, items, solved ? (double)rounds / solved : 0.0, solved ? (double)path_nodes / solved : 0.0,
+            (double)nodes_trees / std::max(nq, 1), max_step, env, gd ? "gd" : "pcs", sequential ? 1 : 0, lmean, lmed, lmax);
     fclose(fp);
     printf("queries %d solved %d in %.3f s (%.3f ms per query), %d workers, %ld batched calls, %.1f items per call\n", nq, solved, secs, 1e3 * secs / std::max(nq, 1),
            workers, calls, calls ? (double)items / calls : 0.0);

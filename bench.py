@@ -130,9 +130,13 @@ def make_rbs_edges(ck, sampling, n_edges, seed):
     return np.concatenate(qa)[:n_edges], np.concatenate(qb)[:n_edges], np.concatenate(iks)[:n_edges]
 
 
-def bind_to_gpu_numa_node(local_rank):
-    """pin this rank (and therefore the first touch of its pinned host buffers) to the CPUs of the GPU's NUMA node: the host
-    side of the e2e path is PCIe / host-memory bound and the ranks otherwise share one node's memory controllers"""
+def bind_to_gpu_numa_node(local_rank, world):
+    """Pin this rank (and therefore the first touch of its pinned host buffers and its copy threads) to host cores of its own:
+    the CPUs of the GPU's NUMA node when the box has several nodes, else an equal slice of the allowed cores per rank (on a
+    single-node box all ranks share one memory system; distinct cores at least keep the ranks' host threads from migrating onto
+    each other).  Returns a dict that goes into config (what was done and why)."""
+    info = {"numa_node": None, "cpus": None, "how": None}
+    allowed = sorted(os.sched_getaffinity(0))
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -143,19 +147,63 @@ def bind_to_gpu_numa_node(local_rank):
         if len(bus.split(":")[0]) == 8:
             bus = bus[4:]
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        allowed = os.sched_getaffinity(0) & cpus
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-            return node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node >= 0 and len(nodes) > 1:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            mine = sorted(set(allowed) & cpus)
+            if mine:
+                os.sched_setaffinity(0, mine)
+                info.update(numa_node=node, cpus="%d-%d (%d)" % (mine[0], mine[-1], len(mine)), how="cpus of the GPU's NUMA node")
+                return info
+        info["numa_node"] = node
+        info["how"] = "single NUMA node (node %d of %d)" % (node, len(nodes))
+    except Exception as e:                      # no pynvml / sysfs entry: say so instead of hiding it
+        info["how"] = "numa lookup failed: %r" % (e,)
+    if world > 1 and len(allowed) >= 2 * world:
+        per = len(allowed) // world
+        mine = allowed[local_rank * per:(local_rank + 1) * per]
+        try:
+            os.sched_setaffinity(0, mine)
+            info["cpus"] = "%d-%d (%d)" % (mine[0], mine[-1], len(mine))
+            info["how"] = (info["how"] or "") + "; equal slice of the allowed cores per rank"
+        except Exception as e:
+            info["how"] = (info["how"] or "") + "; sched_setaffinity failed: %r" % (e,)
+    return info
+
+
+# flop of one conservative box test (csrc/ckc_device.cuh boxes_farther_than: two box_to_world 2 x 57, centre difference 3, t 15, R 45,
+# |R| 9, three + three face axes 24 + 39, nine edge-cross axes 135) and of one exact triangle-pair distance
+FLOP_BOX_TEST = 384.0
+FLOP_TRI_TEST = 1000.0
+MIN_TIMED_S = 0.5          # the timed region repeats the K steps until it is at least this long
+
+
+def collide_roofline(stats, kms, kl, peak32, peak64, stage_share, extra=None):
+    """k_collide: instruction-issue / latency bound FP32 + integer code (ncu: profiles/r2_ncu_collide.txt), not an FP64 kernel.  achieved =
+    the work the kernel EXECUTED by its own counters (box tests x 384 flop + exact triangle tests x 1000 flop) / its CUDA-event time,
+    against the measured FP32 FMA-chain peak.  (The reference-work model of SURVEY 8d -- PQP's 116 full queries per configuration --
+    is not used for a fraction: the kernel prunes most of that work away.)"""
+    dur = kms / max(kl, 1) * 1e-3
+    flop = (FLOP_BOX_TEST * stats["bv_tests"] + FLOP_TRI_TEST * stats["tri_tests"]) / max(kl, 1)
+    ach = flop / dur / 1e12 if dur > 0 else 0.0
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(REPO, "profiles", "r2_traffic.json")))["k_collide"]
     except Exception:
         pass
-    return None
+    r = {"bound": "issue/fp32", "kernel": "k_collide", "achieved": ach, "peak": peak32, "unit": "TFLOP/s", "frac": ach / peak32 if peak32 else None,
+         "traffic": ncu.get("traffic"), "traffic_source": ncu.get("note"),
+         "issue_active_pct_ncu": ncu.get("issue_active_pct"), "lanes_active_ncu": ncu.get("lanes_per_instruction"),
+         "peak_source": "FP32 FMA-chain peak measured live by ckc_measure_fma_peak (FP64: %.1f TFLOP/s); MEASURED_PEAKS.json carries HBM / bf16 only" % peak64,
+         "work_model": "executed work by the kernel's own counters: %.0f flop per box test, %.0f per exact triangle test" % (FLOP_BOX_TEST, FLOP_TRI_TEST),
+         "kernel_ms_per_launch": kms / max(kl, 1), "collision_checks_per_launch": stats["collision_calls"] / max(kl, 1),
+         "stage_share_of_step": stage_share}
+    if extra:
+        r.update(extra)
+    return r
 
 
 def run_native(args):
@@ -165,7 +213,7 @@ def run_native(args):
     from abb_dualarm_planning_b200 import Checker, sampling
 
     rank, local_rank, world = dist_env()
-    numa_node = bind_to_gpu_numa_node(local_rank)
+    binding = bind_to_gpu_numa_node(local_rank, world)
     if args.gpus > 1 and world != args.gpus:
         raise SystemExit("launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world))
     torch.cuda.set_device(local_rank)
@@ -174,8 +222,6 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     ck = Checker(env=1, device=local_rank)
     stream = torch.cuda.current_stream().cuda_stream
-    wl = args.workload
-    n = args.samples or (100000 if wl == "rbs" else 1_000_000)
     K, W = args.steps, max(args.warmup, 0)
 
     def barrier():
@@ -198,9 +244,31 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    out = {}
-    if wl in ("gd", "pcs"):
-        # ---- resident inputs: NB distinct batches per rank, SoA [12][n] in HBM ----
+    def repeats_for(step_fn, timer):
+        """inner repeats R of the K steps so that the timed region lasts >= MIN_TIMED_S (same R on every rank)"""
+        t = timer(lambda: [step_fn(k % NB) for k in range(min(K, 4))]) / min(K, 4)          # seconds per step, untimed estimate
+        t = max_over_ranks(t)
+        return max(1, int(np.ceil(MIN_TIMED_S / max(K * t, 1e-9))))
+
+    def ev_timer(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3
+
+    def wall_timer(fn):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    peaks = {}
+
+    def peak(p):
+        if p not in peaks:
+            peaks[p] = ck.fma_peak(p)
+        return peaks[p]
+
+    def measure_projection(wl, n):
+        """S-GD / S-PCS: value (inputs resident in HBM), e2e (host-buffer C-ABI call), roofline of the dominant kernel"""
+        out = {}
         seeds = [1000 * (rank + 1) + b for b in range(NB)]
         host_q, host_ik, d_q, d_ik = [], [], [], []
         for s in seeds:
@@ -210,7 +278,7 @@ def run_native(args):
                 q, ik = sampling.sample_pcs(s, 0, n)
             hq = torch.from_numpy(q).pin_memory()
             host_q.append(hq)
-            d_q.append(hq.to(dev, non_blocking=True).t().contiguous())          # SoA
+            d_q.append(hq.to(dev, non_blocking=True).t().contiguous())          # SoA [12][n]
             if ik is not None:
                 hik = torch.from_numpy(ik).pin_memory(); host_ik.append(hik); d_ik.append(hik.to(dev))
         d_qout = torch.empty((12, n), dtype=torch.float64, device=dev)
@@ -227,24 +295,25 @@ def run_native(args):
         for w in range(W):
             step_dev(w % NB)
         barrier()
+        R = repeats_for(step_dev, ev_timer)
+        barrier()
         ck.reset_stats()
         sampler = ClockSampler(local_rank); sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for k in range(K):
-            step_dev(k % NB)
+        for r in range(R):
+            for k in range(K):
+                step_dev(k % NB)
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        clocks = sampler.stop()
+        out["clocks"] = sampler.stop()
         stats = ck.stats()
-        ck.set_stage_timing(False)
-        # per-kernel durations for the roofline: the same K steps once more with the chunk overlap switched off, so that every
-        # kernel runs alone on the stream and its CUDA-event bracket measures that kernel only (in the timed region above the
-        # collision kernel of one chunk overlaps the projection kernel of the next)
-        ck.set_overlap(False)
-        ck.set_stage_timing(True)
+        steps_run = K * R
+        # per-kernel durations for the roofline: K steps once more with the chunk overlap switched off, so that every kernel runs
+        # alone on the stream and its CUDA-event bracket measures that kernel only
+        ck.set_overlap(False); ck.set_stage_timing(True)
         es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         es0.record()
         for k in range(K):
@@ -253,18 +322,15 @@ def run_native(args):
         torch.cuda.synchronize()
         ms_serial = es0.elapsed_time(es1)
         stages = ck.stage_times()
-        ck.set_stage_timing(False)
-        ck.set_overlap(True)
+        ck.set_stage_timing(False); ck.set_overlap(True)
         n_valid_last = int(d_valid.sum().item())
-        total_units = world * K * n
-        out["value"] = total_units / (ms * 1e-3)
-        out["ms_per_step"] = ms / K
+        out["value"] = world * steps_run * n / (ms * 1e-3)
+        out["ms_per_step"] = ms / steps_run
+        out["timed_region_s"] = ms * 1e-3
+        out["inner_repeats"] = R
         out["gpu_launches"] = int(sum_over_ranks(stats["kernel_launches"]))
-        out["clocks"] = clocks
 
         # ---- e2e: host-buffer C-ABI call, pinned host memory, H2D + compute + D2H inside the timed region ----
-        # headline e2e = the compact-result call (mask + index / projected configuration of the valid samples: what a planner
-        # keeps); "full_output" = the call that also returns every projected configuration (97 B/sample back over PCIe)
         import ctypes as C
         h_qout = torch.empty((n, 12), dtype=torch.float64).pin_memory()
         h_valid = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -291,131 +357,164 @@ def run_native(args):
             for w in range(min(W, 2) or 1):
                 fn(w % NB)
             barrier()
+            Re = repeats_for(fn, wall_timer)
+            barrier()
             t0 = time.perf_counter()
-            for k in range(K):
-                fn(k % NB)
+            for r in range(Re):
+                for k in range(K):
+                    fn(k % NB)
             torch.cuda.synchronize()
-            e2e[name] = max_over_ranks(time.perf_counter() - t0)
-        n_valid_host = int(nv.value)
+            e2e[name] = max_over_ranks(time.perf_counter() - t0) / Re
         h2d = n * 96 + (n if wl == "pcs" else 0)
         out["e2e"] = {"value": world * K * n / e2e["compact"], "unit": "configs/s", "h2d_bytes_per_step": h2d,
                       "d2h_bytes_per_step": n + 8 + d2h_compact_bytes(n),
                       "api": "ckc_%s_validate_compact (mask + index and projected configuration of the valid samples), pinned host buffers" % wl,
-                      "valid_last_step": n_valid_host, "checksum_valid_last_step": int(h_valid.sum().item()),
+                      "valid_last_step": int(nv.value), "checksum_valid_last_step": int(h_valid.sum().item()),
                       "full_output": {"value": world * K * n / e2e["full"], "d2h_bytes_per_step": n * 96 + n + (n if wl == "pcs" else 0),
                                       "api": "ckc_%s_validate (every projected configuration returned)" % wl}}
 
         # ---- roofline of the dominant kernel (rank 0's own numbers) ----
-        peak64 = ck.fma_peak(64); peak32 = ck.fma_peak(32)
-        wm = json.load(open(os.path.join(REPO, "tests", "golden", "work_model.json")))
-        per_step = K * n
+        per_step = steps_run * n
+        share = {k: round(v["ms"] / max(ms_serial, 1e-9), 4) for k, v in stages.items()}
+        timing_note = ("kernel durations from a second pass of the same K steps with ckc_set_overlap(0) (every kernel alone on the stream, %.3f ms/step); "
+                       "the timed region overlaps chunks (%.3f ms/step)" % (ms_serial / K, ms / steps_run))
+        serial_stats = ck.stats()            # counters since the reset: timed region + the serial pass (K more steps)
         if wl == "gd":
             iters = stats["gd_iterations"] / per_step
-            flop_unit = iters * 2600.0                                     # 2600 flop per Newton iteration
-            kern, kms, kl = "k_gd_project", stages["project"]["ms"], stages["project"]["launches"]
-            flop_launch = flop_unit * n
+            flop_launch = iters * 2600.0 * n                               # 2600 flop per Newton iteration
+            kms, kl = stages["project"]["ms"], stages["project"]["launches"]
+            dur = kms / max(kl, 1) * 1e-3
+            achieved = flop_launch / dur / 1e12 if dur > 0 else 0.0
+            traffic, traffic_src, ncu = None, None, {}
+            try:
+                ncu = json.load(open(os.path.join(REPO, "profiles", "r2_traffic.json")))["k_gd_project"]
+                traffic, traffic_src = ncu["traffic"], ncu["note"]
+            except Exception:
+                pass
+            p64 = peak(64)
+            out["roofline"] = {"bound": "fp64", "kernel": "k_gd_project", "achieved": achieved, "peak": p64, "unit": "TFLOP/s",
+                               "frac": achieved / p64 if p64 else None, "traffic": traffic, "traffic_source": traffic_src,
+                               "fp64_pipe_active_pct_ncu": ncu.get("fp64_pipe_active_pct"),
+                               "peak_source": "FP64 FMA-chain peak measured live by ckc_measure_fma_peak (MEASURED_PEAKS.json has HBM/bf16 only; FP32 FMA peak %.1f TFLOP/s)" % peak(32),
+                               "work_model": "algorithmic flop of the reference path (SURVEY 8d): 2600 flop x measured Newton iterations (%.3f per sample)" % iters,
+                               "kernel_ms_per_launch": kms / max(kl, 1), "stage_share_of_step": share, "timing_note": timing_note,
+                               "hbm_gbs_algorithmic": (per_step * 200.0) / (ms * 1e-3) / 1e9, "hbm_peak_gbs_measured": measured_hbm_peak()}
         else:
-            kern, kms, kl = "k_collide", stages["collide"]["ms"], stages["collide"]["launches"]
-            cfgs = stats["collision_calls"] / max(kl, 1)
-            flop_cfg = 300.0 * (116 + wm["n_bv_mean"]) + 1000.0 * wm["n_tri_mean"]      # reference-work model, PQP counters frozen in tests/golden
-            flop_launch = flop_cfg * cfgs
-        dur = kms / max(kl, 1) * 1e-3
-        achieved = flop_launch / dur / 1e12 if dur > 0 else 0.0
-        # the same kernel by the work it actually executed (own counters): K3 prunes far harder than PQP's 116 full queries, so the
-        # contract figure above (PQP's work per configuration) can exceed the peak; this one cannot
-        executed = None
-        if wl != "gd" and dur > 0:
-            executed = (300.0 * stats["bv_tests"] + 1000.0 * stats["tri_tests"]) / max(kl, 1) / dur / 1e12
-        traffic, traffic_src = None, None
-        try:        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture
-            tr = json.load(open(os.path.join(REPO, "profiles", "r1_traffic.json")))[kern]
-            traffic = tr["traffic"]         # bytes per launch
-            traffic_src = "dram bytes per launch from profiles/" + tr["capture"].replace(".ncu-rep", "") + " (ncu --set full); " + tr["note"]
-        except Exception:
-            pass
-        share = {k: round(v["ms"] / max(ms_serial, 1e-9), 4) for k, v in stages.items()}
-        out["roofline"] = {"bound": "fp64", "kernel": kern, "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
-                           "frac": achieved / peak64 if peak64 else None, "traffic": traffic, "traffic_source": traffic_src,
-                           "achieved_executed_work": executed, "frac_executed_work": (executed / peak64 if executed is not None and peak64 else None),
-                           "peak_source": "FP64 FMA-chain peak measured live by ckc_measure_fma_peak (MEASURED_PEAKS.json has HBM/bf16 only; FP32 FMA peak %.1f TFLOP/s)" % peak32,
-                           "work_model": "algorithmic flop of the reference path (SURVEY 8d): GD 2600 flop x measured Newton iterations; collision 300 flop x (116 + n_bv) + 1000 flop x n_tri with PQP counters of tests/golden/work_model.json",
-                           "kernel_ms_per_launch": kms / max(kl, 1), "stage_share_of_step": share,
-                           "timing_note": "kernel durations from a second pass of the same K steps with ckc_set_overlap(0) (every kernel alone on the stream, %.3f ms/step); the timed region overlaps chunks (%.3f ms/step)" % (ms_serial / K, ms / K),
-                           "hbm_gbs_algorithmic": (per_step * 200.0) / (ms * 1e-3) / 1e9, "hbm_peak_gbs_measured": measured_hbm_peak()}
+            # the serial pass alone: counters of the whole region scaled to the K serial steps
+            sc = {k: serial_stats[k] * K / (steps_run + K) for k in ("bv_tests", "tri_tests", "collision_calls")}
+            out["roofline"] = collide_roofline(sc, stages["collide"]["ms"], stages["collide"]["launches"], peak(32), peak(64), share,
+                                               {"timing_note": timing_note, "hbm_gbs_algorithmic": (per_step * 200.0) / (ms * 1e-3) / 1e9,
+                                                "hbm_peak_gbs_measured": measured_hbm_peak()})
         out["path_stats"] = {"newton_iters_mean": stats["gd_iterations"] / per_step if wl == "gd" else None,
                              "fraction_passing_projection": stats["ik_feasible"] / per_step,
-                             "collision_checks_per_step": stats["collision_calls"] / K, "bv_tests_per_check": stats["bv_tests"] / max(stats["collision_calls"], 1),
+                             "collision_checks_per_step": stats["collision_calls"] / steps_run, "bv_tests_per_check": stats["bv_tests"] / max(stats["collision_calls"], 1),
                              "tri_tests_per_check": stats["tri_tests"] / max(stats["collision_calls"], 1), "valid_last_step": n_valid_last,
-                             "stack_overflow_configs": stats["queue_overflows"]}
-    else:
-        # ---- RBS: n edges per step per rank ----
+                             "configs_sent_to_heavy_kernel": stats["queue_overflows"]}
+        del d_q, d_ik, d_qout, host_q, host_ik
+        return out
+
+    def measure_rbs(n):
+        out = {}
         qa, qb, iks = make_rbs_edges(ck, sampling, n, 7000 + rank)
+        # pinned host buffers for the edge set and the results (the contract's e2e: inputs from pinned host memory every step)
+        h_qa = torch.from_numpy(np.ascontiguousarray(qa)).pin_memory(); h_qb = torch.from_numpy(np.ascontiguousarray(qb)).pin_memory()
+        h_ik = torch.from_numpy(np.ascontiguousarray(iks)).pin_memory()
+        h_ok = torch.empty(n, dtype=torch.uint8).pin_memory(); h_nc = torch.empty(n, dtype=torch.int32).pin_memory()
+
+        def rbs_call():
+            ck._chk(ck.L.ckc_pcs_check_motion_rbs(ck.ctx, n, h_qa.data_ptr(), h_qb.data_ptr(), None, h_ik.data_ptr(), h_ok.data_ptr(), h_nc.data_ptr()))
         for w in range(max(W, 1)):
-            ck.pcs_check_motion_rbs(qa, qb, 0, iks)
+            rbs_call()
         barrier()
+        t1 = max_over_ranks(wall_timer(rbs_call))
+        R = max(1, int(np.ceil(MIN_TIMED_S / max(K * t1, 1e-9))))
         ck.reset_stats(); ck.set_stage_timing(True)
         sampler = ClockSampler(local_rank); sampler.start()
         barrier()
         t0 = time.perf_counter()
         okc = 0
-        for k in range(K):
-            ok, nc = ck.pcs_check_motion_rbs(qa, qb, 0, iks)
-            okc = int(ok.sum())
+        for r in range(R):
+            for k in range(K):
+                rbs_call()
+        okc = int(h_ok.sum().item())
         torch.cuda.synchronize()
         t = max_over_ranks(time.perf_counter() - t0)
         out["clocks"] = sampler.stop()
         stats = ck.stats(); stages = ck.stage_times(); ck.set_stage_timing(False)
-        out["value"] = world * K * n / t
-        out["ms_per_step"] = 1e3 * t / K
+        steps_run = K * R
+        out["value"] = world * steps_run * n / t
+        out["ms_per_step"] = 1e3 * t / steps_run
+        out["timed_region_s"] = t
+        out["inner_repeats"] = R
         out["gpu_launches"] = int(sum_over_ranks(stats["kernel_launches"]))
         out["e2e"] = {"value": out["value"], "unit": "edges/s", "h2d_bytes_per_step": n * 194, "d2h_bytes_per_step": n * 5,
-                      "note": "the RBS entry point only exists in host-buffer form (frontier driven from the host); value == e2e"}
-        peak64 = ck.fma_peak(64)
-        wm = json.load(open(os.path.join(REPO, "tests", "golden", "work_model.json")))
-        cfgs = stats["collision_calls"]
-        flop = cfgs * (300.0 * (116 + wm["n_bv_mean"]) + 1000.0 * wm["n_tri_mean"])
-        dur = stages["collide"]["ms"] * 1e-3
-        out["roofline"] = {"bound": "fp64", "kernel": "k_collide", "achieved": flop / dur / 1e12 if dur else 0.0, "peak": peak64, "unit": "TFLOP/s",
-                           "frac": (flop / dur / 1e12) / peak64 if dur and peak64 else None, "traffic": None,
-                           "achieved_executed_work": ((300.0 * stats["bv_tests"] + 1000.0 * stats["tri_tests"]) / dur / 1e12) if dur else None,
-                           "frac_executed_work": ((300.0 * stats["bv_tests"] + 1000.0 * stats["tri_tests"]) / dur / 1e12 / peak64) if dur and peak64 else None,
-                           "work_model": "contract figure: PQP's work per configuration (300 flop x (116 + n_bv) + 1000 flop x n_tri, counters of tests/golden/work_model.json) -- it can exceed the peak because k_collide prunes far harder than PQP's 116 full queries; *_executed_work uses the kernel's own test counters",
-                           "stage_share_of_step": {k: round(v["ms"] / (1e3 * t), 4) for k, v in stages.items()}}
-        out["path_stats"] = {"edges_ok_fraction": okc / n, "checks_per_edge": stats["collision_calls"] / (K * n)}
+                      "note": "the RBS entry point only exists in host-buffer form (pinned host buffers in, flags + check counts out; the frontier lives on the device); value == e2e"}
+        share = {k: round(v["ms"] / (1e3 * t), 4) for k, v in stages.items()}
+        out["roofline"] = collide_roofline(stats, stages["collide"]["ms"], stages["collide"]["launches"], peak(32), peak(64), share,
+                                           {"timing_note": "one k_collide launch per bisection level (%.1f levels per call); host loop + level synchronisation = %.0f %% of the wall time"
+                                            % (stages["collide"]["launches"] / steps_run, 100.0 * (1 - sum(v["ms"] for v in stages.values()) / (1e3 * t)))})
+        out["path_stats"] = {"edges_ok_fraction": okc / n, "checks_per_edge": stats["collision_calls"] / (steps_run * n),
+                             "levels_per_call": stages["collide"]["launches"] / steps_run}
+        return out
+
+    METRIC = {"gd": "validated closed-chain configs/s (project + FK/limits + collide)", "pcs": "validated closed-chain configs/s (project + FK/limits + collide)",
+              "rbs": "RBS edges/s (checkMotionRBS, PCS)"}
+
+    def workload_text(wl, n):
+        return {"gd": "BASELINE configs[1]: S-GD, %d uniform 12-DOF samples per GPU per step, KDL-style Newton closure projection + joint limits + 116-pair mesh collision, env 1 (3 poles)" % n,
+                "pcs": "BASELINE configs[4] (PCS arm): S-PCS, %d samples per GPU per step, APC/PCS analytic IK projection + 116-pair mesh collision, env 1 (3 poles)" % n,
+                "rbs": "BASELINE configs[2]: S-RBS, %d edges per GPU per step, checkMotionRBS (PCS), RBS_tol 0.05, env 1 (3 poles)" % n}[wl]
+
+    wl = args.workload
+    n = args.samples or (100000 if wl == "rbs" else 1_000_000)
+    out = measure_rbs(n) if wl == "rbs" else measure_projection(wl, n)
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(wl, cores=1, budget_s=12.0)
 
-    # ---- secondary measurements on the other workloads (not the headline, same run, same box) ----
-    if rank == 0 and world == 1 and not args.no_extra and wl == "gd":
-        out["extra"] = extra_measurements(ck, sampling, torch, dev, stream)
+    # ---- the other two workloads as complete sub-records (same run, same box): BASELINE configs[2] and the PCS arm of configs[4] ----
+    extra = {}
+    if not args.no_extra and wl == "gd":
+        for owl in ("pcs", "rbs"):
+            on = 100000 if owl == "rbs" else 1_000_000
+            rec = measure_rbs(on) if owl == "rbs" else measure_projection(owl, on)
+            rec.update(metric=METRIC[owl], unit="edges/s" if owl == "rbs" else "configs/s", n_gpus=world, steps=K, warmup=W, higher_is_better=True, scaling="weak",
+                       dtype="f64", data="synthetic", config={"workload": workload_text(owl, on), "units_per_gpu_per_step": on, "inner_repeats": rec["inner_repeats"]})
+            if rank == 0 and world == 1 and not args.no_cpu:
+                rec["cpu_baseline"] = cpu_baseline(owl, cores=1, budget_s=6.0)
+            extra[owl] = rec
+        if rank == 0 and world == 1:
+            extra.update(extra_measurements(ck, sampling, torch, dev, stream))
 
     if rank == 0:
-        line = {"metric": "validated closed-chain configs/s (project + FK/limits + collide)" if wl != "rbs" else "RBS edges/s (checkMotionRBS, PCS)",
-                "value": out["value"], "unit": "configs/s" if wl != "rbs" else "edges/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": {"gd": "BASELINE configs[1]: S-GD, %d uniform 12-DOF samples per GPU per step, KDL-style Newton closure projection + joint limits + 116-pair mesh collision, env 1 (3 poles)" % n,
-                                        "pcs": "S-PCS, %d samples per GPU per step, APC/PCS analytic IK projection + 116-pair mesh collision, env 1 (3 poles)" % n,
-                                        "rbs": "S-RBS, %d edges per GPU per step, checkMotionRBS (PCS), RBS_tol 0.05, env 1 (3 poles)" % n}[wl],
-                           "units_per_gpu_per_step": n, "parallelism": "shard%d (independent samples, no collective)" % world, "numa_node_rank0": numa_node,
+        line = {"metric": METRIC[wl], "value": out["value"], "unit": "configs/s" if wl != "rbs" else "edges/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_text(wl, n), "units_per_gpu_per_step": n, "parallelism": "shard%d (independent samples, no collective)" % world,
+                           "host_binding_rank0": binding, "inner_repeats": out["inner_repeats"], "timed_region_s": out["timed_region_s"],
+                           "timing": "the K steps are repeated inner_repeats times inside ONE timed region (>= %.1f s); ms_per_step = region / (K x inner_repeats)" % MIN_TIMED_S,
                            "cache": "%d distinct resident input batches cycled (%.0f MB aggregate > 126 MB L2)" % (NB, NB * n * 96 / 1e6) if wl != "rbs" else "edge set re-uploaded from host every step"},
                 "e2e": out["e2e"], "gpu_launches": out["gpu_launches"], "clocks": out["clocks"], "roofline": out["roofline"],
                 "path_stats": out.get("path_stats")}
         if "cpu_baseline" in out:
             line["cpu_baseline"] = out["cpu_baseline"]
-        if "extra" in out:
-            line["extra"] = out["extra"]
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     ck.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _planner_run(exe, env, nq, step, flav, workers, td):
+    outp = os.path.join(td, "paths_%s_%d.txt" % (flav, nq))
+    subprocess.run([exe, "1", str(nq), step, "7", outp, str(workers), flav], env=env, capture_output=True, timeout=600, check=True)
+    t = open(outp).read().strip().split("\n")[-1].split()
+    return dict(zip(t[1::2], t[2::2]))
+
+
 def extra_measurements(ck, sampling, torch, dev, stream):
-    """PCS throughput (device-generated S-PCS samples) and RBS edges/s, measured after the headline run."""
-    import numpy as np
+    """S-PCS generated on the device, and BASELINE configs[3] (planning query): latency of ONE query and throughput of 500"""
     ex = {}
     n = 1 << 24
     d_ok = torch.empty(n, dtype=torch.uint8, device=dev); d_valid = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -423,40 +522,37 @@ def extra_measurements(ck, sampling, torch, dev, stream):
         ck.spcs_validate_seeded_dev(99, 0, n, None, d_ok.data_ptr(), d_valid.data_ptr(), stream)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
+    reps = 8
     e0.record()
     for r in range(reps):
         ck.spcs_validate_seeded_dev(100 + r, 0, n, None, d_ok.data_ptr(), d_valid.data_ptr(), stream)
     e1.record(); torch.cuda.synchronize()
     ex["pcs_seeded_configs_per_s"] = reps * n / (e0.elapsed_time(e1) * 1e-3)
     ex["pcs_seeded_note"] = "S-PCS samples generated on the device from the counter-based generator (no input traffic), %d samples x %d" % (n, reps)
-    ne = 100000
-    qa, qb, iks = make_rbs_edges(ck, sampling, ne, 4242)
-    ck.pcs_check_motion_rbs(qa, qb, 0, iks)                 # warm-up at full size (frontier buffers grow once)
-    t0 = time.perf_counter()
-    ok, nc = ck.pcs_check_motion_rbs(qa, qb, 0, iks)
-    t = time.perf_counter() - t0
-    ex["rbs_edges_per_s"] = ne / t
-    ex["rbs_note"] = "%d S-RBS edges, %.1f%% succeed, %.1f validity checks per edge" % (ne, 100.0 * ok.mean(), nc.mean())
-    # BASELINE configs[3]: the reference's benchmark protocol (500 repetitions of the env-1 CBiRRT-PCS query) as one lock-step ensemble
+    del d_ok, d_valid
     try:
-        import subprocess, tempfile
+        import tempfile
         exe = os.path.join(REPO, "abb_dualarm_planning_b200", "host", "cbirrt_pcs_batch")
         if os.path.exists(exe):
             with tempfile.TemporaryDirectory() as td:
-                out = os.path.join(td, "paths.txt")
                 env = dict(os.environ, CKC_MESH_PATH=os.path.join(REPO, "abb_dualarm_planning_b200", "data", "meshes.ckcmesh"),
                            CKC_DEVICE=str(torch.cuda.current_device()))
+                plan = {}
                 for flav, step, ref_ms in (("pcs", "1.0", 218), ("gd", "2.6", 128)):
-                    subprocess.run([exe, "1", "500", step, "7", out, "4", flav], env=env, capture_output=True, timeout=300, check=True)
-                    t = open(out).read().strip().split("\n")[-1].split()
-                    sm = dict(zip(t[1::2], t[2::2]))
-                    ex["cbirrt_%s_ms_per_query" % flav] = float(sm["ms_per_query"])
-                    ex["cbirrt_%s_note" % flav] = ("%s of %s env-1 start-to-goal queries solved in %.2f s by the lock-step ensemble (host/cbirrt_pcs_batch.cpp, 4 workers, "
-                                                   "max step %s, %s batched calls); the reference reports %d ms per query on its author's CPU (BASELINE.md)"
-                                                   % (sm["solved"], sm["queries"], float(sm["seconds"]), step, sm["gpu_calls"], ref_ms))
+                    one = _planner_run(exe, env, 40, step, flav, 0, td)           # workers = 0: 40 queries one after another, each alone on the device
+                    many = _planner_run(exe, env, 500, step, flav, 4, td)
+                    plan["cbirrt_" + flav] = {
+                        "latency_ms_1_query": float(one["latency_mean_ms"]), "latency_median_ms_1_query": float(one["latency_median_ms"]),
+                        "latency_max_ms_1_query": float(one["latency_max_ms"]), "queries_for_latency": int(one["queries"]), "solved_for_latency": int(one["solved"]),
+                        "gpu_calls_per_query": int(one["gpu_calls"]) / max(int(one["queries"]), 1), "planner_steps_per_query": float(one["mean_rounds"]),
+                        "throughput_ms_per_query_500": float(many["ms_per_query"]), "solved_of_500": int(many["solved"]), "seconds_500": float(many["seconds"]),
+                        "reference_published_ms_per_query": ref_ms,
+                        "note": "latency = mean wall time of one env-1 start-to-goal query run ALONE on the device (40 seeds, one after another) -- what BASELINE.md's %d ms "
+                                "measures (mean of 500 runs, there on the author's CPU); throughput = wall time of 500 concurrent queries / 500 (lock-step ensemble, "
+                                "host/cbirrt_pcs_batch.cpp, 4 workers) -- a different quantity, not comparable with the published latency" % ref_ms}
+                ex["planning"] = plan
     except Exception as e:       # an extra, never the metric
-        ex["cbirrt_pcs_note"] = "not run: %r" % (e,)
+        ex["planning"] = {"not_run": repr(e)}
     return ex
 
 
@@ -596,7 +692,8 @@ def run_reference(args):
     n = args.samples or (100000 if wl == "rbs" else 1_000_000)
     K, W = args.steps, args.warmup
     budget = max(2.0, min(12.0, 150.0 / max(K + W, 1)))          # whole run stays within a few minutes
-    for _ in range(min(W, 1)):
+    W_run = min(W, 1)             # one 1-second warm-up pass at most (page-in of the binaries / meshes); printed as such
+    for _ in range(W_run):
         cpu_baseline(wl, cores, 1.0)
     t0 = time.perf_counter()
     vals = []
@@ -609,7 +706,7 @@ def run_reference(args):
     base["value"] = value
     unit = "edges/s" if wl == "rbs" else "configs/s"
     line = {"impl": "reference", "metric": "RBS edges/s (checkMotionRBS, PCS)" if wl == "rbs" else "validated closed-chain configs/s (project + FK/limits + collide)", "value": value, "unit": unit,
-            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": args.gpus, "steps": K, "warmup": W_run, "warmup_requested": W, "ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "same generator and workload as the native arm (%s), each step a bounded sample sized for ~%.0f s on %d host cores" % (wl, budget, cores),
                        "units_per_gpu_per_step": n},
