@@ -683,7 +683,7 @@ static int run_collision_stage(ckc_ctx* ctx, ckc_lane& L, int64_t m_max, const d
                                uint8_t* d_hit, uint8_t* d_valid, uint8_t* d_pair_flags, cudaStream_t st, bool allow_hop = true) {
     if (m_max <= 0) return CKC_OK;
     CU(L.ovf.reserve((size_t)m_max * 4));
-    CU(L.bigstack.reserve((size_t)160 * 65536 * 4));      /* k_collide_heavy: one 65 536-entry stack per block (<= 160 blocks); diagnostic form: 128 warps */
+    CU(L.bigstack.reserve((size_t)320 * 32768 * 4));      /* heavy routine: one 32 768-entry stack per block (<= 320 blocks); diagnostic form: 128 warps */
     /* on the lane's own stream the collision stage moves to the lane's HIGH-PRIORITY stream: its blocks then win the SM slots
      * that free up while the persistent projection kernels of the other lanes are still queued */
     const bool hop = allow_hop && ctx->overlap && st == L.st && L.st_hi;      /* RBS levels run alone: no hop, four stream operations less per level */
@@ -697,7 +697,7 @@ static int run_collision_stage(ckc_ctx* ctx, ckc_lane& L, int64_t m_max, const d
     { stage_scope ts(ctx, st, 2);
       ckc_launch_collide(w, cfg, d_q, l, d_list, d_m, m_max, d_hit, d_valid, d_pair_flags, L.work_counter(),
                          L.ovf.as<int32_t>(), L.ovf_count(), L.bigstack.as<uint32_t>(), ctx->d_ctr.as<ckc_counters_dev>(), st); }
-    ctx->launches += 2;
+    ctx->launches += 1;
     CU(cudaGetLastError());
     if (hop) { CU(cudaEventRecord(L.ev_c, st)); CU(cudaStreamWaitEvent(lane_st, L.ev_c, 0)); }
     return CKC_OK;
@@ -1331,7 +1331,7 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
             if ((size_t)want_nodes > hit.cap) CU(hit.reserve((size_t)(want_nodes + want_nodes / 2)));
             if (rec && (size_t)want_nodes * 8 > nt.cap) CU(reserve_keep(nt, (size_t)(want_nodes + want_nodes / 2) * 8, (size_t)nnodes * 8, st));
             CU(L.ovf.reserve((size_t)(4 * tail_max) * 4));
-            CU(L.bigstack.reserve((size_t)160 * 65536 * 4));
+            CU(L.bigstack.reserve((size_t)320 * 32768 * 4));
             ckc_rbs_tail_state hs;
             hs.nseg = (int32_t)nseg; hs.nnodes = (int32_t)nnodes; hs.cur = cur; hs.levels = 0; hs.status = -1; hs.total_cand = 0;
             hs.max_seg = (int32_t)(2 * tail_max);

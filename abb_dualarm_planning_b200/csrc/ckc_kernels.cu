@@ -27,7 +27,7 @@ using namespace ckc;
 #ifndef CKC_STACK_CAP
 #define CKC_STACK_CAP 512           /* per-warp shared-memory task stack (entries); 8 warps x (2016 + 1008 + 2048 + 256) B + 3712 B = 46.3 kB per block: two blocks stay inside the 100 kB shared-memory carve-out (the L1 keeps 156 kB for the hierarchy nodes) */
 #endif
-#define CKC_BIG_STACK_CAP 65536     /* per-warp global-memory stack of the overflow path */
+#define CKC_BIG_STACK_CAP 32768     /* global-memory task stack of the heavy routine (per block) and of the diagnostic per-pair form (per warp) */
 #define CKC_TRIQ_CAP 64
 #define CKC_COLLIDE_WARPS 8
 
@@ -375,11 +375,16 @@ __device__ __forceinline__ void collide_block(const ckc_world_dev& w, const coll
 
         if (defer) {
             if (!kPerPair) {
-                if (lane == 0) { const int o = atomicAdd(a.ovf_count, 1); a.ovf_list[o] = cfg; }
+                if (lane == 0) {           /* ticket, entry, fence, then publish in ticket order: the published count never runs ahead of the entries */
+                    const int o = atomicAdd(&a.work_counter[3], 1);
+                    a.ovf_list[o] = cfg;
+                    __threadfence();
+                    while (atomicCAS(&a.work_counter[2], o, o + 1) != o) { }
+                }
                 __syncwarp();
-                continue;                                             /* decided by k_collide_heavy */
+                continue;                                             /* decided by the heavy routine at the end of some block */
             }
-            hit = true;                                               /* diagnostic form, 65 536-entry stack exhausted: report conservatively */
+            hit = true;                                               /* diagnostic form, 32 768-entry stack exhausted: report conservatively */
             if (lane == 0 && a.ctr) atomicAdd(&a.ctr->queue_overflows, 1ull << 32);
         }
         if (kPerPair) {
@@ -404,23 +409,33 @@ __device__ __forceinline__ void collide_block(const ckc_world_dev& w, const coll
     }
 }
 
+__device__ __forceinline__ void collide_heavy_block(const ckc_world_dev& w, const collide_args& a, collide_smem& sm);
+
+/* One launch: every block's warps drain the work counter; a block whose warps have all run out then works through the deferred
+ * (heavy) configurations published so far, as a block, and leaves.  Early blocks thereby do the heavy work in the shadow of the
+ * stragglers; a configuration deferred late is seen at the latest by its own block (its warps have all finished by then).
+ * Nobody waits for anybody: concurrent launches on other streams cannot dead-lock each other. */
 template <bool kPerPair>
 __global__ void __launch_bounds__(CKC_COLLIDE_WARPS * 32, CKC_COLLIDE_MINBLOCKS)
 k_collide(const ckc_world_dev w, const collide_args a) {
     __shared__ collide_smem sm;
     collide_smem_init(w, sm);
     collide_block<kPerPair>(w, a, sm);
+    if (!kPerPair) {
+        __syncthreads();
+        collide_heavy_block(w, a, sm);
+    }
 }
 
 /* ---- K3h: the heavy configurations, one BLOCK per configuration ---------------------------------------------------
  * The configurations k_collide gave up on (work above its thresholds, or a task-stack overflow) are started again from the pair
  * table by a whole block: every round pops up to 256 tasks -- one box test per THREAD --, leaf pairs collect in a 1024-entry
  * queue that is drained with one exact FP64 TriDist per thread (tri_dist_seq: same arithmetic as the cooperative routine, 256 pairs
- * per step instead of 3), the task stack lives in global memory (65 536 entries per block).  A configuration with 450 near-tolerance
+ * per step instead of 3), the task stack lives in global memory (32 768 entries per block).  A configuration with 450 near-tolerance
  * triangle pairs and 50 descent rounds costs one warp ~0.3 ms; here it is two triangle steps and ~25 rounds.  Same boolean:
  * the pruning test and the leaf test are the same functions, only the order of evaluation differs. */
 #define CKC_HEAVY_THREADS 256
-#define CKC_HEAVY_MAX_BLOCKS 160     /* size of the global stack buffer (ckc_host.cu reserves CKC_HEAVY_MAX_BLOCKS x 65 536 entries) */
+#define CKC_HEAVY_MAX_BLOCKS 320     /* size of the global stack buffer (ckc_host.cu reserves CKC_HEAVY_MAX_BLOCKS x CKC_BIG_STACK_CAP entries) */
 #define CKC_HEAVY_TRIQ 1024
 __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp_tot, int& total) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -447,15 +462,24 @@ __device__ __forceinline__ void collide_heavy_block(const ckc_world_dev& w, cons
     const int4* s_pairs = sm.pairs;
     const int tid = threadIdx.x, lane = tid & 31;
     uint32_t* stack = a.big_stack + (size_t)blockIdx.x * CKC_BIG_STACK_CAP;
-    const int m = *a.ovf_count;
     unsigned int n_bv = 0, n_tri = 0;
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_k = atomicAdd(a.work_counter, 1); s_hit = 0; }
+        if (tid == 0) {
+            /* claim the next PUBLISHED entry of the deferred list (work_counter[1] = next, [2] = published count); never wait:
+             * whatever is published later belongs to a block that is still running and will drain it itself */
+            int claimed = -1;
+            for (;;) {
+                const int nx = *(volatile int32_t*)&a.work_counter[1], cnt = *(volatile int32_t*)&a.work_counter[2];
+                if (nx >= cnt) break;
+                if (atomicCAS(&a.work_counter[1], nx, nx + 1) == nx) { claimed = nx; break; }
+            }
+            s_k = claimed; s_hit = 0;
+        }
         __syncthreads();
         const int k = s_k;
-        if (k >= m) break;
-        const int cfg = a.ovf_list[k];
+        if (k < 0) break;
+        const int cfg = *(volatile int32_t*)&a.ovf_list[k];
         const int64_t sample = a.list ? (int64_t)a.list[cfg] : (int64_t)cfg;
         if (tid < 32) {                 /* warp 0: exact frames, then the FP32 copy (rounded from FP64: inside the guard band like the FP32 chain) */
             warp_link_frames(w.static_frames_dev + 36, lane < 12 ? a.q[sample * a.lq.stride_i + lane * a.lq.stride_j] : 0.0, lane, F64);
@@ -528,7 +552,7 @@ __device__ __forceinline__ void collide_heavy_block(const ckc_world_dev& w, cons
             top += npush; ntri += nleaf;
             __syncthreads();
         }
-        if (overflow) { hit = true; if (tid == 0 && a.ctr) atomicAdd(&a.ctr->queue_overflows, 1ull << 32); }      /* 65 536 tasks: report conservatively */
+        if (overflow) { hit = true; if (tid == 0 && a.ctr) atomicAdd(&a.ctr->queue_overflows, 1ull << 32); }      /* 32 768 tasks: report conservatively */
         if (tid == 0) {
             if (a.dbg_rounds) a.dbg_rounds[sample] = 0xffffffffu;
             if (a.hit_out) a.hit_out[sample] = hit ? 1 : 0;
@@ -537,13 +561,6 @@ __device__ __forceinline__ void collide_heavy_block(const ckc_world_dev& w, cons
         }
     }
     if (tid == 0 && a.ctr) { atomicAdd(&a.ctr->bv_tests, (unsigned long long)n_bv); atomicAdd(&a.ctr->tri_tests, (unsigned long long)n_tri); }
-}
-
-__global__ void __launch_bounds__(CKC_HEAVY_THREADS, 1)
-k_collide_heavy(const ckc_world_dev w, const collide_args a) {
-    __shared__ collide_smem sm;
-    collide_smem_init(w, sm);
-    collide_heavy_block(w, a, sm);
 }
 
 /* rank sort of the (decayed) first-hit counters -> processing order for the next launches; one tiny block */
@@ -589,23 +606,18 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     static const int defer_rounds = [] { const char* e = getenv("CKC_DEFER_ROUNDS"); return e ? atoi(e) : 64; }();
     static const int defer_tri = [] { const char* e = getenv("CKC_DEFER_TRI"); return e ? atoi(e) : 24; }();
     a.defer_rounds = defer_rounds; a.defer_tri = defer_tri;
-    /* work_counter[0] main pass, [1] heavy pass; the heavy count sits right behind them in the lanes' scratch block */
-    if (ovf_count == work_counter + 2) cudaMemsetAsync(work_counter, 0, 3 * sizeof(int32_t), st);
-    else { cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st); cudaMemsetAsync(ovf_count, 0, sizeof(int32_t), st); }
+    /* work_counter[0] next configuration, [1] next deferred entry, [2] deferred entries published (= *ovf_count), [3] deferred tickets */
+    if (ovf_count != work_counter + 2) return;                  /* the lanes' scratch block lays them out like this */
+    cudaMemsetAsync(work_counter, 0, 4 * sizeof(int32_t), st);
     if (pair_flags) {           /* diagnostic form: global-memory stacks, 16 blocks (the big-stack buffer holds 128 warps) */
         k_collide<true><<<16, CKC_COLLIDE_WARPS * 32, 0, st>>>(w, a);
         return;
     }
+    /* persistent grid: exactly the resident blocks (the heavy routine's global-memory stack is indexed by the block) */
     int64_t blocks = (m_max + CKC_COLLIDE_WARPS - 1) / CKC_COLLIDE_WARPS;
-    const int64_t resident = (int64_t)cfg.num_sms * CKC_COLLIDE_MINBLOCKS * 3;
+    const int64_t resident = std::min<int64_t>((int64_t)cfg.num_sms * CKC_COLLIDE_MINBLOCKS, CKC_HEAVY_MAX_BLOCKS);
     if (blocks > resident) blocks = resident;
     k_collide<false><<<(unsigned)blocks, CKC_COLLIDE_WARPS * 32, 0, st>>>(w, a);
-    /* heavy pass: one block per SM at most (its global-memory stacks: 65 536 entries per block), exits at once when nothing was deferred */
-    collide_args b = a;
-    b.work_counter = work_counter + 1;
-    int64_t hb = std::min<int64_t>(cfg.num_sms, m_max);      /* the number of deferred configurations is only known on the device */
-    if (hb > CKC_HEAVY_MAX_BLOCKS) hb = CKC_HEAVY_MAX_BLOCKS;
-    k_collide_heavy<<<(unsigned)hb, CKC_HEAVY_THREADS, 0, st>>>(w, b);
 }
 
 /* ================================================================================================================ */
@@ -1148,9 +1160,8 @@ k_rbs_tail(const ckc_kin_dev kin, const ckc_world_dev w, ckc_rbs_dev r0, ckc_rbs
         a.list = r.cand_node; a.d_m = r.cand_count; a.m_max = ncand; a.hit_out = hit; a.valid_out = nullptr;
         collide_block<false>(w, a, sm);
         grid.sync();
-        if (*a.ovf_count > 0) {                     /* warp-uniform across the grid: every block sees the same count */
-            collide_args b = a; b.work_counter = a.work_counter + 1;
-            collide_heavy_block(w, b, sm);
+        if (*(volatile int32_t*)&a.work_counter[2] > 0) {      /* uniform across the grid: every block sees the same published count */
+            collide_heavy_block(w, a, sm);
             __syncthreads();
             collide_smem_init(w, sm);               /* the heavy routine used warp 0's tables and the stacks: restore the static poses */
         }
@@ -1161,7 +1172,7 @@ k_rbs_tail(const ckc_kin_dev kin, const ckc_world_dev w, ckc_rbs_dev r0, ckc_rbs
         if (gtid == 0) {
             st->nnodes = nnodes + ncand; st->nseg = *r.next_count; st->cur = cur ^ 1; st->levels = levels + 1; st->total_cand += ncand;
             *r.cand_count = 0; *r.next_count = 0;
-            a.work_counter[0] = 0; a.work_counter[1] = 0; *a.ovf_count = 0;
+            a.work_counter[0] = 0; a.work_counter[1] = 0; a.work_counter[2] = 0; a.work_counter[3] = 0;
         }
         grid.sync();
     }

@@ -341,7 +341,7 @@ def test_stats_counters(ck, oracle):
     ok, valid, _ = ck.pcs_validate(q, 0, ik)
     s = ck.stats()
     assert s["ik_calls"] == 5000 and s["ik_feasible"] == int(ok.sum()) and s["collision_calls"] == int(ok.sum())
-    assert s["collisions"] == int(ok.sum() - valid.sum()) and s["bv_tests"] > 0 and s["kernel_launches"] >= 3
+    assert s["collisions"] == int(ok.sum() - valid.sum()) and s["bv_tests"] > 0 and s["kernel_launches"] >= 2      # K1 + K3 (one launch: warp phase + heavy phase)
 
 
 def test_compact_result_equals_full_result(ck, oracle):
