@@ -550,6 +550,19 @@ def extra_measurements(ck, sampling, torch, dev, stream):
                         "note": "latency = mean wall time of one env-1 start-to-goal query run ALONE on the device (40 seeds, one after another) -- what BASELINE.md's %d ms "
                                 "measures (mean of 500 runs, there on the author's CPU); throughput = wall time of 500 concurrent queries / 500 (lock-step ensemble, "
                                 "host/cbirrt_pcs_batch.cpp, 4 workers) -- a different quantity, not comparable with the published latency" % ref_ms}
+                lexe = os.path.join(REPO, "abb_dualarm_planning_b200", "host", "lazy_gd_batch")
+                if os.path.exists(lexe):           # BASELINE configs[3] names SBL_GD: planners/SBL_GD.cpp restated over the C ABI, max step 0.6 (run/plan_GD.cpp:289)
+                    def lazy(nq, workers):
+                        outp = os.path.join(td, "sbl_%d.txt" % nq)
+                        subprocess.run([lexe, "sbl", "1", str(nq), "0.6", "7", outp, str(workers)], env=env, capture_output=True, timeout=600, check=True)
+                        t = open(outp).read().strip().split("\n")[-1].split()
+                        return dict(zip(t[1::2], t[2::2]))
+                    one, many = lazy(40, 0), lazy(500, 4)
+                    plan["sbl_gd"] = {"latency_ms_1_query": float(one["latency_mean_ms"]), "latency_median_ms_1_query": float(one["latency_median_ms"]),
+                                      "latency_max_ms_1_query": float(one["latency_max_ms"]), "queries_for_latency": int(one["queries"]), "solved_for_latency": int(one["solved"]),
+                                      "gpu_calls_per_query": int(one["gpu_calls"]) / max(int(one["queries"]), 1),
+                                      "throughput_ms_per_query_500": float(many["ms_per_query"]), "solved_of_500": int(many["solved"]),
+                                      "note": "SBL_GD restated (host/lazy_gd_batch.cpp); latency = one query alone, mean of 40 seeds; the reference's matlab/Benchmark_* logs for SBL_GD are not in the tree (BASELINE.md)"}
                 ex["planning"] = plan
     except Exception as e:       # an extra, never the metric
         ex["planning"] = {"not_run": repr(e)}

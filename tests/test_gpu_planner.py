@@ -92,3 +92,48 @@ def test_prm_pcs_roadmap_path_is_valid(tmp_path, oracle):
     a = np.where(e[:-1, 2:3] == 0, q[:-1], q[1:]); b = np.where(e[:-1, 2:3] == 0, q[1:], q[:-1])
     ok, _ = oracle.pcs_check_motion_rbs(a, b, e[:-1, 0].astype(np.int8), e[:-1, 1].astype(np.int8))
     assert (ok == 1).all()
+
+
+def _plan_lazy(tmp_path, planner, n, step, seed, workers=1):
+    out = str(tmp_path / ("paths_%s_%d.txt" % (planner, n)))
+    env = dict(os.environ, CKC_MESH_PATH=PACK)
+    r = subprocess.run([os.path.join(HOST, "lazy_gd_batch"), planner, "1", str(n), str(step), str(seed), out, str(workers)], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    paths, summary = [], None
+    lines = open(out).read().strip().split("\n")
+    i = 0
+    while i < len(lines):
+        t = lines[i].split()
+        if t[0] == "summary":
+            summary = dict(zip(t[1::2], t[2::2])); i += 1
+        else:
+            m = int(t[3])
+            paths.append(np.array([[float(x) for x in ln.split()] for ln in lines[i + 1:i + 1 + m]])); i += 1 + m
+    return paths, summary
+
+
+@pytest.mark.parametrize("planner,step,n", [("rrt", 1.0, 6), ("lazyrrt", 1.0, 6), ("sbl", 0.6, 10)])
+def test_gd_single_tree_and_lazy_planners(tmp_path, oracle, planner, step, n):
+    """planners/RRT_GD.cpp, LazyRRT_GD.cpp, SBL_GD.cpp restated over the C ABI (host/lazy_gd_batch.cpp): every returned path starts at the
+    start state, ends at the goal, its milestones close the KDL chain and are collision free, and every edge passes the oracle's
+    checkMotionRBS in the direction the planner checked it"""
+    paths, summary = _plan_lazy(tmp_path, planner, n, step, 3, workers=2)
+    assert int(summary["solved"]) == n == len(paths)
+    for P in paths:
+        q = P[:, :12]; e = P[:, 17].astype(int)
+        assert np.abs(q[0] - START).max() == 0 and np.abs(q[-1] - GOAL).max() == 0 and len(q) >= 2
+        assert (oracle.collision_state(q) == 0).all()
+        for row in q[1:-1]:
+            T = oracle.kdl_fk(row)
+            assert np.abs(T[:3, 3] - [900, 0, 0]).max() < 0.1 and np.abs(T[:3, :3] - np.eye(3)).max() < 2e-4
+        a = np.where(e[:-1, None] == 0, q[:-1], q[1:]); b = np.where(e[:-1, None] == 0, q[1:], q[:-1])
+        keep = np.linalg.norm(a - b, axis=1) > 0                 # SBL's junction row repeats the other tree's state
+        ok, _ = oracle.gd_check_motion_rbs(a[keep], b[keep])
+        assert (ok == 1).all() and e[-1] == -1
+
+
+def test_lazy_planner_single_query_matches_its_ensemble_run(tmp_path):
+    p1, _ = _plan_lazy(tmp_path, "sbl", 1, 0.6, 9)
+    p4, _ = _plan_lazy(tmp_path, "sbl", 4, 0.6, 9, workers=1)
+    assert p1[0].shape == p4[0].shape and np.abs(p1[0] - p4[0]).max() == 0
