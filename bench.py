@@ -5,14 +5,19 @@
 
 Default workload = BASELINE.json configs[1]: "GD projection batch: 1e6 random 12-DOF samples, KDL-Jacobian Newton closure
 projection + FK + joint limits + collision, on 1 B200" (S-GD samples, env 1 / 3 poles).  One step = one pass of the hot
-path (project -> limits -> link frames -> collision) over one batch of S samples per GPU.  Weak scaling: every rank
+path (project -> limits -> link frames + collision) over one batch of S samples per GPU.  Weak scaling: every rank
 (one process per GPU, torchrun) validates its own S samples per step; no data-path collective (samples are independent);
-torch.distributed is used only for the barrier and the max-over-ranks of the device time.
+torch.distributed is used only for the barrier, the max-over-ranks of the device time and the summed counters.
 
-Printed JSON line (rank 0): value = whole-job validated configurations / s with inputs resident in HBM;
-e2e = the same metric through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region);
-roofline = dominant kernel against the MEASURED FP64 FMA-chain peak (this path is CUDA-core compute bound, not HBM/tensor);
-cpu_baseline = the CPU restatement of the reference path timed on this box (bounded sample).
+Printed JSON line (rank 0): value = whole-job validated configurations / s with inputs resident in HBM; the K steps are repeated
+inside ONE timed region until it lasts >= 0.5 s (config.inner_repeats); e2e = the same metric through the host-buffer C-ABI
+call (pinned host memory, H2D + D2H inside the timed region); roofline = the dominant kernel: k_gd_project against the
+MEASURED FP64 FMA-chain peak (2600 flop x Newton iterations), k_collide (PCS / RBS) as an instruction-issue bound
+FP32 kernel: executed box / triangle tests (its own counters) against the measured FP32 FMA-chain peak, issue-active from the
+committed ncu capture; cpu_baseline = the reference's CPU path timed on this box (bounded sample, 1 core).
+The default run also carries, under "extra", complete sub-records (value, e2e, roofline, cpu_baseline, clocks) for the two other
+BASELINE workloads -- "pcs" (configs[4], PCS arm; CPU arm = the reference's own compiled code) and "rbs" (configs[2]: 1e5 edges,
+checkMotionRBS) -- and "planning" (configs[3]): single-query latency and 500-query throughput of the restated planners.
 `--impl reference` times the reference's CPU path on all host cores (GD: the restated KDL loop, kind "port" -- real KDL is
 not installable; PCS / RBS: the reference's own compiled code through oracle/_ref, kind "reference").
 """
@@ -230,19 +235,13 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    from abb_dualarm_planning_b200.sharding import reduce_scalar
+
+    def max_over_ranks(x):           # the only cross-rank traffic of a run: timing agreement and summed counters, never data
+        return reduce_scalar(x, "max", dist, dev)
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_scalar(x, "sum", dist, dev)
 
     def repeats_for(step_fn, timer):
         """inner repeats R of the K steps so that the timed region lasts >= MIN_TIMED_S (same R on every rank)"""
