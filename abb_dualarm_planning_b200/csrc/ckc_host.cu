@@ -46,7 +46,7 @@ struct dev_buf {
 struct ckc_lane {
     cudaStream_t st = nullptr;
     cudaStream_t st_hi = nullptr;       /* high-priority stream for the collision stage of this lane's chunk */
-    cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_c = nullptr;
+    cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_c = nullptr, ev_up = nullptr;
     dev_buf qin, qout, ac, ik, ok, valid, list, ovf, bigstack, flags, aux, aux2, small, gdstate, pairstat, smallio;
     int64_t collide_launches = 0;
     /* this lane's own first-hit statistics and processing order of the pair table: [0, MAX_PAIRS) hits, [MAX_PAIRS, 2 MAX_PAIRS)
@@ -85,10 +85,17 @@ struct ckc_ctx {
     int64_t pipe_chunk = 1 << 18;       /* largest pipelined chunk of the host entry points (samples); a call is cut into ~4 chunks
                                            of 2^16 .. pipe_chunk samples (measured: 2^18 beats 2^17 by 10 % on S-GD, 2^16 loses 20 %) */
     bool gd_fan = false;                /* fan GD batches out over the lanes on the _dev paths (CKC_GD_FAN) */
+    int pipe_taper = 0;                 /* the last chunk of a pipelined host call is halved this many times (CKC_PIPE_TAPER) */
+    int64_t pipe_min_chunk = 1 << 14;
+    int pipe_nchunk = 4;                /* chunks a pipelined host call is cut into (CKC_PIPE_NCHUNK), bounded by pipe_chunk and 2^16 samples */
     int host_lanes = 4;                 /* lanes the host pipeline cycles through: a 1e6-sample call is 4 chunks, one per lane, so all
                                            H2D copies are in flight from the start; 8 lanes measured equal or slower (CKC_HOST_LANES) */
     bool overlap = true;                /* device-resident entry points fan out over the lanes */
     cudaEvent_t ev_fork = nullptr;
+    cudaStream_t st_up = nullptr;       /* the host pipeline's uploads, in chunk order on ONE stream (ordered_upload) */
+    bool ordered_upload = false;        /* CKC_ORDERED_UPLOAD: with the H2D copies of all chunks enqueued on their lanes' streams the copy engines
+                                           share the link between them and every chunk arrives late; on one stream chunk 0 arrives first */
+    bool timeline_copies = false;       /* CKC_TIMELINE: the stage timeline also carries the uploads (as stage 1) */
     int64_t launches = 0;
     ckc_stats host_stats;
     /* optional per-stage CUDA-event timing */
@@ -479,6 +486,8 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_p, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_c, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_up, cudaEventDisableTiming);
+        if (e == cudaSuccess && l == 0) e = cudaStreamCreateWithFlags(&ctx->st_up, cudaStreamNonBlocking);
         if (e == cudaSuccess && l == 0) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = ctx->lanes[l].small.reserve(256);
         if (e == cudaSuccess) e = cudaMemset(ctx->lanes[l].small.p, 0, 256);
@@ -561,6 +570,13 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
     if (ch) ctx->overlap = atoi(ch) != 0;
     ch = getenv("CKC_PIPE_CHUNK");
     if (ch && atoll(ch) >= 1024) ctx->pipe_chunk = atoll(ch);
+    ch = getenv("CKC_PIPE_NCHUNK");
+    if (ch && atoi(ch) >= 1 && atoi(ch) <= 64) ctx->pipe_nchunk = atoi(ch);
+    ch = getenv("CKC_ORDERED_UPLOAD");
+    if (ch) ctx->ordered_upload = atoi(ch) != 0;
+    ctx->timeline_copies = getenv("CKC_TIMELINE") != nullptr;
+    ch = getenv("CKC_PIPE_TAPER");
+    if (ch && atoi(ch) >= 0 && atoi(ch) <= 8) ctx->pipe_taper = atoi(ch);
     const char* gf = getenv("CKC_GD_FAN");
     if (gf) ctx->gd_fan = atoi(gf) != 0;
     const char* hl = getenv("CKC_HOST_LANES");
@@ -576,9 +592,10 @@ extern "C" void ckc_destroy(ckc_ctx* ctx) {
     dev_buf* bufs[] = { &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_pairhits, &ctx->d_pairorder, &ctx->rbs_seg[0], &ctx->rbs_seg[1],
                         &ctx->rbs_cand, &ctx->rbs_pool, &ctx->rbs_eok, &ctx->rbs_nck, &ctx->rbs_hit, &ctx->rbs_eac, &ctx->rbs_eik, &ctx->rbs_nt, &ctx->rbs_in };
     for (dev_buf* b : bufs) b->release();
-    for (int l = 0; l < CKC_NUM_LANES; l++) { ctx->lanes[l].release(); if (ctx->lanes[l].ev_done) cudaEventDestroy(ctx->lanes[l].ev_done); if (ctx->lanes[l].ev_p) cudaEventDestroy(ctx->lanes[l].ev_p); if (ctx->lanes[l].ev_c) cudaEventDestroy(ctx->lanes[l].ev_c);
+    for (int l = 0; l < CKC_NUM_LANES; l++) { ctx->lanes[l].release(); if (ctx->lanes[l].ev_done) cudaEventDestroy(ctx->lanes[l].ev_done); if (ctx->lanes[l].ev_p) cudaEventDestroy(ctx->lanes[l].ev_p); if (ctx->lanes[l].ev_c) cudaEventDestroy(ctx->lanes[l].ev_c); if (ctx->lanes[l].ev_up) cudaEventDestroy(ctx->lanes[l].ev_up);
         if (ctx->lanes[l].st_hi) cudaStreamDestroy(ctx->lanes[l].st_hi); if (ctx->lanes[l].st) cudaStreamDestroy(ctx->lanes[l].st); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->st_up) cudaStreamDestroy(ctx->st_up);
     ctx->d_cidx.release(); ctx->d_cq.release(); ctx->d_ccount.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -587,6 +604,7 @@ extern "C" void ckc_destroy(ckc_ctx* ctx) {
 
 static void drain_lanes(ckc_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->st_up) cudaStreamSynchronize(ctx->st_up);
     for (int l = 0; l < CKC_NUM_LANES; l++) if (ctx->lanes[l].st) cudaStreamSynchronize(ctx->lanes[l].st);
 }
 
@@ -782,10 +800,20 @@ static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, co
     if (!ctx || n < 0 || n > 0x7fffffff || (n > 0 && (!q || (flavour == 0 && !ik)))) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     if (n > 0 && n <= CKC_SMALL_MAX && !co) return project_small(ctx, flavour, n, q, ac, ik, q_out, ok, conv, iters, valid, collide);
-    const int64_t C = std::max<int64_t>(1, std::min<int64_t>(ctx->pipe_chunk, std::max<int64_t>(std::min<int64_t>(n, 1 << 16), (n + 3) / 4)));
+    const int64_t C = std::max<int64_t>(1, std::min<int64_t>(ctx->pipe_chunk, std::max<int64_t>(std::min<int64_t>(n, 1 << 16), (n + ctx->pipe_nchunk - 1) / ctx->pipe_nchunk)));
     /* compact mode: each chunk appends its valid (index, configuration) pairs to its own device region; a fixed-size prefix
      * (5 % of the chunk + 1024 entries) of every region is copied back inside the pipeline, the rare overflow afterwards */
-    const int64_t nchunks = n > 0 ? (n + C - 1) / C : 0;
+    /* chunk schedule: uniform chunks of C samples, the LAST one halved pipe_taper times (c -> c/2, c/4, c/4 ...).  The uploads of a call
+     * are serialised on the one H2D link and are what bounds it; everything that still has to run after the last byte has arrived (the
+     * last chunk's kernels and read-back) is pure drain, so the last chunk is made small while the early ones stay large (fewer kernel tails) */
+    std::vector<int64_t> c_off, c_len;
+    for (int64_t off = 0; off < n; off += C) { c_off.push_back(off); c_len.push_back(std::min(C, n - off)); }
+    for (int t = 0; t < ctx->pipe_taper && !c_len.empty() && c_len.back() >= 2 * ctx->pipe_min_chunk; t++) {
+        const int64_t c = c_len.back(), h = c / 2;
+        c_len.back() = h;
+        c_off.push_back(c_off.back() + h); c_len.push_back(c - h);
+    }
+    const int64_t nchunks = (int64_t)c_len.size();
     const int64_t ccopy = C / 20 + 1024;
     int32_t* h_cnt = nullptr; int32_t* h_idx = nullptr; double* h_q = nullptr;
     if (co && n > 0) {
@@ -803,18 +831,27 @@ static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, co
         CU(cudaMemsetAsync(ctx->d_ccount.p, 0, (size_t)nchunks * 4, ctx->lanes[0].st));
         CU(cudaStreamSynchronize(ctx->lanes[0].st));
     }
-    int k = 0;
-    for (int64_t off = 0; off < n; off += C, k++) {
-        const int64_t c = std::min(C, n - off);
+    for (int k = 0; k < (int)nchunks; k++) {
+        const int64_t off = c_off[k], c = c_len[k];
         ckc_lane& L = ctx->lanes[k % ctx->host_lanes];
         cudaStream_t st = L.st;
         CUS(L.qin.reserve((size_t)C * 96)); CUS(L.qout.reserve((size_t)C * 96)); CUS(L.ok.reserve((size_t)C)); CUS(L.valid.reserve((size_t)C));
-        CUS(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, st));
+        if (flavour == 0) { CUS(L.ac.reserve((size_t)C)); CUS(L.ik.reserve((size_t)C)); }
+        {
+            cudaStream_t up = ctx->ordered_upload ? ctx->st_up : st;
+            if (ctx->ordered_upload && k >= ctx->host_lanes) CUS(cudaStreamWaitEvent(up, L.ev_done, 0));      /* the lane's previous chunk has left its buffers */
+            const bool saved_t = ctx->stage_timing; ctx->stage_timing = saved_t && ctx->timeline_copies;
+            { stage_scope ts(ctx, up, 1);
+              CUS(cudaMemcpyAsync(L.qin.p, q + off * 12, (size_t)c * 96, cudaMemcpyHostToDevice, up));
+              if (flavour == 0) {
+                  if (ac) CUS(cudaMemcpyAsync(L.ac.p, ac + off, (size_t)c, cudaMemcpyHostToDevice, up));
+                  CUS(cudaMemcpyAsync(L.ik.p, ik + off, (size_t)c, cudaMemcpyHostToDevice, up));
+              } }
+            ctx->stage_timing = saved_t;
+            if (ctx->ordered_upload) { CUS(cudaEventRecord(L.ev_up, up)); CUS(cudaStreamWaitEvent(st, L.ev_up, 0)); }
+        }
         int rc;
         if (flavour == 0) {
-            CUS(L.ac.reserve((size_t)C)); CUS(L.ik.reserve((size_t)C));
-            if (ac) CUS(cudaMemcpyAsync(L.ac.p, ac + off, (size_t)c, cudaMemcpyHostToDevice, st));
-            CUS(cudaMemcpyAsync(L.ik.p, ik + off, (size_t)c, cudaMemcpyHostToDevice, st));
             rc = run_pcs_chunk(ctx, L, c, L.qin.as<double>(), AOS, ac ? L.ac.as<int8_t>() : nullptr, L.ik.as<int8_t>(), 0, 0, 0, L.qout.as<double>(), AOS,
                                L.ok.as<uint8_t>(), L.valid.as<uint8_t>(), collide, st);
         } else {
@@ -838,12 +875,14 @@ static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, co
             CUS(cudaMemcpyAsync(h_idx + (size_t)k * ccopy, dci, (size_t)cc * 4, cudaMemcpyDeviceToHost, st));
             CUS(cudaMemcpyAsync(h_q + (size_t)k * ccopy * 12, dcq, (size_t)cc * 96, cudaMemcpyDeviceToHost, st));
         }
+        if (ctx->ordered_upload) CUS(cudaEventRecord(L.ev_done, st));
     }
     for (int l = 0; l < CKC_NUM_LANES; l++) CU(cudaStreamSynchronize(ctx->lanes[l].st));
+    if (ctx->ordered_upload) CU(cudaStreamSynchronize(ctx->st_up));
     if (co) {
         int64_t total = 0;
         for (int64_t kk = 0; kk < nchunks; kk++) {
-            const int64_t cnt = h_cnt[kk], off = kk * C;
+            const int64_t cnt = h_cnt[kk], off = c_off[kk];
             const int64_t room = std::max<int64_t>(0, std::min(cnt, co->cap - total));
             const int64_t staged = std::min(room, ccopy);
             if (staged > 0) {
@@ -1501,7 +1540,7 @@ extern "C" int ckc_debug_timeline(ckc_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (int l = 0; l < CKC_NUM_LANES; l++) cudaStreamSynchronize(ctx->lanes[l].st);
     cudaEvent_t base = ctx->pending[0].e0;
-    static const char* nm[4] = { "project", "frames", "collide", "rbs" };
+    static const char* nm[4] = { "project", "upload", "collide", "rbs" };
     for (auto& p : ctx->pending) {
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, base, p.e0); cudaEventElapsedTime(&b, base, p.e1);
