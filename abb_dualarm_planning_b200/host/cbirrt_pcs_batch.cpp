@@ -68,7 +68,15 @@ struct Tree {
     }
 };
 
-enum Wait { W_NONE, W_PROJECT, W_PROJECT_FALLBACK, W_IDENTIFY, W_RBS0, W_RBS1 };
+enum Wait { W_NONE, W_PROJECT, W_PROJECT_FALLBACK, W_IDENTIFY, W_RBS0, W_RBS1, W_SPEC };
+
+/* one step of a growTree window (CBiRRT-PCS): the interpolated state, after step A the projected one */
+struct SpecStep {
+    double ds[12];
+    int ik[2];
+    bool reach = false, direct = false, ok = false, valid = false;
+    int rbs = -1;            /* -1: no RBS pass validated the edge yet; 0 / 1: the active chain that did */
+};
 
 struct Query {
     Tree t[2];                       /* 0 = start tree, 1 = goal tree */
@@ -85,6 +93,7 @@ struct Query {
     /* the step in flight */
     Wait wait = W_NONE;
     double dstate[12]; int ik[2];
+    std::vector<SpecStep> win; bool win_fallback = false, win_cut = false;      /* the window in flight (CBiRRT-PCS) */
     std::vector<int> path_tree, path_node;
     Node junction; bool junction_in_start_tree = false;      /* the copy of the connection state that :430-433 drops */
 };
@@ -103,6 +112,7 @@ struct Ensemble {
     ckc_ctx* ctx = nullptr;
     double max_step = 1.0;
     bool gd = false;                 /* CBiRRT-GD (planners/CBiRRT_GD.cpp) instead of CBiRRT-PCS */
+    int window = 64;                 /* growTree steps asked per round and query (CBiRRT-PCS); 1 = the reference's step-by-step order */
     std::vector<Query> qs;
     long calls = 0, items = 0;
     double t_kind[3] = { 0, 0, 0 }; long n_kind[3] = { 0, 0, 0 }; long i_kind[3] = { 0, 0, 0 };      /* validate / identify / rbs */
@@ -176,7 +186,9 @@ struct Ensemble {
     void advance(Query& Q) {
         while (!Q.solved && Q.wait == W_NONE) {
             if (Q.stage == 0) begin_iteration(Q);
-            grow_head(Q);
+            if (gd) grow_head(Q);
+            else if (Q.count == 0) end_grow(Q);
+            else build_window(Q);
         }
     }
 
@@ -204,87 +216,156 @@ struct Ensemble {
             }
             if (!live) break;
             if (gd) { run_gd_steps(idx, q, qo, qa, qb, valid, res, nchk); continue; }
-            /* ---- step A / A': projection + collision ---- */
-            for (int pass = 0; pass < 2; pass++) {
-                const Wait want = pass == 0 ? W_PROJECT : W_PROJECT_FALLBACK;
-                idx.clear();
-                for (size_t k = 0; k < qs.size(); k++) if (!qs[k].solved && qs[k].wait == want) idx.push_back((int)k);
-                if (idx.empty()) continue;
-                const size_t m = idx.size();
-                q.resize(m * 12); qo.resize(m * 12); ac.resize(m); ik.resize(m); ok.resize(m); valid.resize(m);
-                for (size_t i = 0; i < m; i++) {
-                    Query& Q = qs[idx[i]];
-                    memcpy(&q[12 * i], Q.dstate, 96);
-                    ac[i] = (int8_t)Q.active_chain; ik[i] = (int8_t)Q.t[Q.g_tree].n[Q.nm].ik[Q.active_chain];
-                }
-                mark();
-                check(ckc_pcs_validate(ctx, (int64_t)m, q.data(), ac.data(), ik.data(), qo.data(), ok.data(), valid.data()), m, 0);
-                for (size_t i = 0; i < m; i++) {
-                    Query& Q = qs[idx[i]];
-                    if (!ok[i]) {
-                        if (pass == 0) { Q.active_chain = 1 - Q.active_chain; Q.wait = W_PROJECT_FALLBACK; }      /* :196-203 / :214-221 */
-                        else end_grow(Q);
-                        continue;
+            run_pcs_steps(idx, q, qo, qa, qb, ac, ik, id, ok, valid, res, nchk);
+        }
+    }
+
+    /* ---- CBiRRT-PCS: one round = the WINDOW of every live query ------------------------------------------------------------
+     * Inside one growTree call the reference walks from nmotion toward the target in steps of max_step, and each step is
+     * project -> identify -> RBS, one question at a time (:173-298).  The questions of consecutive steps look dependent (step k + 1
+     * starts from the node step k added) but are not: the projection only REPLACES the passive arm (apc_class.cpp:356-389), so the
+     * active arm's joints of node k are those of the interpolated state, the next interpolation factor (activeDistance, :122-140)
+     * and the next active joints follow from them alone, and the projection arguments (active chain, that chain's IK branch) are
+     * inherited unchanged.  The whole run of steps is therefore known up front: a window of up to `window` steps is projected +
+     * collision-checked in ONE ckc_pcs_validate, identified in one ckc_identify_ik and its edges are checked in one or two
+     * ckc_pcs_check_motion_rbs calls; the steps are then committed in order up to the first one the reference would have stopped
+     * at (projection failure -> that step is re-asked exactly, with the fall-back chain; collision or failed edge -> growTree
+     * returns).  Same tree, same path, same random stream as the step-by-step planner (window = 1 IS that planner); only
+     * speculative work behind a failing step is wasted.  This is the batching INSIDE one query that SURVEY 8(f) row 1 asks for. */
+    void build_window(Query& Q) {
+        const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
+        Q.win.clear(); Q.win_fallback = false; Q.win_cut = false;
+        double cur[12]; memcpy(cur, nmn.q, 96);
+        int cnt = Q.count;
+        while (cnt > 0 && (int)Q.win.size() < window) {
+            cnt--;
+            SpecStep st;
+            const double d = active_distance(Q.active_chain, cur, Q.target);
+            if (d > max_step) {
+                const double f = max_step / d;
+                for (int j = 0; j < 12; j++) st.ds[j] = cur[j] + (Q.target[j] - cur[j]) * f;      /* RealVectorStateSpace::interpolate */
+                st.reach = false;
+            } else { memcpy(st.ds, Q.target, 96); st.reach = true; }
+            st.direct = Q.mode == 2 && st.reach;       /* the state belongs to the opposite tree and already satisfies the constraint */
+            st.ik[0] = st.ik[1] = -1;
+            if (st.direct) { st.ik[0] = Q.target_ik[0]; st.ik[1] = Q.target_ik[1]; st.ok = st.valid = true; }
+            Q.win.push_back(st);
+            if (st.reach) break;
+            memcpy(cur, st.ds, 96);                    /* active joints exact; the passive ones are replaced by the projection anyway */
+        }
+        Q.wait = W_SPEC;
+    }
+
+    void run_pcs_steps(std::vector<int>& idx, std::vector<double>& q, std::vector<double>& qo, std::vector<double>& qa, std::vector<double>& qb,
+                       std::vector<int8_t>& ac, std::vector<int8_t>& ik, std::vector<int8_t>& id, std::vector<uint8_t>& ok, std::vector<uint8_t>& valid,
+                       std::vector<uint8_t>& res, std::vector<int32_t>& nchk) {
+        std::vector<std::pair<int, int> > ref;          /* (query, step) of every batched item */
+        /* ---- step A / A': projection + collision of the windows; A' = the fall-back chain for a window whose FIRST step did not close ---- */
+        for (int pass = 0; pass < 2; pass++) {
+            ref.clear();
+            for (size_t k = 0; k < qs.size(); k++) {
+                Query& Q = qs[k];
+                if (Q.solved || Q.wait != W_SPEC || Q.win_fallback != (pass == 1)) continue;
+                for (size_t i = 0; i < Q.win.size(); i++) if (!Q.win[i].direct) ref.push_back(std::make_pair((int)k, (int)i));
+            }
+            if (ref.empty()) continue;
+            const size_t m = ref.size();
+            q.resize(m * 12); qo.resize(m * 12); ac.resize(m); ik.resize(m); ok.resize(m); valid.resize(m);
+            for (size_t i = 0; i < m; i++) {
+                Query& Q = qs[ref[i].first];
+                memcpy(&q[12 * i], Q.win[ref[i].second].ds, 96);
+                ac[i] = (int8_t)Q.active_chain; ik[i] = (int8_t)Q.t[Q.g_tree].n[Q.nm].ik[Q.active_chain];
+            }
+            mark();
+            check(ckc_pcs_validate(ctx, (int64_t)m, q.data(), ac.data(), ik.data(), qo.data(), ok.data(), valid.data()), m, 0);
+            for (size_t i = 0; i < m; i++) {
+                Query& Q = qs[ref[i].first]; SpecStep& st = Q.win[ref[i].second];
+                st.ok = ok[i] != 0; st.valid = valid[i] != 0;
+                if (st.ok) { memcpy(st.ds, &qo[12 * i], 96); st.ik[Q.active_chain] = Q.t[Q.g_tree].n[Q.nm].ik[Q.active_chain]; }
+            }
+            for (size_t k = 0; k < qs.size(); k++) {
+                Query& Q = qs[k];
+                if (Q.solved || Q.wait != W_SPEC || Q.win_fallback != (pass == 1)) continue;
+                for (size_t i = 0; i < Q.win.size(); i++) {
+                    const SpecStep& st = Q.win[i];
+                    if (st.direct) continue;
+                    if (!st.ok) {
+                        if (i > 0) Q.win.resize(i);                       /* commit the steps before it; this one is re-asked exactly next round */
+                        else if (pass == 0) { Q.active_chain = 1 - Q.active_chain; Q.win.resize(1); Q.win_fallback = true; }      /* :196-203 / :214-221 */
+                        else { Q.count--; end_grow(Q); }                  /* neither chain closes the step */
+                        break;
                     }
-                    if (!valid[i]) { end_grow(Q); continue; }                 /* :236-240 collision */
-                    memcpy(Q.dstate, &qo[12 * i], 96);
-                    Q.ik[Q.active_chain] = Q.t[Q.g_tree].n[Q.nm].ik[Q.active_chain];
-                    Q.wait = W_IDENTIFY;
-                }
-            }
-            /* ---- step B: identify_state_ik(dstate, ik) (:251) ---- */
-            idx.clear();
-            for (size_t k = 0; k < qs.size(); k++) if (!qs[k].solved && qs[k].wait == W_IDENTIFY) idx.push_back((int)k);
-            if (!idx.empty()) {
-                const size_t m = idx.size();
-                q.resize(m * 12); id.resize(m * 2);
-                for (size_t i = 0; i < m; i++) memcpy(&q[12 * i], qs[idx[i]].dstate, 96);
-                mark();
-                check(ckc_identify_ik(ctx, (int64_t)m, q.data(), id.data()), m, 1);
-                for (size_t i = 0; i < m; i++) {
-                    Query& Q = qs[idx[i]];
-                    for (int c = 0; c < 2; c++) if (Q.ik[c] == -1) Q.ik[c] = id[2 * i + c];
-                    Q.wait = W_RBS0;
-                }
-            }
-            /* ---- step C / C': RBS local connection (:275-279) ---- */
-            for (int pass = 0; pass < 2; pass++) {
-                idx.clear();
-                for (size_t k = 0; k < qs.size(); k++) {
-                    Query& Q = qs[k];
-                    if (Q.solved || Q.wait != (pass == 0 ? W_RBS0 : W_RBS1)) continue;
-                    const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
-                    if (nmn.ik[pass] == Q.ik[pass]) idx.push_back((int)k);
-                    else if (pass == 0) Q.wait = W_RBS1;
-                    else { Q.xmotion = Q.nm; end_grow(Q); }                                   /* :300-303 */
-                }
-                if (idx.empty()) continue;
-                const size_t m = idx.size();
-                qa.resize(m * 12); qb.resize(m * 12); ac.resize(m); ik.resize(m); res.resize(m); nchk.resize(m);
-                for (size_t i = 0; i < m; i++) {
-                    Query& Q = qs[idx[i]];
-                    const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
-                    memcpy(&qa[12 * i], nmn.q, 96); memcpy(&qb[12 * i], Q.dstate, 96);
-                    ac[i] = (int8_t)pass; ik[i] = (int8_t)nmn.ik[pass];
-                }
-                mark();
-                check(ckc_pcs_check_motion_rbs(ctx, (int64_t)m, qa.data(), qb.data(), ac.data(), ik.data(), res.data(), nchk.data()), m, 2);
-                for (size_t i = 0; i < m; i++) {
-                    Query& Q = qs[idx[i]];
-                    if (!res[i]) {
-                        if (pass == 0) Q.wait = W_RBS1;
-                        else { Q.xmotion = Q.nm; end_grow(Q); }
-                        continue;
+                    if (!st.valid) {                                      /* :236-240 collision: growTree returns after the steps before it */
+                        Q.win.resize(i); Q.win_cut = true;
+                        if (i == 0) { Q.count--; end_grow(Q); }
+                        break;
                     }
-                    Node nn;                                                                  /* :283-293 */
-                    memcpy(nn.q, Q.dstate, 96); nn.ik[0] = Q.ik[0]; nn.ik[1] = Q.ik[1];
-                    nn.parent = Q.nm; nn.a_chain = Q.active_chain; nn.e_ac = pass; nn.e_ik = Q.t[Q.g_tree].n[Q.nm].ik[pass];
-                    Q.t[Q.g_tree].n.push_back(nn);
-                    Q.nm = (int)Q.t[Q.g_tree].n.size() - 1; Q.xmotion = Q.nm;
-                    Q.wait = W_NONE;
-                    if (Q.reach) { Q.reached = true; end_grow(Q); }                           /* :295-298 */
                 }
             }
+        }
+        /* ---- step B: identify_state_ik of every projected state (:251) ---- */
+        ref.clear();
+        for (size_t k = 0; k < qs.size(); k++) {
+            Query& Q = qs[k];
+            if (Q.solved || Q.wait != W_SPEC) continue;
+            for (size_t i = 0; i < Q.win.size(); i++) if (!Q.win[i].direct) ref.push_back(std::make_pair((int)k, (int)i));
+        }
+        if (!ref.empty()) {
+            const size_t m = ref.size();
+            q.resize(m * 12); id.resize(m * 2);
+            for (size_t i = 0; i < m; i++) memcpy(&q[12 * i], qs[ref[i].first].win[ref[i].second].ds, 96);
+            mark();
+            check(ckc_identify_ik(ctx, (int64_t)m, q.data(), id.data()), m, 1);
+            for (size_t i = 0; i < m; i++) {
+                SpecStep& st = qs[ref[i].first].win[ref[i].second];
+                for (int c = 0; c < 2; c++) if (st.ik[c] == -1) st.ik[c] = id[2 * i + c];
+            }
+        }
+        /* ---- step C / C': RBS local connection of every window edge, active chain 0 where the branches agree, else / then chain 1 (:275-279) ---- */
+        for (int pass = 0; pass < 2; pass++) {
+            ref.clear();
+            for (size_t k = 0; k < qs.size(); k++) {
+                Query& Q = qs[k];
+                if (Q.solved || Q.wait != W_SPEC) continue;
+                for (size_t i = 0; i < Q.win.size(); i++) {
+                    const SpecStep& st = Q.win[i];
+                    const int* pik = i == 0 ? Q.t[Q.g_tree].n[Q.nm].ik : Q.win[i - 1].ik;
+                    if (st.rbs < 0 && pik[pass] == st.ik[pass]) ref.push_back(std::make_pair((int)k, (int)i));
+                }
+            }
+            if (ref.empty()) continue;
+            const size_t m = ref.size();
+            qa.resize(m * 12); qb.resize(m * 12); ac.resize(m); ik.resize(m); res.resize(m); nchk.resize(m);
+            for (size_t i = 0; i < m; i++) {
+                Query& Q = qs[ref[i].first]; const int w = ref[i].second;
+                const double* pq = w == 0 ? Q.t[Q.g_tree].n[Q.nm].q : Q.win[w - 1].ds;
+                const int* pik = w == 0 ? Q.t[Q.g_tree].n[Q.nm].ik : Q.win[w - 1].ik;
+                memcpy(&qa[12 * i], pq, 96); memcpy(&qb[12 * i], Q.win[w].ds, 96);
+                ac[i] = (int8_t)pass; ik[i] = (int8_t)pik[pass];
+            }
+            mark();
+            check(ckc_pcs_check_motion_rbs(ctx, (int64_t)m, qa.data(), qb.data(), ac.data(), ik.data(), res.data(), nchk.data()), m, 2);
+            for (size_t i = 0; i < m; i++) if (res[i]) qs[ref[i].first].win[ref[i].second].rbs = pass;
+        }
+        /* ---- commit the windows in step order (:283-303) ---- */
+        for (auto& Q : qs) {
+            if (Q.solved || Q.wait != W_SPEC) continue;
+            Q.wait = W_NONE;
+            bool ended = false;
+            for (size_t i = 0; i < Q.win.size() && !ended; i++) {
+                const SpecStep& st = Q.win[i];
+                Q.count--;
+                if (st.rbs < 0) { Q.xmotion = Q.nm; end_grow(Q); ended = true; break; }
+                const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
+                Node nn;
+                memcpy(nn.q, st.ds, 96); nn.ik[0] = st.ik[0]; nn.ik[1] = st.ik[1];
+                nn.parent = Q.nm; nn.e_ac = st.rbs; nn.e_ik = nmn.ik[st.rbs];
+                nn.a_chain = st.direct ? (nmn.ik[0] == st.ik[0] ? 0 : 1) : Q.active_chain;          /* :262-266 picks the chain of the direct step */
+                Q.t[Q.g_tree].n.push_back(nn);
+                Q.nm = (int)Q.t[Q.g_tree].n.size() - 1; Q.xmotion = Q.nm;
+                if (st.reach) { Q.reached = true; end_grow(Q); ended = true; }                      /* :295-298 */
+            }
+            if (!ended && Q.win_cut) { Q.count--; end_grow(Q); }
         }
     }
     /* CBiRRT-GD: IKproject(dstate) = kdl::GD + joint limits + collision (StateValidityCheckerGD.cpp:96-110) in one batched
@@ -354,6 +435,7 @@ int main(int argc, char** argv) {
     int8_t id[4]; uint8_t hit[2];
     for (int w = 0; w < workers; w++) {
         E[w].max_step = max_step; E[w].gd = gd;
+        if (getenv("CKC_PLAN_WINDOW")) E[w].window = std::max(1, atoi(getenv("CKC_PLAN_WINDOW")));
         if (ckc_create(&E[w].ctx, env, mesh ? mesh : "./simulator", dev ? atoi(dev) : 0) != CKC_OK) { fprintf(stderr, "ckc_create failed\n"); return 1; }
     }
     /* :325-343, :380-396: start and goal must be identifiable on both chains and collision free */

@@ -549,6 +549,10 @@ def extra_measurements(ck, sampling, torch, dev, stream):
                         "note": "latency = mean wall time of one env-1 start-to-goal query run ALONE on the device (40 seeds, one after another) -- what BASELINE.md's %d ms "
                                 "measures (mean of 500 runs, there on the author's CPU); throughput = wall time of 500 concurrent queries / 500 (lock-step ensemble, "
                                 "host/cbirrt_pcs_batch.cpp, 4 workers) -- a different quantity, not comparable with the published latency" % ref_ms}
+                    if flav == "pcs":          # batching inside ONE query: a growTree call's run of steps as one window (same tree as step by step)
+                        sbs = _planner_run(exe, dict(env, CKC_PLAN_WINDOW="1"), 40, step, flav, 0, td)
+                        plan["cbirrt_pcs"].update({"window_steps_per_round": 64, "latency_ms_1_query_step_by_step": float(sbs["latency_mean_ms"]),
+                                                   "gpu_calls_per_query_step_by_step": int(sbs["gpu_calls"]) / max(int(sbs["queries"]), 1)})
                 lexe = os.path.join(REPO, "abb_dualarm_planning_b200", "host", "lazy_gd_batch")
                 if os.path.exists(lexe):           # BASELINE configs[3] names SBL_GD: planners/SBL_GD.cpp restated over the C ABI, max step 0.6 (run/plan_GD.cpp:289)
                     def lazy(nq, workers):
