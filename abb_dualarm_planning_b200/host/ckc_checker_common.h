@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <ctime>
 #include <fstream>
 #include <iostream>
@@ -33,7 +34,15 @@ public:
         const char* p = getenv("CKC_MESH_PATH");
         const char* dev = getenv("CKC_DEVICE");
         std::string path = p ? p : "./simulator";
-        int rc = ckc_create(&ctx_, env, path.c_str(), dev ? atoi(dev) : 0);
+        /* CKC_DEVICES=0,1,2,3: a multi-device context -- every batched member (sample_q's candidate batches, checkMotionRBSBatch,
+         * isValidBatch ...) is then split over those GPUs inside the library; the planner code does not change */
+        const char* devs = getenv("CKC_DEVICES");
+        int rc;
+        if (devs && strchr(devs, ',')) {
+            std::vector<int> ids;
+            for (const char* c = devs; *c; ) { ids.push_back(atoi(c)); c = strchr(c, ','); if (!c) break; c++; }
+            rc = ckc_create_multi(&ctx_, env, path.c_str(), ids.data(), (int)ids.size());
+        } else rc = ckc_create(&ctx_, env, path.c_str(), devs ? atoi(devs) : (dev ? atoi(dev) : 0));
         if (rc != CKC_OK) {           /* the reference exit(-1)s when a mesh cannot be opened (collisionDetection.cpp:503) */
             fprintf(stderr, "ckc_create(%s) failed: %d\n", path.c_str(), rc);
             exit(-1);

@@ -13,8 +13,8 @@ HOST = os.path.join(REPO, "abb_dualarm_planning_b200", "host")
 PACK = os.path.join(REPO, "abb_dualarm_planning_b200", "data", "meshes.ckcmesh")
 
 
-def _run(binary, inp, out):
-    env = dict(os.environ, CKC_MESH_PATH=PACK)
+def _run(binary, inp, out, **extra_env):
+    env = dict(os.environ, CKC_MESH_PATH=PACK, **extra_env)
     r = subprocess.run([os.path.join(HOST, binary), inp, out], env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(out))
     assert r.returncode == 0, r.stderr[-2000:]
 
@@ -38,6 +38,12 @@ def test_pcs_dropin_class(tmp_path, oracle, gold):
             f.write(" ".join(repr(float(x)) for x in r[:12]) + " %d " % int(r[12]) + " ".join(repr(float(x)) for x in r[13:]) + "\n")
     _run("test_dropin_pcs", inp, out)
     lines = open(out).read().strip().split("\n")
+    # the same driver on a multi-device context (CKC_DEVICES: the drop-in class then owns one sub-context per listed device and the
+    # library splits every batch over them; with one GPU in the box the same device twice): identical answers
+    import torch
+    out2 = str(tmp_path / "out_multi.txt")
+    _run("test_dropin_pcs", inp, out2, CKC_DEVICES="0,1" if torch.cuda.device_count() >= 2 else "0,0")
+    assert open(out2).read().strip().split("\n")[:len(rows)] == lines[:len(rows)]
     res = np.array([[float(x) for x in ln.split()] for ln in lines[:len(rows)]])
     qq, kk, qb = rows[:, :12], rows[:, 12].astype(np.int8), rows[:, 13:]
     ok_o, q_o = oracle.pcs_project(qq, 0, kk)
