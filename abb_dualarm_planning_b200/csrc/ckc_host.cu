@@ -46,7 +46,8 @@ struct dev_buf {
 struct ckc_lane {
     cudaStream_t st = nullptr;
     cudaStream_t st_hi = nullptr;       /* high-priority stream for the collision stage of this lane's chunk */
-    cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_c = nullptr, ev_up = nullptr;
+    cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_c = nullptr, ev_up = nullptr, ev_busy = nullptr;
+    bool busy_set = false;              /* ev_busy has been recorded: the lane's scratch is in use by a device-resident call until it fires */
     dev_buf qin, qout, ac, ik, ok, valid, list, ovf, bigstack, flags, aux, aux2, small, gdstate, pairstat, smallio;
     int64_t collide_launches = 0;
     /* this lane's own first-hit statistics and processing order of the pair table: [0, MAX_PAIRS) hits, [MAX_PAIRS, 2 MAX_PAIRS)
@@ -86,6 +87,7 @@ struct ckc_ctx {
                                            of 2^16 .. pipe_chunk samples (measured: 2^18 beats 2^17 by 10 % on S-GD, 2^16 loses 20 %) */
     bool gd_fan = false;                /* fan GD batches out over the lanes on the _dev paths (CKC_GD_FAN) */
     int pipe_taper = 0;                 /* the last chunk of a pipelined host call is halved this many times (CKC_PIPE_TAPER) */
+    int pipe_taper_front = 0;           /* the first chunk halved this many times (CKC_PIPE_TAPER_FRONT) */
     int64_t pipe_min_chunk = 1 << 14;
     int pipe_nchunk = 4;                /* chunks a pipelined host call is cut into (CKC_PIPE_NCHUNK), bounded by pipe_chunk and 2^16 samples */
     int host_lanes = 4;                 /* lanes the host pipeline cycles through: a 1e6-sample call is 4 chunks, one per lane, so all
@@ -97,6 +99,7 @@ struct ckc_ctx {
                                            share the link between them and every chunk arrives late; on one stream chunk 0 arrives first */
     bool timeline_copies = false;       /* CKC_TIMELINE: the stage timeline also carries the uploads (as stage 1) */
     int64_t launches = 0;
+    unsigned dev_rot = 0;               /* lane rotation of the device-resident entry points */
     ckc_stats host_stats;
     /* optional per-stage CUDA-event timing */
     bool stage_timing = false;
@@ -487,6 +490,7 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_p, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_c, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_up, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].ev_busy, cudaEventDisableTiming);
         if (e == cudaSuccess && l == 0) e = cudaStreamCreateWithFlags(&ctx->st_up, cudaStreamNonBlocking);
         if (e == cudaSuccess && l == 0) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = ctx->lanes[l].small.reserve(256);
@@ -570,6 +574,8 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
     if (ch) ctx->overlap = atoi(ch) != 0;
     ch = getenv("CKC_PIPE_CHUNK");
     if (ch && atoll(ch) >= 1024) ctx->pipe_chunk = atoll(ch);
+    ch = getenv("CKC_PIPE_TAPER_FRONT");
+    if (ch && atoi(ch) >= 0 && atoi(ch) <= 8) ctx->pipe_taper_front = atoi(ch);
     ch = getenv("CKC_PIPE_NCHUNK");
     if (ch && atoi(ch) >= 1 && atoi(ch) <= 64) ctx->pipe_nchunk = atoi(ch);
     ch = getenv("CKC_ORDERED_UPLOAD");
@@ -592,7 +598,7 @@ extern "C" void ckc_destroy(ckc_ctx* ctx) {
     dev_buf* bufs[] = { &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_pairhits, &ctx->d_pairorder, &ctx->rbs_seg[0], &ctx->rbs_seg[1],
                         &ctx->rbs_cand, &ctx->rbs_pool, &ctx->rbs_eok, &ctx->rbs_nck, &ctx->rbs_hit, &ctx->rbs_eac, &ctx->rbs_eik, &ctx->rbs_nt, &ctx->rbs_in };
     for (dev_buf* b : bufs) b->release();
-    for (int l = 0; l < CKC_NUM_LANES; l++) { ctx->lanes[l].release(); if (ctx->lanes[l].ev_done) cudaEventDestroy(ctx->lanes[l].ev_done); if (ctx->lanes[l].ev_p) cudaEventDestroy(ctx->lanes[l].ev_p); if (ctx->lanes[l].ev_c) cudaEventDestroy(ctx->lanes[l].ev_c); if (ctx->lanes[l].ev_up) cudaEventDestroy(ctx->lanes[l].ev_up);
+    for (int l = 0; l < CKC_NUM_LANES; l++) { ctx->lanes[l].release(); if (ctx->lanes[l].ev_done) cudaEventDestroy(ctx->lanes[l].ev_done); if (ctx->lanes[l].ev_p) cudaEventDestroy(ctx->lanes[l].ev_p); if (ctx->lanes[l].ev_c) cudaEventDestroy(ctx->lanes[l].ev_c); if (ctx->lanes[l].ev_up) cudaEventDestroy(ctx->lanes[l].ev_up); if (ctx->lanes[l].ev_busy) cudaEventDestroy(ctx->lanes[l].ev_busy);
         if (ctx->lanes[l].st_hi) cudaStreamDestroy(ctx->lanes[l].st_hi); if (ctx->lanes[l].st) cudaStreamDestroy(ctx->lanes[l].st); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->st_up) cudaStreamDestroy(ctx->st_up);
@@ -813,6 +819,15 @@ static int project_host(ckc_ctx* ctx, int flavour /*0 PCS, 1 GD*/, int64_t n, co
         c_len.back() = h;
         c_off.push_back(c_off.back() + h); c_len.push_back(c - h);
     }
+    /* the FIRST chunk halved pipe_taper_front times (c/4, c/4, c/2, c, c ...): the kernels of a call cannot start before the first chunk
+     * has arrived, and where the kernels (not the link) pace the pipeline that wait is added to the call one to one */
+    for (int t = 0; t < ctx->pipe_taper_front && !c_len.empty() && c_len.front() >= 2 * ctx->pipe_min_chunk; t++) {
+        const int64_t c = c_len.front(), h = c / 2;
+        c_len.front() = c - h;
+        c_off.front() += h;
+        c_off.insert(c_off.begin(), c_off.front() - h); c_len.insert(c_len.begin(), h);
+        if (t + 1 < ctx->pipe_taper_front) { /* keep halving the new first piece */ }
+    }
     const int64_t nchunks = (int64_t)c_len.size();
     const int64_t ccopy = C / 20 + 1024;
     int32_t* h_cnt = nullptr; int32_t* h_idx = nullptr; double* h_q = nullptr;
@@ -973,10 +988,16 @@ template <class F>
 static int dev_fanout(ckc_ctx* ctx, cudaStream_t user, int64_t n, bool fan, F body) {
     if (n <= 0) return CKC_OK;
     if (!fan || !ctx->overlap || n < (1 << 17)) {
+        /* the call runs in order on the caller's stream with the scratch buffers of ONE lane; consecutive calls rotate over the lanes, so
+         * calls issued on different caller streams can be in flight together (one call's collision kernel then fills the tail of the next
+         * call's projection kernel); a lane's previous user is awaited through the lane's event, whatever stream it ran on */
+        ckc_lane& L = ctx->lanes[(ctx->dev_rot++) % CKC_FAN_LANES];
+        if (L.busy_set) CU(cudaStreamWaitEvent(user, L.ev_busy, 0));
         for (int64_t off = 0; off < n; off += ctx->chunk) {
-            int rc = body(ctx->lanes[0], off, std::min(ctx->chunk, n - off), user);
+            int rc = body(L, off, std::min(ctx->chunk, n - off), user);
             if (rc) return rc;
         }
+        CU(cudaEventRecord(L.ev_busy, user)); L.busy_set = true;
         return CKC_OK;
     }
     int64_t c = (n + CKC_FAN_LANES - 1) / CKC_FAN_LANES;

@@ -9,7 +9,8 @@ path (project -> limits -> link frames + collision) over one batch of S samples 
 (one process per GPU, torchrun) validates its own S samples per step; no data-path collective (samples are independent);
 torch.distributed is used only for the barrier, the max-over-ranks of the device time and the summed counters.
 
-Printed JSON line (rank 0): value = whole-job validated configurations / s with inputs resident in HBM; the K steps are repeated
+Printed JSON line (rank 0): value = whole-job validated configurations / s with inputs resident in HBM, the steps issued on two caller
+streams in turn (config.caller_streams; one_caller_stream = the same steps on one stream); the K steps are repeated
 inside ONE timed region until it lasts >= 0.5 s (config.inner_repeats); e2e = the same metric through the host-buffer C-ABI
 call (pinned host memory, H2D + D2H inside the timed region); roofline = the dominant kernel: k_gd_project against the
 MEASURED FP64 FMA-chain peak (2600 flop x Newton iterations), k_collide (PCS / RBS) as an instruction-issue bound
@@ -44,6 +45,7 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="gd", choices=["gd", "pcs", "rbs"])
     ap.add_argument("--samples", type=int, default=0, help="units per GPU per step (default: 1e6 samples; 1e5 edges for rbs = BASELINE configs[2])")
+    ap.add_argument("--streams", type=int, default=2, help="caller streams the resident GD steps alternate over (2: step i+1's projection overlaps step i's collision tail)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary PCS / RBS measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     return ap.parse_args()
@@ -249,9 +251,20 @@ def run_native(args):
         t = max_over_ranks(t)
         return max(1, int(np.ceil(MIN_TIMED_S / max(K * t, 1e-9))))
 
+    side = []                        # extra caller streams of the resident GD steps (--streams), empty otherwise
+
+    def fork_streams():              # the side streams start after everything issued so far on the current stream ...
+        if side:
+            ev = torch.cuda.Event(); ev.record()
+            for st_ in side: st_.wait_event(ev)
+
+    def join_streams():              # ... and the current stream continues after everything issued on them
+        for st_ in side:
+            ev = torch.cuda.Event(); ev.record(st_); torch.cuda.current_stream().wait_event(ev)
+
     def ev_timer(fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        e0.record(); fork_streams(); fn(); join_streams(); e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e-3
 
     def wall_timer(fn):
@@ -283,11 +296,19 @@ def run_native(args):
         d_qout = torch.empty((12, n), dtype=torch.float64, device=dev)
         d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
         d_valid = torch.empty(n, dtype=torch.uint8, device=dev)
+        # caller streams of the resident GD steps: with 2, consecutive steps are issued on alternating streams with their own output buffers
+        NS = max(1, args.streams) if wl == "gd" else 1
+        side[:] = [torch.cuda.Stream(device=dev) for _ in range(NS)] if NS > 1 else []
+        outs = [(d_qout, d_valid)] + [(torch.empty_like(d_qout), torch.empty_like(d_valid)) for _ in range(NS - 1)]
         torch.cuda.synchronize()
+        step_no = [0]
 
         def step_dev(b):
             if wl == "gd":
-                ck.gd_validate_dev(n, d_q[b].data_ptr(), d_qout.data_ptr(), d_valid.data_ptr(), stream)
+                slot = step_no[0] % len(side) if side else 0
+                step_no[0] += 1
+                qo, va = outs[slot]
+                ck.gd_validate_dev(n, d_q[b].data_ptr(), qo.data_ptr(), va.data_ptr(), side[slot].cuda_stream if side else stream)
             else:
                 ck.pcs_validate_dev(n, d_q[b].data_ptr(), None, d_ik[b].data_ptr(), d_qout.data_ptr(), d_ok.data_ptr(), d_valid.data_ptr(), stream)
 
@@ -301,17 +322,35 @@ def run_native(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
+        fork_streams()
         for r in range(R):
             for k in range(K):
                 step_dev(k % NB)
+        join_streams()
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
         out["clocks"] = sampler.stop()
         stats = ck.stats()
         steps_run = K * R
+        if side:                         # for the record: the same K steps issued on ONE caller stream (every call waits for the one before it)
+            keep = list(side); side[:] = []
+            barrier()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
+            for r in range(max(1, R // 2)):
+                for k in range(K):
+                    step_dev(k % NB)
+            e3.record()
+            barrier()
+            ms1 = max_over_ranks(e2.elapsed_time(e3))
+            out["one_caller_stream"] = {"value": world * K * max(1, R // 2) * n / (ms1 * 1e-3), "ms_per_step": ms1 / (K * max(1, R // 2))}
+            out["caller_streams"] = len(keep)
+            side[:] = keep
         # per-kernel durations for the roofline: K steps once more with the chunk overlap switched off, so that every kernel runs
         # alone on the stream and its CUDA-event bracket measures that kernel only
+        torch.cuda.synchronize()
+        side[:] = []                     # the serial pass and everything after it run on the current stream
         ck.set_overlap(False); ck.set_stage_timing(True)
         es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         es0.record()
@@ -495,6 +534,12 @@ def run_native(args):
                            "cache": "%d distinct resident input batches cycled (%.0f MB aggregate > 126 MB L2)" % (NB, NB * n * 96 / 1e6) if wl != "rbs" else "edge set re-uploaded from host every step"},
                 "e2e": out["e2e"], "gpu_launches": out["gpu_launches"], "clocks": out["clocks"], "roofline": out["roofline"],
                 "path_stats": out.get("path_stats")}
+        if "caller_streams" in out:
+            line["config"]["caller_streams"] = out["caller_streams"]
+            line["config"]["caller_streams_note"] = ("the resident steps are issued on %d caller streams in turn (each with its own output buffers; the library rotates its scratch "
+                                                     "lanes per call): step i+1's projection kernel fills the tail of step i's collision kernel; one_caller_stream = the same "
+                                                     "steps on one stream" % out["caller_streams"])
+            line["one_caller_stream"] = out["one_caller_stream"]
         if "cpu_baseline" in out:
             line["cpu_baseline"] = out["cpu_baseline"]
         if extra:
