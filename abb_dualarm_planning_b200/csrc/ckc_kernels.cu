@@ -324,11 +324,6 @@ __device__ __forceinline__ void collide_block(const ckc_world_dev& w, const coll
                 if (!skip) {
                     const box32 A = load_box(w.nodes + pr.node_a + na);
                     const box32 B = load_box(w.nodes + pr.node_b + nb);
-#ifdef CKC_PREFETCH_CHILDREN
-                    /* the children (siblings are adjacent) are what the next round loads if this pair survives: start their way into L1 now */
-                    if (A.child >= 0) { const ckc_node* c = w.nodes + pr.node_a + A.child; asm volatile("prefetch.global.L1 [%0];" :: "l"(c)); asm volatile("prefetch.global.L1 [%0];" :: "l"(c + 1)); }
-                    if (B.child >= 0) { const ckc_node* c = w.nodes + pr.node_b + B.child; asm volatile("prefetch.global.L1 [%0];" :: "l"(c)); asm volatile("prefetch.global.L1 [%0];" :: "l"(c + 1)); }
-#endif
                     float gap6;
                     const bool far = boxes_farther_than(A, F + 12 * pr.frame_a, B, F + 12 * pr.frame_b, w.cull_tol, gap6);
                     if (!far) {

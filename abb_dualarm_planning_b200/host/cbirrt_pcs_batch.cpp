@@ -19,7 +19,7 @@
  * One query (n = 1) therefore behaves like the reference's serial planner; n = 500 runs the reference's benchmark
  * protocol (500 repetitions of the same query, run/plan_PCS.cpp:300-330) in the time of a few.
  *
- * usage: cbirrt_pcs_batch <env> <n_queries> <max_step> <seed> <out.txt> [workers] [pcs|gd] [max_rounds]
+ * usage: cbirrt_pcs_batch <env> <n_queries> <max_step> <seed> <out.txt> [workers] [pcs|gd|hb] [max_rounds]
  * flavour gd = planners/CBiRRT_GD.cpp: 12-D distance, IKproject(dstate) = kdl::GD + limits + collision (ckc_gd_validate),
  * checkMotionRBS(s1, s2) (ckc_gd_check_motion_rbs); rows then carry -1 for the branch / edge columns.
  * out.txt: per solved query "query k nodes m rounds r" followed by m rows
@@ -112,6 +112,7 @@ struct Ensemble {
     ckc_ctx* ctx = nullptr;
     double max_step = 1.0;
     bool gd = false;                 /* CBiRRT-GD (planners/CBiRRT_GD.cpp) instead of CBiRRT-PCS */
+    bool hb = false;                 /* CBiRRT-HB (planners/CBiRRT_HB.cpp): kdl::GD projection, IK-branch identification, APC (PCS) local connection */
     int window = 64;                 /* growTree steps asked per round and query (CBiRRT-PCS); 1 = the reference's step-by-step order */
     std::vector<Query> qs;
     long calls = 0, items = 0;
@@ -174,11 +175,9 @@ struct Ensemble {
         } else { memcpy(Q.dstate, Q.target, sizeof(Q.dstate)); Q.reach = true; }
         if (Q.mode == 1 || !Q.reach) { Q.ik[0] = Q.ik[1] = -1; Q.wait = W_PROJECT; return; }
         if (gd) { Q.wait = W_RBS0; return; }       /* CBiRRT_GD.cpp:183-206: no branch bookkeeping */
-        /* the state belongs to the opposite tree and already satisfies the constraint */
+        /* the state belongs to the opposite tree and already satisfies the constraint (CBiRRT_HB.cpp:205-212) */
         Q.ik[0] = Q.target_ik[0]; Q.ik[1] = Q.target_ik[1];
-        if (nmn.ik[0] == Q.ik[0]) Q.active_chain = 0;
-        else if (nmn.ik[1] == Q.ik[1]) Q.active_chain = 1;
-        else { end_grow(Q); return; }
+        if (nmn.ik[0] != Q.ik[0] && nmn.ik[1] != Q.ik[1]) { end_grow(Q); return; }
         Q.wait = W_RBS0;
     }
 
@@ -186,7 +185,7 @@ struct Ensemble {
     void advance(Query& Q) {
         while (!Q.solved && Q.wait == W_NONE) {
             if (Q.stage == 0) begin_iteration(Q);
-            if (gd) grow_head(Q);
+            if (gd || hb) grow_head(Q);
             else if (Q.count == 0) end_grow(Q);
             else build_window(Q);
         }
@@ -216,6 +215,7 @@ struct Ensemble {
             }
             if (!live) break;
             if (gd) { run_gd_steps(idx, q, qo, qa, qb, valid, res, nchk); continue; }
+            if (hb) { run_hb_steps(idx, q, qo, qa, qb, ac, ik, id, valid, res, nchk); continue; }
             run_pcs_steps(idx, q, qo, qa, qb, ac, ik, id, ok, valid, res, nchk);
         }
     }
@@ -410,6 +410,73 @@ struct Ensemble {
         }
     }
 
+    /* CBiRRT-HB (planners/CBiRRT_HB.cpp:160-246): the step is projected with kdl::GD + limits + collision (IKproject(dstate),
+     * StateValidityCheckerHB.cpp:109-122 -> ckc_gd_validate), BOTH IK branches of the projected state are identified from scratch
+     * (:199 -> ckc_identify_ik), growTree returns when neither branch matches the neighbour's (:211), and the edge is checked with the
+     * APC bisection, active chain 0 where that branch agrees, then chain 1 (:217-221 -> ckc_pcs_check_motion_rbs).  The Newton
+     * projection moves all twelve joints, so the steps of a growTree call cannot be asked as one window: one step per round. */
+    void run_hb_steps(std::vector<int>& idx, std::vector<double>& q, std::vector<double>& qo, std::vector<double>& qa, std::vector<double>& qb,
+                      std::vector<int8_t>& ac, std::vector<int8_t>& ik, std::vector<int8_t>& id, std::vector<uint8_t>& valid, std::vector<uint8_t>& res,
+                      std::vector<int32_t>& nchk) {
+        idx.clear();
+        for (size_t k = 0; k < qs.size(); k++) if (!qs[k].solved && qs[k].wait == W_PROJECT) idx.push_back((int)k);
+        if (!idx.empty()) {
+            const size_t m = idx.size();
+            q.resize(m * 12); qo.resize(m * 12); valid.resize(m); id.resize(m * 2);
+            for (size_t i = 0; i < m; i++) memcpy(&q[12 * i], qs[idx[i]].dstate, 96);
+            mark();
+            check(ckc_gd_validate(ctx, (int64_t)m, q.data(), qo.data(), valid.data()), m, 0);
+            mark();
+            check(ckc_identify_ik(ctx, (int64_t)m, qo.data(), id.data()), m, 1);      /* rows of rejected samples are ignored */
+            for (size_t i = 0; i < m; i++) {
+                Query& Q = qs[idx[i]];
+                if (!valid[i]) { end_grow(Q); continue; }                                     /* :192-193 */
+                memcpy(Q.dstate, &qo[12 * i], 96);
+                Q.ik[0] = id[2 * i]; Q.ik[1] = id[2 * i + 1];                                 /* :199 */
+                const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
+                if (nmn.ik[0] != Q.ik[0] && nmn.ik[1] != Q.ik[1]) { end_grow(Q); continue; } /* :211-212 */
+                Q.wait = W_RBS0;
+            }
+        }
+        for (int pass = 0; pass < 2; pass++) {
+            idx.clear();
+            for (size_t k = 0; k < qs.size(); k++) {
+                Query& Q = qs[k];
+                if (Q.solved || Q.wait != (pass == 0 ? W_RBS0 : W_RBS1)) continue;
+                const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
+                if (nmn.ik[pass] == Q.ik[pass]) idx.push_back((int)k);
+                else if (pass == 0) Q.wait = W_RBS1;
+                else { Q.xmotion = Q.nm; end_grow(Q); }
+            }
+            if (idx.empty()) continue;
+            const size_t m = idx.size();
+            qa.resize(m * 12); qb.resize(m * 12); ac.resize(m); ik.resize(m); res.resize(m); nchk.resize(m);
+            for (size_t i = 0; i < m; i++) {
+                Query& Q = qs[idx[i]];
+                const Node& nmn = Q.t[Q.g_tree].n[Q.nm];
+                memcpy(&qa[12 * i], nmn.q, 96); memcpy(&qb[12 * i], Q.dstate, 96);
+                ac[i] = (int8_t)pass; ik[i] = (int8_t)nmn.ik[pass];
+            }
+            mark();
+            check(ckc_pcs_check_motion_rbs(ctx, (int64_t)m, qa.data(), qb.data(), ac.data(), ik.data(), res.data(), nchk.data()), m, 2);
+            for (size_t i = 0; i < m; i++) {
+                Query& Q = qs[idx[i]];
+                if (!res[i]) {
+                    if (pass == 0) Q.wait = W_RBS1;
+                    else { Q.xmotion = Q.nm; end_grow(Q); }                                   /* :243-246 */
+                    continue;
+                }
+                Node nn;                                                                      /* :225-236 */
+                memcpy(nn.q, Q.dstate, 96); nn.ik[0] = Q.ik[0]; nn.ik[1] = Q.ik[1];
+                nn.parent = Q.nm; nn.a_chain = pass; nn.e_ac = pass; nn.e_ik = Q.t[Q.g_tree].n[Q.nm].ik[pass];
+                Q.t[Q.g_tree].n.push_back(nn);
+                Q.nm = (int)Q.t[Q.g_tree].n.size() - 1; Q.xmotion = Q.nm;
+                Q.wait = W_NONE;
+                if (Q.reach) { Q.reached = true; end_grow(Q); }                               /* :238-241 */
+            }
+        }
+    }
+
     void check(int rc, size_t m, int kind) {
         if (rc != CKC_OK) { fprintf(stderr, "ckc: %s\n", ckc_last_error(ctx)); exit(-1); }
         t_kind[kind] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_mark).count();
@@ -419,13 +486,14 @@ struct Ensemble {
 };
 
 int main(int argc, char** argv) {
-    if (argc < 6) { fprintf(stderr, "usage: %s <env> <n_queries> <max_step> <seed> <out.txt> [workers] [pcs|gd] [max_rounds]\n", argv[0]); return 2; }
+    if (argc < 6) { fprintf(stderr, "usage: %s <env> <n_queries> <max_step> <seed> <out.txt> [workers] [pcs|gd|hb] [max_rounds]\n", argv[0]); return 2; }
     const int env = atoi(argv[1]), nq = atoi(argv[2]); const double max_step = atof(argv[3]); const uint64_t seed = strtoull(argv[4], nullptr, 10);
     /* workers = 0: SEQUENTIAL mode -- the queries run one after another, each alone on the device (single-query latency, what the
      * reference's 500-repetition benchmark measures); the summary then also carries latency_mean / median / max */
     const bool sequential = argc > 6 && atoi(argv[6]) == 0;
     const int workers = std::max(1, std::min(argc > 6 ? atoi(argv[6]) : 1, std::max(nq, 1)));
     const bool gd = argc > 7 && strcmp(argv[7], "gd") == 0;
+    const bool hb = argc > 7 && strcmp(argv[7], "hb") == 0;
     const int max_rounds = argc > 8 ? atoi(argv[8]) : 20000;
     const char* mesh = getenv("CKC_MESH_PATH"); const char* dev = getenv("CKC_DEVICE");
     const double* start = env == 2 ? kStart2 : kStart1; const double* goal = env == 2 ? kGoal2 : kGoal1;
@@ -434,7 +502,7 @@ int main(int argc, char** argv) {
     std::vector<Ensemble> E(workers);
     int8_t id[4]; uint8_t hit[2];
     for (int w = 0; w < workers; w++) {
-        E[w].max_step = max_step; E[w].gd = gd;
+        E[w].max_step = max_step; E[w].gd = gd; E[w].hb = hb;
         if (getenv("CKC_PLAN_WINDOW")) E[w].window = std::max(1, atoi(getenv("CKC_PLAN_WINDOW")));
         if (ckc_create(&E[w].ctx, env, mesh ? mesh : "./simulator", dev ? atoi(dev) : 0) != CKC_OK) { fprintf(stderr, "ckc_create failed\n"); return 1; }
     }
@@ -525,7 +593,7 @@ int main(int argc, char** argv) {
     }
     fprintf(fp, "summary queries %d solved %d seconds %.6f ms_per_query %.4f workers %d gpu_calls %ld items %ld mean_rounds %.1f mean_path_nodes %.1f mean_tree_nodes %.1f max_step %.3f env %d flavour %s sequential %d latency_mean_ms %.4f latency_median_ms %.4f latency_max_ms %.4f\n",
             nq, solved, secs, 1e3 * secs / std::max(nq, 1), sequential ? 0 : workers, calls, items, solved ? (double)rounds / solved : 0.0, solved ? (double)path_nodes / solved : 0.0,
-            (double)nodes_trees / std::max(nq, 1), max_step, env, gd ? "gd" : "pcs", sequential ? 1 : 0, lmean, lmed, lmax);
+            (double)nodes_trees / std::max(nq, 1), max_step, env, gd ? "gd" : (hb ? "hb" : "pcs"), sequential ? 1 : 0, lmean, lmed, lmax);
     fclose(fp);
     printf("queries %d solved %d in %.3f s (%.3f ms per query), %d workers, %ld batched calls, %.1f items per call\n", nq, solved, secs, 1e3 * secs / std::max(nq, 1),
            workers, calls, calls ? (double)items / calls : 0.0);

@@ -582,7 +582,7 @@ def extra_measurements(ck, sampling, torch, dev, stream):
                 env = dict(os.environ, CKC_MESH_PATH=os.path.join(REPO, "abb_dualarm_planning_b200", "data", "meshes.ckcmesh"),
                            CKC_DEVICE=str(torch.cuda.current_device()))
                 plan = {}
-                for flav, step, ref_ms in (("pcs", "1.0", 218), ("gd", "2.6", 128)):
+                for flav, step, ref_ms in (("pcs", "1.0", 218), ("gd", "2.6", 128), ("hb", "1.0", None)):
                     one = _planner_run(exe, env, 40, step, flav, 0, td)           # workers = 0: 40 queries one after another, each alone on the device
                     many = _planner_run(exe, env, 500, step, flav, 4, td)
                     plan["cbirrt_" + flav] = {
@@ -593,7 +593,9 @@ def extra_measurements(ck, sampling, torch, dev, stream):
                         "reference_published_ms_per_query": ref_ms,
                         "note": "latency = mean wall time of one env-1 start-to-goal query run ALONE on the device (40 seeds, one after another) -- what BASELINE.md's %d ms "
                                 "measures (mean of 500 runs, there on the author's CPU); throughput = wall time of 500 concurrent queries / 500 (lock-step ensemble, "
-                                "host/cbirrt_pcs_batch.cpp, 4 workers) -- a different quantity, not comparable with the published latency" % ref_ms}
+                                "host/cbirrt_pcs_batch.cpp, 4 workers) -- a different quantity, not comparable with the published latency" % (ref_ms or 0)}
+                    if ref_ms is None:
+                        plan["cbirrt_" + flav]["note"] = "CBiRRT-HB restated (kdl::GD projection, IK-branch identification, APC local connection); no published figure in BASELINE.md"
                     if flav == "pcs":          # batching inside ONE query: a growTree call's run of steps as one window (same tree as step by step)
                         sbs = _planner_run(exe, dict(env, CKC_PLAN_WINDOW="1"), 40, step, flav, 0, td)
                         plan["cbirrt_pcs"].update({"window_steps_per_round": 64, "latency_ms_1_query_step_by_step": float(sbs["latency_mean_ms"]),

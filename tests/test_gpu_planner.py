@@ -89,6 +89,22 @@ def test_cbirrt_gd_ensemble_paths_are_valid(tmp_path, oracle):
         assert (ok == 1).all()
 
 
+def test_cbirrt_hb_ensemble_paths_are_valid(tmp_path, oracle):
+    """the hybrid flavour (planners/CBiRRT_HB.cpp): kdl::GD projection of every step, both IK branches identified, APC bisection as local
+    connection -- milestones closed on both chains with the recorded branches, collision free, every edge accepted by the oracle's PCS
+    checkMotionRBS with the recorded arguments"""
+    paths, summary, _ = _plan(tmp_path, 12, 1.0, 11, "hb", workers=2)
+    assert int(summary["solved"]) == 12 == len(paths) and summary["flavour"] == "hb"
+    for P in paths:
+        q = P[:, :12]; ikn = P[:, 13:15].astype(int); e = P[:, 15:18].astype(int)
+        assert np.abs(q[0] - START).max() == 0 and np.abs(q[-1] - GOAL).max() == 0
+        assert (oracle.collision_state(q) == 0).all()
+        assert (oracle.identify_state_ik(q) == ikn).all()
+        a = np.where(e[:-1, 2:3] == 0, q[:-1], q[1:]); b = np.where(e[:-1, 2:3] == 0, q[1:], q[:-1])
+        ok, _ = oracle.pcs_check_motion_rbs(a, b, e[:-1, 0].astype(np.int8), e[:-1, 1].astype(np.int8))
+        assert (ok == 1).all()
+
+
 def test_prm_pcs_roadmap_path_is_valid(tmp_path, oracle):
     """the roadmap flavour (planners/PRM_PCS.cpp): batched sample_q + batched addMilestone connections"""
     out = str(tmp_path / "prm.txt")
