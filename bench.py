@@ -582,7 +582,7 @@ def extra_measurements(ck, sampling, torch, dev, stream):
                 env = dict(os.environ, CKC_MESH_PATH=os.path.join(REPO, "abb_dualarm_planning_b200", "data", "meshes.ckcmesh"),
                            CKC_DEVICE=str(torch.cuda.current_device()))
                 plan = {}
-                for flav, step, ref_ms in (("pcs", "1.0", 218), ("gd", "2.6", 128), ("hb", "1.0", None)):
+                for flav, step, ref_ms in (("pcs", "1.0", 218), ("gd", "2.6", 128), ("hb", "1.4", 342)):
                     one = _planner_run(exe, env, 40, step, flav, 0, td)           # workers = 0: 40 queries one after another, each alone on the device
                     many = _planner_run(exe, env, 500, step, flav, 4, td)
                     plan["cbirrt_" + flav] = {
@@ -593,18 +593,16 @@ def extra_measurements(ck, sampling, torch, dev, stream):
                         "reference_published_ms_per_query": ref_ms,
                         "note": "latency = mean wall time of one env-1 start-to-goal query run ALONE on the device (40 seeds, one after another) -- what BASELINE.md's %d ms "
                                 "measures (mean of 500 runs, there on the author's CPU); throughput = wall time of 500 concurrent queries / 500 (lock-step ensemble, "
-                                "host/cbirrt_pcs_batch.cpp, 4 workers) -- a different quantity, not comparable with the published latency" % (ref_ms or 0)}
-                    if ref_ms is None:
-                        plan["cbirrt_" + flav]["note"] = "CBiRRT-HB restated (kdl::GD projection, IK-branch identification, APC local connection); no published figure in BASELINE.md"
+                                "host/cbirrt_pcs_batch.cpp, 4 workers) -- a different quantity, not comparable with the published latency" % ref_ms}
                     if flav == "pcs":          # batching inside ONE query: a growTree call's run of steps as one window (same tree as step by step)
                         sbs = _planner_run(exe, dict(env, CKC_PLAN_WINDOW="1"), 40, step, flav, 0, td)
                         plan["cbirrt_pcs"].update({"window_steps_per_round": 64, "latency_ms_1_query_step_by_step": float(sbs["latency_mean_ms"]),
                                                    "gpu_calls_per_query_step_by_step": int(sbs["gpu_calls"]) / max(int(sbs["queries"]), 1)})
                 lexe = os.path.join(REPO, "abb_dualarm_planning_b200", "host", "lazy_gd_batch")
-                if os.path.exists(lexe):           # BASELINE configs[3] names SBL_GD: planners/SBL_GD.cpp restated over the C ABI, max step 0.6 (run/plan_GD.cpp:289)
+                if os.path.exists(lexe):           # BASELINE configs[3] names SBL_GD: planners/SBL_GD.cpp restated over the C ABI, max step 0.8 (the best step of BASELINE.md)
                     def lazy(nq, workers):
                         outp = os.path.join(td, "sbl_%d.txt" % nq)
-                        subprocess.run([lexe, "sbl", "1", str(nq), "0.6", "7", outp, str(workers)], env=env, capture_output=True, timeout=600, check=True)
+                        subprocess.run([lexe, "sbl", "1", str(nq), "0.8", "7", outp, str(workers)], env=env, capture_output=True, timeout=600, check=True)
                         t = open(outp).read().strip().split("\n")[-1].split()
                         return dict(zip(t[1::2], t[2::2]))
                     one, many = lazy(40, 0), lazy(500, 4)
@@ -612,7 +610,8 @@ def extra_measurements(ck, sampling, torch, dev, stream):
                                       "latency_max_ms_1_query": float(one["latency_max_ms"]), "queries_for_latency": int(one["queries"]), "solved_for_latency": int(one["solved"]),
                                       "gpu_calls_per_query": int(one["gpu_calls"]) / max(int(one["queries"]), 1),
                                       "throughput_ms_per_query_500": float(many["ms_per_query"]), "solved_of_500": int(many["solved"]),
-                                      "note": "SBL_GD restated (host/lazy_gd_batch.cpp); latency = one query alone, mean of 40 seeds; the reference's matlab/Benchmark_* logs for SBL_GD are not in the tree (BASELINE.md)"}
+                                      "reference_published_ms_per_query": 163,
+                                      "note": "SBL_GD restated (host/lazy_gd_batch.cpp), max step 0.8 (the reference's best, BASELINE.md: 163 ms per query on the author's CPU); latency = one query alone, mean of 40 seeds"}
                 ex["planning"] = plan
     except Exception as e:       # an extra, never the metric
         ex["planning"] = {"not_run": repr(e)}
