@@ -86,6 +86,10 @@ struct ckc_ctx {
     int64_t pipe_chunk = 1 << 18;       /* largest pipelined chunk of the host entry points (samples); a call is cut into ~4 chunks
                                            of 2^16 .. pipe_chunk samples (measured: 2^18 beats 2^17 by 10 % on S-GD, 2^16 loses 20 %) */
     bool gd_fan = false;                /* fan GD batches out over the lanes on the _dev paths (CKC_GD_FAN) */
+    bool pcs_fan = false;               /* the same for PCS batches (CKC_PCS_FAN).  Round 1 fanned them out (1.24e9 -> 1.9e9 configs/s); since the collision
+                                           kernel finishes its heavy configurations inside the launch, one launch per batch is faster (2.08e9 -> 2.33e9), and the
+                                           overlap between batches comes from the CALLER issuing on two streams (3.06e9).  A fanned-out call uses all lanes and
+                                           the context's fork event: only one such call may be in flight per context */
     int pipe_taper = 0;                 /* the last chunk of a pipelined host call is halved this many times (CKC_PIPE_TAPER) */
     int pipe_taper_front = 0;           /* the first chunk halved this many times (CKC_PIPE_TAPER_FRONT) */
     int64_t pipe_min_chunk = 1 << 14;
@@ -583,6 +587,8 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
     ctx->timeline_copies = getenv("CKC_TIMELINE") != nullptr;
     ch = getenv("CKC_PIPE_TAPER");
     if (ch && atoi(ch) >= 0 && atoi(ch) <= 8) ctx->pipe_taper = atoi(ch);
+    const char* pf = getenv("CKC_PCS_FAN");
+    if (pf) ctx->pcs_fan = atoi(pf) != 0;
     const char* gf = getenv("CKC_GD_FAN");
     if (gf) ctx->gd_fan = atoi(gf) != 0;
     const char* hl = getenv("CKC_HOST_LANES");
@@ -1031,7 +1037,7 @@ extern "C" int ckc_pcs_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, 
     if (ctx && !ctx->children.empty()) return fail(ctx, CKC_ERR_ARG, "device-resident entry points take a single-device context");
     if (!ctx || n < 0 || !d_q || !d_ik || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    return dev_fanout(ctx, (cudaStream_t)stream, n, true, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
+    return dev_fanout(ctx, (cudaStream_t)stream, n, ctx->pcs_fan, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
         /* the projected configurations are needed by the collision stage: the caller's buffer or an internal one */
         double* qo; ckc_layout lo;
         if (d_q_out) { qo = d_q_out + off; lo = soa(n); }
@@ -1045,7 +1051,7 @@ extern "C" int ckc_spcs_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_
     if (ctx && !ctx->children.empty()) return fail(ctx, CKC_ERR_ARG, "device-resident entry points take a single-device context");
     if (!ctx || n < 0 || !d_valid) return fail(ctx, CKC_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    return dev_fanout(ctx, (cudaStream_t)stream, n, true, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
+    return dev_fanout(ctx, (cudaStream_t)stream, n, ctx->pcs_fan, [&](ckc_lane& L, int64_t off, int64_t c, cudaStream_t st) -> int {
         double* qo; ckc_layout l;
         if (d_q_out) { qo = d_q_out + off; l = soa(n); }
         else { CU(L.qout.reserve((size_t)c * 96)); qo = L.qout.as<double>(); l = soa(c); }

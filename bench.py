@@ -297,7 +297,7 @@ def run_native(args):
         d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
         d_valid = torch.empty(n, dtype=torch.uint8, device=dev)
         # caller streams of the resident GD steps: with 2, consecutive steps are issued on alternating streams with their own output buffers
-        NS = max(1, args.streams) if wl == "gd" else 1
+        NS = max(1, args.streams)
         side[:] = [torch.cuda.Stream(device=dev) for _ in range(NS)] if NS > 1 else []
         outs = [(d_qout, d_valid)] + [(torch.empty_like(d_qout), torch.empty_like(d_valid)) for _ in range(NS - 1)]
         torch.cuda.synchronize()
@@ -310,7 +310,10 @@ def run_native(args):
                 qo, va = outs[slot]
                 ck.gd_validate_dev(n, d_q[b].data_ptr(), qo.data_ptr(), va.data_ptr(), side[slot].cuda_stream if side else stream)
             else:
-                ck.pcs_validate_dev(n, d_q[b].data_ptr(), None, d_ik[b].data_ptr(), d_qout.data_ptr(), d_ok.data_ptr(), d_valid.data_ptr(), stream)
+                slot = step_no[0] % len(side) if side else 0
+                step_no[0] += 1
+                qo, va = outs[slot]
+                ck.pcs_validate_dev(n, d_q[b].data_ptr(), None, d_ik[b].data_ptr(), qo.data_ptr(), d_ok.data_ptr(), va.data_ptr(), side[slot].cuda_stream if side else stream)
 
         for w in range(W):
             step_dev(w % NB)
