@@ -188,7 +188,7 @@ FLOP_TRI_TEST = 1000.0
 MIN_TIMED_S = 0.5          # the timed region repeats the K steps until it is at least this long
 
 
-def collide_roofline(stats, kms, kl, peak32, peak64, stage_share, extra=None):
+def collide_roofline(stats, kms, kl, peak32, peak64, stage_share, extra=None, capture="k_collide"):
     """k_collide: instruction-issue / latency bound FP32 + integer code (ncu: profiles/r2_ncu_collide.txt), not an FP64 kernel.  achieved =
     the work the kernel EXECUTED by its own counters (box tests x 384 flop + exact triangle tests x 1000 flop) / its CUDA-event time,
     against the measured FP32 FMA-chain peak.  (The reference-work model of SURVEY 8d -- PQP's 116 full queries per configuration --
@@ -198,7 +198,7 @@ def collide_roofline(stats, kms, kl, peak32, peak64, stage_share, extra=None):
     ach = flop / dur / 1e12 if dur > 0 else 0.0
     ncu = {}
     try:
-        ncu = json.load(open(os.path.join(REPO, "profiles", "r2_traffic.json")))["k_collide"]
+        ncu = json.load(open(os.path.join(REPO, "profiles", "r2_traffic.json")))[capture]
     except Exception:
         pass
     r = {"bound": "issue/fp32", "kernel": "k_collide", "achieved": ach, "peak": peak32, "unit": "TFLOP/s", "frac": ach / peak32 if peak32 else None,
@@ -445,7 +445,7 @@ def run_native(args):
             sc = {k: serial_stats[k] * K / (steps_run + K) for k in ("bv_tests", "tri_tests", "collision_calls")}
             out["roofline"] = collide_roofline(sc, stages["collide"]["ms"], stages["collide"]["launches"], peak(32), peak(64), share,
                                                {"timing_note": timing_note, "hbm_gbs_algorithmic": (per_step * 200.0) / (ms * 1e-3) / 1e9,
-                                                "hbm_peak_gbs_measured": measured_hbm_peak()})
+                                                "hbm_peak_gbs_measured": measured_hbm_peak()}, capture="k_collide_pcs")
         out["path_stats"] = {"newton_iters_mean": stats["gd_iterations"] / per_step if wl == "gd" else None,
                              "fraction_passing_projection": stats["ik_feasible"] / per_step,
                              "collision_checks_per_step": stats["collision_calls"] / steps_run, "bv_tests_per_check": stats["bv_tests"] / max(stats["collision_calls"], 1),
@@ -570,13 +570,18 @@ def extra_measurements(ck, sampling, torch, dev, stream):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 8
+    two = [torch.cuda.Stream(device=dev) for _ in range(2)]                      # two caller streams with their own mask buffers, as in the resident steps
+    d_ok2 = torch.empty_like(d_ok); d_valid2 = torch.empty_like(d_valid)
     e0.record()
+    for st_ in two: st_.wait_event(e0)
     for r in range(reps):
-        ck.spcs_validate_seeded_dev(100 + r, 0, n, None, d_ok.data_ptr(), d_valid.data_ptr(), stream)
+        ck.spcs_validate_seeded_dev(100 + r, 0, n, None, (d_ok if r % 2 == 0 else d_ok2).data_ptr(), (d_valid if r % 2 == 0 else d_valid2).data_ptr(), two[r % 2].cuda_stream)
+    for st_ in two:
+        ev = torch.cuda.Event(); ev.record(st_); torch.cuda.current_stream().wait_event(ev)
     e1.record(); torch.cuda.synchronize()
     ex["pcs_seeded_configs_per_s"] = reps * n / (e0.elapsed_time(e1) * 1e-3)
     ex["pcs_seeded_note"] = "S-PCS samples generated on the device from the counter-based generator (no input traffic), %d samples x %d" % (n, reps)
-    del d_ok, d_valid
+    del d_ok, d_valid, d_ok2, d_valid2
     try:
         import tempfile
         exe = os.path.join(REPO, "abb_dualarm_planning_b200", "host", "cbirrt_pcs_batch")

@@ -172,12 +172,17 @@ int ckc_spcs_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64
 int ckc_gd_validate_dev(ckc_ctx* ctx, int64_t n, const double* d_q, double* d_q_out, uint8_t* d_valid, void* stream);
 int ckc_sgd_validate_seeded_dev(ckc_ctx* ctx, uint64_t seed, uint64_t i0, int64_t n, double* d_q_out,
                                 uint8_t* d_ok, uint8_t* d_valid, void* stream);
-/* The device-resident entry points cut a batch into a few chunks that run on internal streams (forked from / joined to the
- * caller's stream), overlapping the collision kernel of one chunk with the projection kernel of the next.  enable = 0 runs
- * every kernel in order on the caller's stream (used when single kernels are timed).  Default: enabled. */
+/* A device-resident call runs its kernels in order on the CALLER's stream with one of four internal scratch sets (rotated per call;
+ * a set's previous user is awaited through an event, whatever stream it ran on).  Calls issued on different caller streams therefore
+ * overlap on the device -- the way to get the collision tail of one batch hidden behind the projection of the next is to issue
+ * consecutive batches on two streams.  (CKC_PCS_FAN / CKC_GD_FAN = 1 instead cut ONE call into chunks on internal streams, forked
+ * from / joined to the caller's stream; only one such call may be in flight per context.)
+ * ckc_set_overlap(0): the host pipelines stop moving the collision stage to their high-priority stream and nothing fans out --
+ * every kernel runs alone and in order (used when single kernels are timed).  Default: enabled. */
 int ckc_set_overlap(ckc_ctx* ctx, int enable);
 /* Per-stage device timing (CUDA events recorded on the launching stream around each kernel stage; resolved lazily).
- * stage 0 = projection kernel (PCS / GD / RX), 1 = link frames, 2 = collision (both passes), 3 = RBS expand/push.
+ * stage 0 = projection kernel (PCS / GD / RX), 1 = unused since the link frames are computed inside the collision kernel (with
+ * CKC_TIMELINE set: the uploads of the host pipeline), 2 = collision, 3 = RBS expand / push / tail.
  * ms[s] = accumulated device milliseconds, launches[s] = number of timed stage executions since the last reset. */
 int ckc_set_stage_timing(ckc_ctx* ctx, int enable);
 int ckc_get_stage_times(ckc_ctx* ctx, double ms[4], int64_t launches[4]);

@@ -38,7 +38,7 @@ caps = [("r2_prof_gd_project.ncu-rep", "r2_ncu_gd_project.txt", "k_gd_project",
          "ncu --set full of k_collide<0> in the GD workload (31.5 k configurations per launch; link frames computed in the warp, heavy routine at the end of the same launch)",
          "31.5k configurations per launch (GD workload); algorithmic bytes = 31.5e3 x (96 B joints in + 1 B mask out) = 3.1e6; the rest is the hierarchy / triangle working set entering L2 once per (cold, profiler-serialised) launch"),
         ("r2_prof_collide_pcs.ncu-rep", "r2_ncu_collide_pcs.txt", "k_collide_pcs",
-         "ncu --set full of k_collide<0> in the PCS workload (one 250 k-sample chunk: ~6 k configurations per launch)", "one pipeline chunk of the PCS workload")]
+         "ncu --set full of k_collide<0> in the PCS workload (one launch per 1e6-sample batch: ~24 k configurations)", "24k configurations per launch (PCS workload, one launch per 1e6-sample batch); see k_collide for the DRAM note")]
 for rep, dst, key, header, note in caps:
     rp = os.path.join(G, rep)
     if not os.path.exists(rp):
