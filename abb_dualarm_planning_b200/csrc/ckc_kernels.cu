@@ -10,11 +10,14 @@
  *                       traversal of the OBB hierarchies with a shared-memory task stack; FP32 conservative box culling
  *                       (guard band), interpenetrating pairs first and split four ways, warp-cooperative FP64 PQP-exact
  *                       triangle distance at the leaves (9 lanes per triangle pair), __ballot_sync early-out on the first
- *                       hit, adaptive per-lane pair order.
- *   k_gd_project    K5  persistent grid with lane-level work stealing: Jacobian-free two-walk Newton iteration (kdl::GD);
+ *                       hit, adaptive per-lane pair order; configurations that stay undecided go to a deferred list and are finished
+ *                       by whole blocks (one test per thread) at the end of the same launch.
+ *   k_gd_project    K5  persistent grid with lane-level work stealing: Jacobian-free two-walk Newton iteration (kdl::GD), both walks
+ *                       unrolled over the compile-time axis sequence, the two collinear wrist joints merged (variant 2);
  *   k_gd_finish         dense post-processing, joint limits, work-list append.
- *   k_rbs_expand / k_rbs_push  K4: one level of the recursive-bisection frontier.
- *   k_isvalid_prepare / k_isvalid_combine: isValid(const ob::State*) around K2 / K3.
+ *   k_rbs_expand / k_rbs_push  K4: one level of the recursive-bisection frontier; k_rbs_tail: the thin levels in one cooperative launch.
+ *   k_isvalid_prepare / k_isvalid_combine: isValid(const ob::State*) around K3.
+ *   k_fk, k_ik, k_kdl_fk: the single FK / IK members as batches.
  *   k_rx_check, k_limits, k_identify_ik, k_compact_valid, k_update_pair_order, k_fma_peak, k_transpose: helpers.
  */
 #include "ckc_device.cuh"
