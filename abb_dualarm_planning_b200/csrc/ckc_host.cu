@@ -75,7 +75,7 @@ struct ckc_ctx {
     cudaStream_t stream = nullptr;
     int64_t chunk = 1 << 20;            /* samples per internal batch */
     /* persistent device storage */
-    dev_buf d_nodes, d_tris, d_ctr, d_pairtab, d_static, d_pairhits, d_pairorder;
+    dev_buf d_nodes, d_tris, d_ctr, d_pairtab, d_static, d_pairhits, d_pairorder, d_bodies;
     dev_buf d_cidx, d_cq, d_ccount;                     /* compact outputs of the *_compact entry points (per chunk regions) */
     void* h_stage = nullptr; size_t h_stage_cap = 0;    /* pinned staging of the compact outputs */
     void* h_small = nullptr;                            /* pinned staging of the small-batch path (project_small) */
@@ -520,6 +520,7 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
     ctx->world.tris = ctx->d_tris.as<double>();
     {   /* pair table and static poses as global-memory tables */
         std::vector<ckc_pair_dev> pt(ctx->world.npairs);
+        std::vector<std::pair<int, int> > body_key;
         for (int p = 0; p < ctx->world.npairs; p++) {
             const ckc_pair& pr = ctx->world.pairs[p];
             pt[p].node_a = ctx->world.node_off[pr.mesh_a]; pt[p].node_b = ctx->world.node_off[pr.mesh_b];
@@ -537,6 +538,29 @@ extern "C" int ckc_create(ckc_ctx** out, int env, const char* mesh_path, int dev
             };
             const float rsum = (float)((radius(pr.mesh_a) + radius(pr.mesh_b) + ctx->world.cull_tol) * (1 + 1e-5) + 2e-3);
             memcpy(&pt[p].pad0, &rsum, 4);
+            /* the two bodies of the entry: distinct (frame, mesh) combinations, numbered in order of appearance */
+            int bid[2];
+            for (int side = 0; side < 2; side++) {
+                const int fr = side == 0 ? pr.frame_a : pr.frame_b, me = side == 0 ? pr.mesh_a : pr.mesh_b;
+                int found = -1;
+                for (size_t b = 0; b < body_key.size(); b++) if (body_key[b].first == fr && body_key[b].second == me) { found = (int)b; break; }
+                if (found < 0) { found = (int)body_key.size(); body_key.push_back(std::make_pair(fr, me)); }
+                bid[side] = found;
+            }
+            pt[p].pad1 = bid[0] | (bid[1] << 8);
+        }
+        if (body_key.size() > 32) { ckc_destroy(ctx); g_create_error = "pair table names more than 32 (frame, mesh) bodies"; return CKC_ERR_ARG; }
+        {
+            std::vector<float> bt(4 * 32, 0.0f);
+            for (size_t b = 0; b < body_key.size(); b++) {
+                const ckc_node& r = ctx->meshes[body_key[b].second].nodes[0];
+                bt[4 * b] = r.c[0]; bt[4 * b + 1] = r.c[1]; bt[4 * b + 2] = r.c[2];
+                const int fr = body_key[b].first; memcpy(&bt[4 * b + 3], &fr, 4);
+            }
+            if (ctx->d_bodies.reserve(bt.size() * 4) != cudaSuccess || cudaMemcpy(ctx->d_bodies.p, bt.data(), bt.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+                std::string msg = std::string("device upload: ") + cudaGetErrorString(cudaGetLastError()); ckc_destroy(ctx); g_create_error = msg; return CKC_ERR_CUDA;
+            }
+            ctx->world.body_tab = ctx->d_bodies.as<float4>(); ctx->world.nbodies = (int)body_key.size();
         }
         /* obstacle poses, then the base frames of the two robots: robot 1 R0 = Rz(0)^2 = I, robot 2 R02 = Rz(3.14159265/2)^2 */
         double stat[5][12];
@@ -601,7 +625,7 @@ extern "C" void ckc_destroy(ckc_ctx* ctx) {
     if (!ctx) return;
     if (!ctx->children.empty()) { for (ckc_ctx* c : ctx->children) ckc_destroy(c); delete ctx; return; }
     cudaSetDevice(ctx->device);
-    dev_buf* bufs[] = { &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_pairhits, &ctx->d_pairorder, &ctx->rbs_seg[0], &ctx->rbs_seg[1],
+    dev_buf* bufs[] = { &ctx->d_bodies, &ctx->d_pairtab, &ctx->d_static, &ctx->d_nodes, &ctx->d_tris, &ctx->d_ctr, &ctx->d_pairhits, &ctx->d_pairorder, &ctx->rbs_seg[0], &ctx->rbs_seg[1],
                         &ctx->rbs_cand, &ctx->rbs_pool, &ctx->rbs_eok, &ctx->rbs_nck, &ctx->rbs_hit, &ctx->rbs_eac, &ctx->rbs_eik, &ctx->rbs_nt, &ctx->rbs_in };
     for (dev_buf* b : bufs) b->release();
     for (int l = 0; l < CKC_NUM_LANES; l++) { ctx->lanes[l].release(); if (ctx->lanes[l].ev_done) cudaEventDestroy(ctx->lanes[l].ev_done); if (ctx->lanes[l].ev_p) cudaEventDestroy(ctx->lanes[l].ev_p); if (ctx->lanes[l].ev_c) cudaEventDestroy(ctx->lanes[l].ev_c); if (ctx->lanes[l].ev_up) cudaEventDestroy(ctx->lanes[l].ev_up); if (ctx->lanes[l].ev_busy) cudaEventDestroy(ctx->lanes[l].ev_busy);

@@ -44,6 +44,9 @@ struct ckc_world_dev {
     unsigned int* pair_hits;            /* [CKC_MAX_PAIRS] how often each table entry produced the first hit (decayed): adaptive processing order */
     const int* pair_order;              /* [CKC_MAX_PAIRS] table entries sorted by decreasing pair_hits; any order yields the same boolean */
     const double*   tris;               /* all meshes, concatenated, 9 doubles per triangle (FP64, as parsed) */
+    const float4* body_tab;             /* [nbodies] distinct (frame, mesh) combinations of the pair table: root-box centre (mesh frame) xyz, frame index as int bits in w;
+                                           a pair entry names its two bodies in pad1 (body_a | body_b << 8) -- k_collide transforms each centre once per configuration */
+    int nbodies;
     int node_off[CKC_NUM_MESHES];       /* first node of each mesh */
     int tri_off[CKC_NUM_MESHES];        /* first triangle of each mesh */
     int npairs;

@@ -248,6 +248,20 @@ __device__ __forceinline__ void collide_block(const ckc_world_dev& w, const coll
          * first round and leaves through the ballot early-out.  Most of the 116 entries are far apart in most configurations: the
          * pre-test replaces ~3 of the ~4 root rounds (480 instructions per lane each) by ~35 instructions per lane and entry */
         __syncwarp();
+        /* the root-box centre of every body (a (frame, mesh) combination the pair table names; <= 32) in world coordinates, one body per
+         * lane, once per configuration: a table entry's sphere test is then two shared-memory reads and seven FP32 operations instead of
+         * two box transforms (same arithmetic as root_spheres_close, same decisions) */
+        /* storage: the last 96 words of this warp's task stack -- seeding writes at most CKC_MAX_PAIRS entries from the bottom, and only
+         * after the last pre-test has been read (the ballots of the loop below order the two) */
+        static_assert(CKC_MAX_PAIRS + 96 <= CKC_STACK_CAP, "body centres share the warp's task stack during seeding");
+        float (*ctr)[3] = reinterpret_cast<float (*)[3]>(&sm.stack[wib][CKC_STACK_CAP - 96]);
+        if (lane < w.nbodies) {
+            const float4 b = __ldg(w.body_tab + lane);
+            const float* Fb = F + 12 * __float_as_int(b.w);
+#pragma unroll
+            for (int r = 0; r < 3; r++) ctr[lane][r] = Fb[3 * r] * b.x + Fb[3 * r + 1] * b.y + Fb[3 * r + 2] * b.z + Fb[9 + r];
+        }
+        __syncwarp();
         int top = 0;
         {
             uint32_t task[(CKC_MAX_PAIRS + 31) / 32]; bool keep[(CKC_MAX_PAIRS + 31) / 32]; int before[(CKC_MAX_PAIRS + 31) / 32];
@@ -257,7 +271,13 @@ __device__ __forceinline__ void collide_block(const ckc_world_dev& w, const coll
                 keep[it] = false; task[it] = 0;
                 if (k2 < w.npairs) {
                     const int p = __ldg(w.pair_order + k2);
-                    keep[it] = root_spheres_close(w, smem_pair(s_pairs, p), F);
+                    const int4 pb = s_pairs[2 * p + 1];                       /* frame_a, frame_b, radius sum (float bits), body_a | body_b << 8 */
+                    const float* ca = ctr[pb.w & 255]; const float* cb = ctr[pb.w >> 8];
+                    float d2 = 0;
+#pragma unroll
+                    for (int r = 0; r < 3; r++) d2 += (cb[r] - ca[r]) * (cb[r] - ca[r]);
+                    const float rs = __int_as_float(pb.z);
+                    keep[it] = !(d2 > rs * rs);                               /* NaN poses stay in (the reference reports them in collision) */
                     task[it] = (uint32_t)p << 22;
                 }
                 const unsigned mk = __ballot_sync(0xffffffffu, keep[it]);
