@@ -5,7 +5,7 @@
  *   identify_state_ik(q1, q2)          branches of the projected point       (shared with PCS)
  *   checkMotionRBS(q, q', ac, ik)      APC local connection to a second projected point
  * usage: test_dropin_hb <in.txt> <out.txt>     in: n then n lines "qa[12] qb[12]"
- * out: per line  va vb  ik0 ik1  ika0 ikb0(second point)  rbs   qa_projected[12]
+ * out: per line  va vb  ik0 ik1  ika0 ikb0(second point)  rbs   qa_projected[12]  qb_projected[12]
  */
 #include "StateValidityCheckerHB.h"
 
@@ -28,6 +28,7 @@ int main(int argc, char** argv) {
         }
         out << va << " " << vb << " " << ida[0] << " " << ida[1] << " " << idb[0] << " " << idb[1] << " " << rbs;
         for (int j = 0; j < 12; j++) out << " " << a[j];
+        for (int j = 0; j < 12; j++) out << " " << b[j];
         out << "\n";
     }
     srand(3);

@@ -156,9 +156,10 @@ def test_hb_dropin_class(tmp_path, oracle):
     assert (d.max(axis=1) < 2e-5).mean() >= 0.95
     same = both.copy(); same[both] = (ida[:, 0] >= 0) & (ida[:, 0] == idb[:, 0])
     ia = oracle.identify_state_ik(pa[same])[:, 0].astype(np.int8)
-    # the class ran the bisection on ITS projected points; the oracle's agree to ~1e-6, which does not move an RBS answer off a knife edge here
-    rbs_o, _ = oracle.pcs_check_motion_rbs(pa[same], pb[same], 0, ia)
-    assert (res[same][:, 6] == rbs_o).mean() >= 0.95 and same.sum() >= 10
+    # the class ran the bisection on ITS OWN projected points (columns 7:19 and 19:31): the oracle's bisection of exactly those end points
+    # must give the same answer for every edge (no tolerance: same inputs, bit-exact PCS path)
+    rbs_o, _ = oracle.pcs_check_motion_rbs(res[same][:, 7:19], res[same][:, 19:31], 0, ia)
+    assert (res[same][:, 6] == rbs_o).all() and same.sum() >= 10
     s = np.array([float(x) for x in lines[len(qa)].split()[1:]])
     assert oracle.gd_validate(s[None])[0][0] == 1             # the GD sampler returns a valid (closed, in limits, collision free) point
 
@@ -179,7 +180,7 @@ def _rx_rbs_oracle(oracle, a, b, eps, depth=0):
 def test_rx_dropin_class(tmp_path, oracle, gold):
     """relaxed-constraint flavour (StateValidityCheckerRX): residual test, validity, bisection over unprojected midpoints"""
     g = gold("rx_confs_eps0.7.npz")
-    eps = 0.7 * (1 + 1e-4)
+    eps = 0.7
     qa = g["q"][:60]
     rng = np.random.default_rng(11)
     qb = qa + rng.normal(size=qa.shape) * np.where(np.arange(60)[:, None] % 2 == 0, 0.01, 0.1)      # short and longer edges

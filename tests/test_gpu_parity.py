@@ -178,7 +178,9 @@ def test_rbs_degenerate_edges(ck, gold):
 
 def _gd_agreement(orc, qo, q_o, d):
     dm = d.max(axis=1)
-    assert (dm < TOL_Q).mean() > 0.99 and (dm < 1e-4).mean() >= 0.998
+    # measured on 100 000 seeds per environment (tools/gd_agreement_probe.py, profiles/r2_gd_agreement.txt): within 1e-6 rad on 99.92 % (env 1) /
+    # 99.81 % (env 2) of the samples, within 1e-4 on 99.986 % / 99.964 %, identical iteration counts and masks on all of them
+    assert (dm < TOL_Q).mean() > 0.995 and (dm < 1e-4).mean() >= 0.9985
     for i in np.where(dm >= 1e-6)[0]:                        # closure of every point that differs (reference tolerance: 0.1 mm)
         T = orc.kdl_fk(qo[i])
         assert abs(T[0, 3] - orc.kin.D) < 0.1 and abs(T[1, 3]) < 0.1 and abs(T[2, 3]) < 0.1 and np.abs(T[:3, :3] - np.eye(3)).max() < 2e-4
@@ -196,10 +198,10 @@ def test_gd_projection_vs_oracle(ck, oracle):
     # kdl::GD stops at eps = 1e-5 and KDL's GetRot() snaps rotation errors below 1e-6 to zero, so the converged point is only
     # defined to ~1e-5 rad by the reference algorithm itself; and Newton from a uniform seed is chaotic on a few samples:
     # an FMA and a non-FMA build of the SAME CPU restatement differ by > 1e-4 rad on 5 (env 1) / 39 (env 2) of 100 000 seeds
-    # (max 1.8 rad: another closed configuration).  Tolerance: 1e-6 rad (north star) on >= 99 %, 1e-4 on >= 99.8 %, and every
+    # (max 1.8 rad: another closed configuration).  Tolerance: 1e-6 rad (north star) on >= 99.5 %, 1e-4 on >= 99.85 %, and every
     # returned point -- the outliers included -- closes the chain.
     _gd_agreement(oracle, qo, q_o, d)
-    assert (np.abs(it - it_o) <= 1).mean() >= 0.998          # convergence test sits at 1e-5: one iteration of slack
+    assert (it == it_o).mean() >= 0.9995                     # measured: the same iteration count on every one of 100 000 seeds
     assert 8.5 < it.mean() < 10.5                           # reference statistics: ~9.5 Newton iterations from uniform seeds
 
 
@@ -219,7 +221,7 @@ def test_gd_million_sample_mask_vs_restatement(ck, gold):
     want = np.unpackbits(g["valid_bits"])[:n]
     valid, _ = ck.gd_validate(sampling.sample_gd(int(g["seed"]), 0, n))
     assert want.sum() == 14097
-    assert (valid != want).sum() <= 2          # measured 0; Newton from uniform seeds is chaotic on ~1e-4 of the samples (Oracle)
+    assert (valid != want).sum() == 0          # all 1 000 000 flags (the chaotic ~1e-4 of the samples move joints, none of them moved a flag)
 
 
 def test_gd_pinned_by_reference_closure_check(ck, gold):
@@ -273,8 +275,8 @@ def test_rx_validate_vs_oracle_and_fixtures(oracle, gold):
     from abb_dualarm_planning_b200 import Checker
     g = gold("rx_confs_eps0.7.npz")
     c1 = Checker(env=1)
-    valid, res = c1.rx_validate(g["q"], 0.7 * (1 + 1e-4))
-    ok_o, res_o = oracle.rx_check(g["q"], 0.7 * (1 + 1e-4))
+    valid, res = c1.rx_validate(g["q"], 0.7)
+    ok_o, res_o = oracle.rx_check(g["q"], 0.7)
     assert np.abs(res - res_o).max() < 1e-9
     want = ok_o & oracle.check_angle_limits(g["q"]) & (1 - oracle.collision_state(g["q"]).astype(np.uint8))
     assert (valid == want).all()
@@ -313,8 +315,8 @@ def test_env2_gd_rx_and_rbs_vs_oracle(oracle_env2, gold):
     valid, _ = c2.gd_validate(q)
     assert (valid == valid_o).all()
     g = gold("rx_confs_eps0.5_env2.npz")                    # configurations the reference's RX checker accepted in env 2
-    v, res = c2.rx_validate(g["q"], 0.5 * (1 + 1e-4))
-    ok_r, res_o = oracle_env2.rx_check(g["q"], 0.5 * (1 + 1e-4))
+    v, res = c2.rx_validate(g["q"], 0.5)
+    ok_r, res_o = oracle_env2.rx_check(g["q"], 0.5)
     assert np.abs(res - res_o).max() < 1e-9
     want = ok_r & oracle_env2.check_angle_limits(g["q"]) & (1 - oracle_env2.collision_state(g["q"]).astype(np.uint8))
     assert (v == want).all() and v.mean() > 0.9

@@ -146,7 +146,7 @@ def test_rx_fixtures(oracle, oracle_env2, gold):
     for name in ("rx_confs_eps0.7.npz", "rx_confs_eps1.0.npz", "rx_confs_eps0.5_env2.npz"):
         g = gold(name)
         orc = oracle if int(g["env"]) == 1 else oracle_env2
-        ok, res = orc.rx_check(g["q"], float(g["eps"]) * (1 + 1e-4))    # 6-digit text precision
+        ok, res = orc.rx_check(g["q"], float(g["eps"]))                 # no widening: every stored configuration stays below eps when recomputed
         assert ok.all()
         assert res.max() > 0.9 * float(g["eps"])              # the accepted set fills the bound
 
