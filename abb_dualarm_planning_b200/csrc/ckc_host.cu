@@ -737,7 +737,7 @@ static int run_collision_stage(ckc_ctx* ctx, ckc_lane& L, int64_t m_max, const d
                                uint8_t* d_hit, uint8_t* d_valid, uint8_t* d_pair_flags, cudaStream_t st, bool allow_hop = true) {
     if (m_max <= 0) return CKC_OK;
     CU(L.ovf.reserve((size_t)m_max * 4));
-    CU(L.bigstack.reserve((size_t)320 * 32768 * 4));      /* heavy routine: one 32 768-entry stack per block (<= 320 blocks); diagnostic form: 128 warps */
+    CU(L.bigstack.reserve((size_t)CKC_HEAVY_MAX_BLOCKS * 32768 * 4));      /* heavy routine: one 32 768-entry stack per block (<= 320 blocks); diagnostic form: 128 warps */
     /* on the lane's own stream the collision stage moves to the lane's HIGH-PRIORITY stream: its blocks then win the SM slots
      * that free up while the persistent projection kernels of the other lanes are still queued */
     const bool hop = allow_hop && ctx->overlap && st == L.st && L.st_hi;      /* RBS levels run alone: no hop, four stream operations less per level */
@@ -1421,7 +1421,7 @@ static int rbs_host(ckc_ctx* ctx, int flavour, int64_t n_edges, const double* qa
             if ((size_t)want_nodes > hit.cap) CU(hit.reserve((size_t)(want_nodes + want_nodes / 2)));
             if (rec && (size_t)want_nodes * 8 > nt.cap) CU(reserve_keep(nt, (size_t)(want_nodes + want_nodes / 2) * 8, (size_t)nnodes * 8, st));
             CU(L.ovf.reserve((size_t)(4 * tail_max) * 4));
-            CU(L.bigstack.reserve((size_t)320 * 32768 * 4));
+            CU(L.bigstack.reserve((size_t)CKC_HEAVY_MAX_BLOCKS * 32768 * 4));
             ckc_rbs_tail_state hs;
             hs.nseg = (int32_t)nseg; hs.nnodes = (int32_t)nnodes; hs.cur = cur; hs.levels = 0; hs.status = -1; hs.total_cand = 0;
             hs.max_seg = (int32_t)(2 * tail_max);

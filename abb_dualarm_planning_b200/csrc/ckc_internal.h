@@ -13,6 +13,9 @@
 #define CKC_NUM_DYN_FRAMES 18   /* frames that depend on the configuration */
 #define CKC_MAX_PAIRS 116
 #define CKC_FRAME_DOUBLES (CKC_NUM_DYN_FRAMES * 12)
+#ifndef CKC_HEAVY_MAX_BLOCKS
+#define CKC_HEAVY_MAX_BLOCKS 320    /* most blocks a collision launch may have: each owns a 32 768-entry global task stack for the heavy routine */
+#endif
 
 enum { CKC_M_BASE = 0, CKC_M_LINK1, CKC_M_LINK2, CKC_M_LINK3, CKC_M_LINK4, CKC_M_LINK5, CKC_M_LINK6, CKC_M_EE,
        CKC_M_TABLE, CKC_M_OBS, CKC_M_CONE, CKC_M_ROD };

@@ -32,7 +32,9 @@ using namespace ckc;
 #endif
 #define CKC_BIG_STACK_CAP 32768     /* global-memory task stack of the heavy routine (per block) and of the diagnostic per-pair form (per warp) */
 #define CKC_TRIQ_CAP 64
+#ifndef CKC_COLLIDE_WARPS
 #define CKC_COLLIDE_WARPS 8
+#endif
 
 /* ================================================================================================================ */
 /* K1                                                                                                                 */
@@ -457,8 +459,8 @@ k_collide(const ckc_world_dev w, const collide_args a) {
  * per step instead of 3), the task stack lives in global memory (32 768 entries per block).  A configuration with 450 near-tolerance
  * triangle pairs and 50 descent rounds costs one warp ~0.3 ms; here it is two triangle steps and ~25 rounds.  Same boolean:
  * the pruning test and the leaf test are the same functions, only the order of evaluation differs. */
-#define CKC_HEAVY_THREADS 256
-#define CKC_HEAVY_MAX_BLOCKS 320     /* size of the global stack buffer (ckc_host.cu reserves CKC_HEAVY_MAX_BLOCKS x CKC_BIG_STACK_CAP entries) */
+#define CKC_HEAVY_THREADS (CKC_COLLIDE_WARPS * 32)
+/* CKC_HEAVY_MAX_BLOCKS (ckc_internal.h): size of the global stack buffer (ckc_host.cu reserves CKC_HEAVY_MAX_BLOCKS x CKC_BIG_STACK_CAP entries) */
 #define CKC_HEAVY_TRIQ 1024
 __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp_tot, int& total) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
