@@ -298,7 +298,7 @@ __device__ __forceinline__ void collide_block(const ckc_world_dev& w, const coll
         __syncwarp();
 
         while (!hit) {
-            /* a configuration that is still undecided after this much work (defaults: 64 box rounds or 24 triangle steps, ~0.1 % of
+            /* a configuration that is still undecided after this much work (defaults: 128 box rounds or 24 triangle steps, ~0.1 % of
              * the IK-feasible S-PCS configurations: hundreds of triangle pairs within a few mm of the tolerance) would keep one
              * warp busy for 0.1 - 0.3 ms and set the duration of a small launch.  It goes to k_collide_heavy, where a block works on
              * it with one thread per test (~25 us of one SM per configuration, whatever its weight: lower thresholds lose, measured). */
@@ -628,7 +628,7 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     a.flush_n = flush_n < 1 ? 1 : (flush_n > CKC_TRIQ_CAP - 32 ? CKC_TRIQ_CAP - 32 : flush_n);      /* a round queues up to 32 leaf pairs on top of flush_n - 1 */
     a.likely_gap = likely_gap;
 
-    static const int defer_rounds = [] { const char* e = getenv("CKC_DEFER_ROUNDS"); return e ? atoi(e) : 64; }();
+    static const int defer_rounds = [] { const char* e = getenv("CKC_DEFER_ROUNDS"); return e ? atoi(e) : 128; }();
     static const int defer_tri = [] { const char* e = getenv("CKC_DEFER_TRI"); return e ? atoi(e) : 24; }();
     a.defer_rounds = defer_rounds; a.defer_tri = defer_tri;
     /* work_counter[0] next configuration, [1] next deferred entry, [2] deferred entries published (= *ovf_count), [3] deferred tickets */
