@@ -640,7 +640,8 @@ void ckc_launch_collide(const ckc_world_dev& w, const ckc_launch_cfg& cfg, const
     }
     /* persistent grid: exactly the resident blocks (the heavy routine's global-memory stack is indexed by the block) */
     int64_t blocks = (m_max + CKC_COLLIDE_WARPS - 1) / CKC_COLLIDE_WARPS;
-    const int64_t resident = std::min<int64_t>((int64_t)cfg.num_sms * CKC_COLLIDE_MINBLOCKS, CKC_HEAVY_MAX_BLOCKS);
+    static const int blocks_per_sm = [] { const char* e = getenv("CKC_K3_BLOCKS_PER_SM"); const int v = e ? atoi(e) : CKC_COLLIDE_MINBLOCKS; return v < 1 || v > CKC_COLLIDE_MINBLOCKS ? CKC_COLLIDE_MINBLOCKS : v; }();      /* occupancy experiments */
+    const int64_t resident = std::min<int64_t>((int64_t)cfg.num_sms * blocks_per_sm, CKC_HEAVY_MAX_BLOCKS);
     if (blocks > resident) blocks = resident;
     k_collide<false><<<(unsigned)blocks, CKC_COLLIDE_WARPS * 32, 0, st>>>(w, a);
 }
