@@ -51,6 +51,38 @@ def test_bad_arguments_and_io_errors():
     assert b"sm_100a" in L.ckc_version()
 
 
+def test_oversized_mesh_is_refused_at_create(tmp_path):
+    """the kernels pack (pair, node A, node B) and (pair, triangle A, triangle B) into one task word with 11 / 10-bit fields: a mesh with
+    more than 1 024 triangles must be refused at ckc_create (CKC_ERR_ARG) instead of aliasing bits into the pair index; a bad pack and a
+    truncated .tris file are I/O errors.  All of it is decided on the host before the first CUDA call, so this runs without a GPU."""
+    import struct
+    import numpy as np
+    from abb_dualarm_planning_b200 import load_library
+    from abb_dualarm_planning_b200.binding import MESH_PACK
+    L = load_library()
+    L.ckc_create_error.restype = C.c_char_p
+    blob = open(MESH_PACK, "rb").read()
+    assert blob[:8] == b"CKCMESH1"
+    nm = struct.unpack("<i", blob[8:12])[0]
+    off, out = 12, b"CKCMESH1" + struct.pack("<i", nm)
+    rng = np.random.default_rng(0)
+    for m in range(nm):
+        mid, n = struct.unpack("<ii", blob[off:off + 8]); off += 8
+        tri = blob[off:off + 72 * n]; off += 72 * n
+        if m == 3:                                             # Link3_r.tris has 1 000 triangles: 25 more are one too many bits
+            tri = tri + (rng.normal(size=(25, 9)) * 50).astype("<f8").tobytes(); n += 25
+        out += struct.pack("<ii", mid, n) + tri
+    big = tmp_path / "big.ckcmesh"; big.write_bytes(out)
+    ctx = C.c_void_p()
+    assert L.ckc_create(C.byref(ctx), 1, str(big).encode(), 0) == -1 and not ctx.value            # CKC_ERR_ARG
+    assert b"1024 triangles" in L.ckc_create_error()
+    bad = tmp_path / "bad.ckcmesh"; bad.write_bytes(blob[:1000])
+    assert L.ckc_create(C.byref(ctx), 1, str(bad).encode(), 0) == -2 and not ctx.value            # CKC_ERR_IO
+    d = tmp_path / "tris"; d.mkdir()
+    (d / "Base_r.tris").write_text("3\n0 0 0 1 0 0 0 1 0\n")                                    # header says 3 triangles, one present
+    assert L.ckc_create(C.byref(ctx), 1, str(d).encode(), 0) == -2 and not ctx.value
+
+
 def test_product_does_not_touch_the_oracle():
     """a product path that routes through oracle/ would void every parity claim"""
     pkg = os.path.join(REPO, "abb_dualarm_planning_b200")
