@@ -13,4 +13,4 @@ print('gd N=$N value %.3e e2e %.3e ms/step %.3f'%(d['value'],d['e2e']['value'],d
 for k in ('pcs','rbs'):
     r=d['extra'][k]; print(k,'value %.3e e2e %.3e ms/step %.3f'%(r['value'],r['e2e']['value'],r['ms_per_step']))
 PY
-python tools/multi_probe.py $N > gpurun_out/multi_probe.txt 2>&1; cat gpurun_out/multi_probe.txt
+[ "$N" = "8" ] && { python tools/multi_probe.py $N > gpurun_out/multi_probe.txt 2>&1; cat gpurun_out/multi_probe.txt; } || true
