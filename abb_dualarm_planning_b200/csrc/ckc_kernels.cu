@@ -27,6 +27,15 @@
 
 using namespace ckc;
 
+/* -DCKC_BOUNDS: every write into a task stack / leaf-pair queue and every node / triangle index is checked on the device (the kernel
+ * traps on a violation); compute-sanitizer is not available on the GPU pool, this build is its stand-in (tools/gpu/gpu_bounds.sh) */
+#ifdef CKC_BOUNDS
+#include <cassert>
+#define CKC_CHECK(cond) assert(cond)
+#else
+#define CKC_CHECK(cond) ((void)0)
+#endif
+
 #ifndef CKC_STACK_CAP
 #define CKC_STACK_CAP 512           /* per-warp shared-memory task stack (entries); 8 warps x (2016 + 1008 + 2048 + 256) B + 3712 B = 46.3 kB per block: two blocks stay inside the 100 kB shared-memory carve-out (the L1 keeps 156 kB for the hierarchy nodes) */
 #endif
@@ -288,7 +297,7 @@ __device__ __forceinline__ void collide_block(const ckc_world_dev& w, const coll
             }
 #pragma unroll
             for (int it = 0; it < (CKC_MAX_PAIRS + 31) / 32; it++)
-                if (keep[it]) stack[top - 1 - before[it]] = task[it];      /* first entry of the order on top */
+                if (keep[it]) { CKC_CHECK(top - 1 - before[it] >= 0 && top - 1 - before[it] < CKC_STACK_CAP - 96 && top <= cap); stack[top - 1 - before[it]] = task[it]; }      /* first entry of the order on top */
         }
         int ntri = 0;
         int rounds_box = 0, steps_tri = 0;
@@ -347,12 +356,15 @@ __device__ __forceinline__ void collide_block(const ckc_world_dev& w, const coll
                 bool skip = false;
                 if (kPerPair) skip = a.pair_flags[sample * CKC_MAX_PAIRS + p] != 0;      /* pair already decided */
                 if (!skip) {
+                    CKC_CHECK(p < w.npairs && pr.frame_a >= 0 && pr.frame_a < CKC_NUM_FRAMES && pr.frame_b >= 0 && pr.frame_b < CKC_NUM_FRAMES);
                     const box32 A = load_box(w.nodes + pr.node_a + na);
                     const box32 B = load_box(w.nodes + pr.node_b + nb);
+                    CKC_CHECK((A.child >= 0 ? A.child + 1 : ~A.child) < 2048 && (B.child >= 0 ? B.child + 1 : ~B.child) < 2048);
                     float gap6;
                     const bool far = boxes_farther_than(A, F + 12 * pr.frame_a, B, F + 12 * pr.frame_b, w.cull_tol, gap6);
                     if (!far) {
                         if (A.child < 0 && B.child < 0) {
+                            CKC_CHECK(~A.child < 1024 && ~B.child < 1024);
                             leafpair = true; tt = ((uint32_t)p << 20) | ((uint32_t)(~A.child) << 10) | (uint32_t)(~B.child);
                             likely = gap6 < a.likely_gap;             /* the two triangles' boxes are within ~2 mm along every face axis */
                         }
@@ -382,7 +394,7 @@ __device__ __forceinline__ void collide_block(const ckc_world_dev& w, const coll
             const unsigned mt = __ballot_sync(0xffffffffu, leafpair);
             const unsigned me = __ballot_sync(0xffffffffu, expand);
             const unsigned m4 = __ballot_sync(0xffffffffu, expand4);
-            if (leafpair) triq[ntri + __popc(mt & lt_mask)] = tt;
+            if (leafpair) { CKC_CHECK(ntri + __popc(mt & lt_mask) < CKC_TRIQ_CAP); triq[ntri + __popc(mt & lt_mask)] = tt; }
             ntri += __popc(mt);
             /* children of interpenetrating boxes go on top of the others: they are popped first, which takes a colliding
              * configuration to its hit in fewer rounds (any order gives the same boolean) */
@@ -392,6 +404,7 @@ __device__ __forceinline__ void collide_block(const ckc_world_dev& w, const coll
             const unsigned mshallow = me & ~md;
             int pos = top + 4 * __popc(m4 & lt_mask);
             if (expand) pos = top + 4 * __popc(m4) + (deep ? 2 * __popc(mshallow) + 2 * __popc(md & lt_mask) : 2 * __popc(mshallow & lt_mask));
+            CKC_CHECK(!(expand || expand4) || (pos >= 0 && pos + (expand4 ? 4 : 2) <= cap));
             if (expand) { stack[pos] = c1; stack[pos + 1] = c0; }
             if (expand4) { stack[pos] = c0 + (1u << 11) + 1u; stack[pos + 1] = c0 + (1u << 11); stack[pos + 2] = c0 + 1u; stack[pos + 3] = c0; }
             top += npush;
@@ -571,6 +584,7 @@ __device__ __forceinline__ void collide_heavy_block(const ckc_world_dev& w, cons
             const int cpos = block_exclusive_scan(nchild, s_tot, npush);
             const int lpos = block_exclusive_scan(leafpair ? 1 : 0, s_tot, nleaf);
             if (top + npush > CKC_BIG_STACK_CAP) { overflow = true; break; }
+            CKC_CHECK(top + cpos >= 0 && top + cpos + nchild <= CKC_BIG_STACK_CAP && (!leafpair || ntri + lpos < CKC_HEAVY_TRIQ));
             if (nchild == 2) { stack[top + cpos] = c1; stack[top + cpos + 1] = c0; }
             if (four) { stack[top + cpos] = c0 + (1u << 11) + 1u; stack[top + cpos + 1] = c0 + (1u << 11); stack[top + cpos + 2] = c0 + 1u; stack[top + cpos + 3] = c0; }
             if (leafpair) triq[ntri + lpos] = tt;
